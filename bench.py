@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the embedding-vs-gallery matching path (BASELINE.json metric: face queries/s at a
+1 M x 512 gallery, top-5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch F] ...
+
+One "step" = one batch of F query embeddings matched against the whole resident gallery
+(normalise -> scan -> top-k -> threshold).  Prints ONE JSON line (see DESIGN.md "Measurement").
+  value     device-timed (CUDA events) whole-job queries/s, inputs already in HBM
+  e2e       the same through the host-buffer C-ABI call (frg_match_host): pinned host queries in,
+            H2D + kernels + D2H of ids/scores/decisions inside the timed region
+  roofline  dominant kernel: algorithmic bytes (or flops) / its CUDA-event time vs the measured peak
+  cpu_baseline  the reference's per-face Python loop (oracle port) on the host cores, bounded sample
+--impl reference times only that CPU loop, on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "face queries/sec at 1Mx512 gallery top-5"
+UNIT = "queries/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+_G = None
+
+
+def _cpu_worker(args):
+    """The reference's per-face loop (oracle port of infrenceServer.py:530-552 / peopleCount.py:860-887)."""
+    q_block, threshold = args
+    from oracle import matcher_oracle as mo
+    ids, emb = _G
+    t0 = time.perf_counter()
+    out = []
+    for e in q_block:
+        q = mo.normalise(e)
+        bid, bs = mo.scan_best(q, emb)
+        out.append((bid, float(bs), bool(bid and bs >= threshold)))
+    return out, time.perf_counter() - t0
+
+
+def _gen_rows(args):
+    a, b, dim, seed = args
+    from oracle import synth
+    return a, synth.gallery(b - a, dim, seed, row0=a)
+
+
+def cpu_gallery(n, dim, seed, procs):
+    """frg-synth-v1 gallery on the host (bit-identical to the device generator), generated in parallel."""
+    from multiprocessing import shared_memory
+    out = np.empty((n, dim), np.float32)
+    step = max(1, (n + procs * 4 - 1) // (procs * 4))
+    jobs = [(a, min(n, a + step), dim, seed) for a in range(0, n, step)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        for a, rows in pool.imap_unordered(_gen_rows, jobs):
+            out[a:a + len(rows)] = rows
+    return out
+
+
+def run_cpu_loop(G, Q, threshold, procs, steps, warmup):
+    """Process-per-camera model of the reference (infrenceServer.py:640-646): `procs` workers, each
+    matching its share of every batch with the verbatim per-face loop.  Returns (q/s, per-step s, results)."""
+    global _G
+    ids = ["%024x" % i for i in range(len(G))]
+    _G = (ids, dict(zip(ids, G)))            # the reference's Dict[str, np.ndarray]; forked, not copied
+    times, results = [], None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        for it in range(warmup + steps):
+            blocks = [b for b in np.array_split(Q, procs) if len(b)]
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(b, threshold) for b in blocks])
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+                results = [r for part, _ in res for r in part]
+    _G = None
+    per_step = float(np.mean(times))
+    return len(Q) / per_step, per_step, results
+
+
+# ------------------------------------------------------------------------------------ arms
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU matcher (oracle port; the reference itself is a Python
+    script that cannot travel to the GPU box) on all host cores, on the same workload."""
+    if rank != 0:
+        return
+    procs = args.cpu_procs or (os.cpu_count() or 1)
+    n, dim = args.rows, args.dim
+    t0 = time.perf_counter()
+    G = cpu_gallery(n, dim, args.seed, procs)
+    from oracle import synth
+    q_per_step = args.cpu_queries or procs            # one query per worker per step: ~n * 1 us each
+    Q, _ = synth.queries(q_per_step, n, dim)
+    gen_s = time.perf_counter() - t0
+    qps, per_step, _ = run_cpu_loop(G, Q, 0.45, procs, args.steps, args.warmup)
+    sample = "%d queries/step (1 per worker) x %d rows, top-1 + threshold (the reference has no top-k)" % (q_per_step, n)
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, q_per_step),
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "setup_s": gen_s}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": "configs[1]: 512-d cosine, 1M-template gallery, top-5, single B200",
+            "gallery_rows": args.rows, "dim": args.dim, "batch": batch, "k": args.k, "threshold": 0.45,
+            "variant": args.variant,
+            "l2_policy": "inputs larger than L2 (gallery %.2f GB fp32 + %.2f GB bf16 plane vs 126 MB L2)" % (
+                args.rows * args.dim * 4 / 1e9, args.rows * args.dim * 2 / 1e9)}
+
+
+def ours_arm(args, rank, world):
+    import torch
+    import facerecognition_infrenceengine_b200 as frg
+    from facerecognition_infrenceengine_b200 import _native as N
+    from oracle import matcher_oracle as mo
+    from oracle import synth
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    n, dim, F, k = args.rows, args.dim, args.batch, args.k
+
+    store = frg.GalleryStore(dim=dim, capacity=n, device=local)
+    store.fill_synthetic(n, 0, args.seed)
+    torch.cuda.synchronize()
+    matcher = frg.Matcher(store)
+
+    # a ring of distinct query batches (50 % genuine / 50 % impostor)
+    nb = 4
+    Qh = [synth.queries(F, n, dim, q0=i * F)[0] for i in range(nb)]
+    Qd = [torch.from_numpy(q).to(dev) for q in Qh]
+    outs = [(torch.empty((F, k), dtype=torch.int64, device=dev), torch.empty((F, k), dtype=torch.float32, device=dev),
+             torch.empty((F,), dtype=torch.uint8, device=dev)) for _ in range(nb)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        matcher.match_device(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    launches_per_step = N.last_launch_count()
+    variant = N.last_variant()
+
+    # ---- device-timed region
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    N.profile_enable(True)
+    N.profile_collect()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    dom_ms, dom_launches = N.profile_collect()
+    N.profile_enable(False)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = F * world / (ms_per_step * 1e-3)      # queries are sharded across ranks, galleries replicated
+
+    # ---- parity spot-check of what was just timed (never inside the timed region)
+    parity = None
+    if rank == 0 and not args.no_check:
+        nchk = min(F, 32)
+        G, _ = store.read_rows()
+        ref_rows, ref_scores, ref_acc = mo.match_topk(Qh[0][:nchk], G, k + 1, 0.45)
+        got_r, got_s, got_a = (x.cpu().numpy() for x in outs[(args.steps - 1) % nb]) if (args.steps - 1) % nb == 0 else (None,) * 3
+        step(0)
+        torch.cuda.synchronize()
+        got_r, got_s, got_a = (x.cpu().numpy() for x in outs[0])
+        ids_ok = bool(mo.ids_match_with_gap(ref_rows, ref_scores, got_r[:nchk], 1e-4).all())
+        parity = {"checked_queries": nchk, "ids_ok": ids_ok,
+                  "max_abs_dscore": float(np.abs(got_s[:nchk] - ref_scores[:, :k]).max()),
+                  "accept_ok": bool((got_a[:nchk].astype(bool) == ref_acc).all())}
+        del G
+
+    # ---- end to end through the host-buffer ABI call
+    Qp = [torch.from_numpy(q).pin_memory() for q in Qh]
+    res = frg.MatchResult(np.empty((F, k), np.int64), np.empty((F, k), np.float32), np.zeros(F, np.uint8))
+    rows_p = torch.empty((F, k), dtype=torch.int64).pin_memory()
+    sc_p = torch.empty((F, k), dtype=torch.float32).pin_memory()
+    ac_p = torch.empty((F,), dtype=torch.uint8).pin_memory()
+    res = frg.MatchResult(rows_p.numpy(), sc_p.numpy(), ac_p.numpy())
+    for i in range(max(3, args.warmup)):
+        matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
+    e2e_steps = args.steps
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": F * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
+           "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / e2e_steps * 1e3,
+           "api": "frg_match_host via Matcher.match (pinned host buffers)"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel
+    dom_launch_ms = dom_ms / max(dom_launches, 1)
+    if variant in ("scan_f32",):
+        bytes_per_launch = n * dim * 4
+        achieved = bytes_per_launch / (dom_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "scan_f32_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": dom_launch_ms,
+                "launches_per_step": dom_launches / args.steps, "peak_source": peaks["source"]}
+    else:
+        roof = tc_roofline(args, variant, n, dim, F, dom_launch_ms, dom_launches, peaks)
+    roof["kernel_share_of_step"] = dom_ms / total_ms
+
+    # ---- CPU baseline (bounded sample of the same workload, on this box's host cores)
+    cpu = None
+    if not args.no_cpu:
+        procs = args.cpu_procs or (os.cpu_count() or 1)
+        G, _ = store.read_rows()                        # bit-identical to the CPU generator (tested)
+        q_cpu = args.cpu_queries or procs
+        qps, per_step, results = run_cpu_loop(G, Qh[0][:q_cpu], 0.45, procs, 1, 0)
+        # the same queries through the GPU: identical ids and decisions
+        r = matcher.match(Qh[0][:q_cpu], 1, 0.45, variant=args.variant)
+        same = all((res_[0] == gid[0]) and (res_[2] == bool(a)) for res_, gid, a in zip(results, r.ids, r.accept))
+        cpu = {"value": qps, "unit": UNIT, "cores": procs, "kind": "port",
+               "sample": "%d queries (1 per worker process) x %d rows, top-1 + threshold 0.45, "
+                         "per-face Python loop of peopleCount.py:860-887" % (q_cpu, n),
+               "seconds": per_step, "gpu_agrees": bool(same)}
+        del G
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
+            "data": "synthetic", "config": workload_config(args, F), "variant": variant,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "parity": parity, "peaks": peaks}
+    print(json.dumps(line), flush=True)
+
+
+def tc_roofline(args, variant, n, dim, F, launch_ms, launches, peaks):
+    flops = 2.0 * F * n * dim
+    bytes_ = n * dim * 2
+    t_hbm = bytes_ / (peaks["hbm_gbs"] * 1e9)
+    t_tc = flops / (peaks["bf16_tflops"] * 1e12)
+    if t_tc >= t_hbm:
+        ach = flops / (launch_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "tc_match_kernel", "achieved": ach, "peak": peaks["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                "algorithmic_flops_per_launch": flops, "launch_ms": launch_ms, "peak_source": peaks["source"]}
+    ach = bytes_ / (launch_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "tc_match_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": bytes_,
+            "launch_ms": launch_ms, "peak_source": peaks["source"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--variant", default="auto")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    ap.add_argument("--cpu-queries", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours_arm(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,509 @@
+// C ABI of libfrg.so (include/frg.h): store life-cycle, ingest, match dispatch, merge.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "frg_internal.cuh"
+
+namespace frg {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+static thread_local const char* g_variant = "none";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", int(e), cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? FRG_ERR_NOMEM : FRG_ERR_CUDA;
+}
+
+void note_launch(const char* variant) {
+  ++g_launches;
+  if (variant) g_variant = variant;
+}
+void reset_launches() { g_launches = 0; g_variant = "none"; }
+
+struct ProfileSpan { cudaEvent_t a, b; int launches; };
+static thread_local bool g_profile = false;
+static thread_local std::vector<ProfileSpan> g_spans;
+static thread_local cudaEvent_t g_open = nullptr;
+
+void profile_begin(cudaStream_t st) {
+  if (!g_profile) return;
+  if (cudaEventCreate(&g_open) != cudaSuccess) { g_open = nullptr; return; }
+  cudaEventRecord(g_open, st);
+}
+
+void profile_end(cudaStream_t st, int launches) {
+  if (!g_profile || !g_open) return;
+  ProfileSpan sp{g_open, nullptr, launches};
+  g_open = nullptr;
+  if (cudaEventCreate(&sp.b) != cudaSuccess) { cudaEventDestroy(sp.a); return; }
+  cudaEventRecord(sp.b, st);
+  g_spans.push_back(sp);
+}
+
+int device_info(int device, DeviceInfo* out) {
+  static std::mutex mu;
+  static std::vector<DeviceInfo> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0) { set_error("negative device"); return FRG_ERR_INVALID; }
+  if (int(cache.size()) <= device) cache.resize(device + 1);
+  DeviceInfo& d = cache[device];
+  if (d.sm_count == 0) {
+    cudaDeviceProp p;
+    FRG_CUDA(cudaGetDeviceProperties(&p, device));
+    d.sm_count = p.multiProcessorCount;
+    d.cc_major = p.major;
+    d.cc_minor = p.minor;
+    d.smem_optin = p.sharedMemPerBlockOptin;
+  }
+  *out = d;
+  return FRG_OK;
+}
+
+int store_begin_write(frg_store* s, cudaStream_t stream) {
+  for (cudaStream_t r : s->readers) {
+    if (r == stream) continue;
+    cudaEvent_t ev;
+    FRG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FRG_CUDA(cudaEventRecord(ev, r));
+    FRG_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+    FRG_CUDA(cudaEventDestroy(ev));   // destruction is deferred until the event completes
+  }
+  s->readers.clear();
+  if (s->has_write) FRG_CUDA(cudaStreamWaitEvent(stream, s->last_write, 0));
+  return FRG_OK;
+}
+
+int store_end_write(frg_store* s, cudaStream_t stream) {
+  FRG_CUDA(cudaEventRecord(s->last_write, stream));
+  s->has_write = true;
+  s->version++;
+  return FRG_OK;
+}
+
+int store_begin_read(frg_store* s, cudaStream_t stream) {
+  if (s->has_write) FRG_CUDA(cudaStreamWaitEvent(stream, s->last_write, 0));
+  bool seen = false;
+  for (cudaStream_t r : s->readers) seen |= (r == stream);
+  if (!seen) s->readers.push_back(stream);
+  return FRG_OK;
+}
+
+static size_t row_bytes(const frg_store* s) {
+  return size_t(s->dim) * (sizeof(float) + ((s->flags & FRG_STORE_BF16_PLANE) ? sizeof(__nv_bfloat16) : 0)) +
+         sizeof(int32_t);
+}
+
+static int alloc_arrays(frg_store* s, int64_t cap, float** m, __nv_bfloat16** p, int32_t** t) {
+  *m = nullptr; *p = nullptr; *t = nullptr;
+  const int64_t c = cap > 0 ? cap : 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(m), size_t(c) * s->dim * sizeof(float));
+  if (e == cudaSuccess && (s->flags & FRG_STORE_BF16_PLANE))
+    e = cudaMalloc(reinterpret_cast<void**>(p), size_t(c) * s->dim * sizeof(__nv_bfloat16));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(t), size_t(c) * sizeof(int32_t));
+  if (e != cudaSuccess) {
+    cudaFree(*m); cudaFree(*p); cudaFree(*t);
+    *m = nullptr; *p = nullptr; *t = nullptr;
+    return cuda_fail(e, "cudaMalloc(store arrays)", __FILE__, __LINE__);
+  }
+  return FRG_OK;
+}
+
+// grow to at least `cap` rows; s->mu held.  Synchronous (rare, off the hot path).
+static int grow_locked(frg_store* s, int64_t cap) {
+  if (cap <= s->capacity) return FRG_OK;
+  FRG_CUDA(cudaDeviceSynchronize());
+  float* m; __nv_bfloat16* p; int32_t* t;
+  FRG_CHECK(alloc_arrays(s, cap, &m, &p, &t));
+  if (s->rows > 0) {
+    FRG_CUDA(cudaMemcpy(m, s->master, size_t(s->rows) * s->dim * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (p) FRG_CUDA(cudaMemcpy(p, s->plane, size_t(s->rows) * s->dim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+    FRG_CUDA(cudaMemcpy(t, s->tags, size_t(s->rows) * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+  }
+  cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
+  s->master = m; s->plane = p; s->tags = t;
+  s->capacity = cap;
+  s->readers.clear();
+  s->has_write = false;
+  return FRG_OK;
+}
+
+static int64_t next_capacity(int64_t have, int64_t need) {
+  int64_t c = have > 0 ? have : 1024;
+  while (c < need) c += c / 2 + 1024;
+  return c;
+}
+
+// exact live-row recount (synchronous; s->mu held): mutators only mark the count stale
+static int count_live(frg_store* s) {
+  FRG_CUDA(cudaDeviceSynchronize());
+  std::vector<int32_t> t(static_cast<size_t>(s->rows));
+  if (s->rows > 0)
+    FRG_CUDA(cudaMemcpy(t.data(), s->tags, size_t(s->rows) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  int64_t live = 0;
+  for (int32_t v : t) live += v >= 0;
+  s->live = live;
+  return FRG_OK;
+}
+
+}  // namespace frg
+
+using namespace frg;
+
+extern "C" {
+
+int frg_abi_version(void) { return FRG_ABI_VERSION; }
+const char* frg_last_error(void) { return g_err; }
+int frg_last_launch_count(void) { return g_launches; }
+const char* frg_last_variant(void) { return g_variant; }
+
+int frg_profile_enable(int32_t on) {
+  g_profile = on != 0;
+  return FRG_OK;
+}
+
+int frg_profile_collect(float* dominant_ms, int32_t* dominant_launches) {
+  float total = 0.f;
+  int launches = 0;
+  int rc = FRG_OK;
+  for (auto& sp : g_spans) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (e != cudaSuccess && rc == FRG_OK) rc = cuda_fail(e, "profile events", __FILE__, __LINE__);
+    total += ms;
+    launches += sp.launches;
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  g_spans.clear();
+  if (dominant_ms) *dominant_ms = total;
+  if (dominant_launches) *dominant_launches = launches;
+  return rc;
+}
+
+int frg_device_count(int32_t* count) {
+  if (!count) { set_error("count is NULL"); return FRG_ERR_INVALID; }
+  int n = 0;
+  *count = 0;
+  FRG_CUDA(cudaGetDeviceCount(&n));
+  *count = n;
+  return FRG_OK;
+}
+
+int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t flags, frg_store** out) {
+  if (!out) { set_error("out is NULL"); return FRG_ERR_INVALID; }
+  *out = nullptr;
+  if (dim <= 0 || dim % 8 != 0) { set_error("dim %d must be a positive multiple of 8", dim); return FRG_ERR_INVALID; }
+  if (capacity < 0) { set_error("negative capacity"); return FRG_ERR_INVALID; }
+  DeviceInfo di;
+  FRG_CHECK(device_info(device, &di));
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
+  frg_store* s = new (std::nothrow) frg_store();
+  if (!s) { set_error("out of host memory"); return FRG_ERR_NOMEM; }
+  s->device = device; s->dim = dim; s->flags = flags;
+  int rc = alloc_arrays(s, capacity, &s->master, &s->plane, &s->tags);
+  if (rc != FRG_OK) { delete s; return rc; }
+  s->capacity = capacity > 0 ? capacity : 1;
+  cudaError_t e = cudaEventCreateWithFlags(&s->last_write, cudaEventDisableTiming);
+  if (e != cudaSuccess) { frg_store_destroy(s); return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); }
+  // keep stream-ordered workspaces cached instead of returning them to the OS after every match
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  *out = s;
+  return FRG_OK;
+}
+
+int frg_store_destroy(frg_store* s) {
+  if (!s) return FRG_OK;
+  {
+    DeviceGuard g(s->device);
+    cudaDeviceSynchronize();
+    cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
+    if (s->last_write) cudaEventDestroy(s->last_write);
+    ::operator delete(s->tmap_plane);
+  }
+  delete s;
+  return FRG_OK;
+}
+
+int frg_store_reserve(frg_store* s, int64_t capacity) {
+  if (!s) { set_error("store is NULL"); return FRG_ERR_INVALID; }
+  DeviceGuard g(s->device);
+  std::lock_guard<std::mutex> lk(s->mu);
+  return grow_locked(s, capacity);
+}
+
+int frg_store_stats(frg_store* s, frg_store_stats_t* out) {
+  if (!s || !out) { set_error("NULL argument"); return FRG_ERR_INVALID; }
+  DeviceGuard g(s->device);
+  std::lock_guard<std::mutex> lk(s->mu);
+  memset(out, 0, sizeof(*out));
+  if (s->live < 0) FRG_CHECK(count_live(s));   // lazily recounted after device-side mutations
+  out->rows = s->rows; out->live = s->live; out->capacity = s->capacity; out->version = s->version;
+  out->bytes = int64_t(row_bytes(s)) * s->capacity;
+  out->dim = s->dim; out->device = s->device; out->flags = s->flags;
+  return FRG_OK;
+}
+
+int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
+                     int64_t n, uint32_t flags, void* stream) {
+  if (!s || (n > 0 && !vecs) || n < 0) { set_error("upsert: bad argument"); return FRG_ERR_INVALID; }
+  if (n == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (!rows && s->rows + n > s->capacity) FRG_CHECK(grow_locked(s, next_capacity(s->capacity, s->rows + n)));
+  FRG_CHECK(store_begin_write(s, st));
+  const bool normalise = !(flags & FRG_ROWS_PRENORMALISED) && !(s->flags & FRG_STORE_RAW);
+  FRG_CHECK(launch_ingest(vecs, rows, tags, n, s->rows, s->dim, normalise, s->master, s->plane, s->tags, st));
+  if (!rows) s->rows += n;
+  s->live = -1;
+  return store_end_write(s, st);
+}
+
+
+
+int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
+                          int64_t n, uint32_t flags) {
+  if (!s || (n > 0 && !vecs) || n < 0) { set_error("upsert_host: bad argument"); return FRG_ERR_INVALID; }
+  if (n == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (rows)
+      for (int64_t i = 0; i < n; ++i)
+        if (rows[i] < 0 || rows[i] >= s->rows) {
+          set_error("upsert_host: row %lld out of range [0, %lld)", (long long)rows[i], (long long)s->rows);
+          return FRG_ERR_STATE;
+        }
+  }
+  float* dv = nullptr; int64_t* dr = nullptr; int32_t* dt = nullptr;
+  int rc = FRG_OK;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() { cudaFree(dv); cudaFree(dr); cudaFree(dt); };
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dv), size_t(n) * s->dim * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(dv, vecs, size_t(n) * s->dim * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && rows) {
+    e = cudaMalloc(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemcpy(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess && tags) {
+    e = cudaMalloc(reinterpret_cast<void**>(&dt), size_t(n) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(dt, tags, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upsert_host staging", __FILE__, __LINE__); }
+  rc = frg_store_upsert(s, dr, dv, dt, n, flags, st);
+  if (rc == FRG_OK) {
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+  }
+  cleanup();
+  return rc;
+}
+
+int frg_store_remove(frg_store* s, const int64_t* rows, int64_t n, void* stream) {
+  if (!s || (n > 0 && !rows) || n < 0) { set_error("remove: bad argument"); return FRG_ERR_INVALID; }
+  if (n == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(s->mu);
+  FRG_CHECK(store_begin_write(s, st));
+  FRG_CHECK(launch_tombstone(rows, n, s->rows, s->tags, st));
+  s->live = -1;
+  return store_end_write(s, st);
+}
+
+int frg_store_remove_host(frg_store* s, const int64_t* rows, int64_t n) {
+  if (!s || (n > 0 && !rows) || n < 0) { set_error("remove_host: bad argument"); return FRG_ERR_INVALID; }
+  if (n == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  int64_t* dr = nullptr;
+  FRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(int64_t)));
+  cudaError_t e = cudaMemcpy(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? frg_store_remove(s, dr, n, nullptr) : cuda_fail(e, "cudaMemcpy", __FILE__, __LINE__);
+  if (rc == FRG_OK) {
+    e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+  }
+  cudaFree(dr);
+  return rc;
+}
+
+int frg_store_compact(frg_store* s, int64_t* old_to_new) {
+  if (!s) { set_error("store is NULL"); return FRG_ERR_INVALID; }
+  DeviceGuard g(s->device);
+  std::lock_guard<std::mutex> lk(s->mu);
+  FRG_CUDA(cudaDeviceSynchronize());
+  const int64_t n = s->rows;
+  std::vector<int32_t> t(static_cast<size_t>(n));
+  if (n > 0) FRG_CUDA(cudaMemcpy(t.data(), s->tags, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::vector<int64_t> src;
+  src.reserve(size_t(n));
+  for (int64_t r = 0; r < n; ++r) {
+    if (t[size_t(r)] >= 0) {
+      if (old_to_new) old_to_new[r] = int64_t(src.size());
+      src.push_back(r);
+    } else if (old_to_new) {
+      old_to_new[r] = -1;
+    }
+  }
+  const int64_t m = int64_t(src.size());
+  if (m == n) { s->live = n; return FRG_OK; }
+  float* nm; __nv_bfloat16* np; int32_t* nt;
+  FRG_CHECK(alloc_arrays(s, s->capacity, &nm, &np, &nt));
+  int64_t* dsrc = nullptr;
+  int rc = FRG_OK;
+  if (m > 0) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dsrc), size_t(m) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemcpy(dsrc, src.data(), size_t(m) * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "compact staging", __FILE__, __LINE__);
+    if (rc == FRG_OK) rc = launch_gather_rows(dsrc, m, s->dim, s->master, s->plane, s->tags, nm, np, nt, nullptr);
+    if (rc == FRG_OK) {
+      e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
+    }
+    cudaFree(dsrc);
+  }
+  if (rc != FRG_OK) { cudaFree(nm); cudaFree(np); cudaFree(nt); return rc; }
+  cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
+  s->master = nm; s->plane = np; s->tags = nt;
+  s->rows = m; s->live = m; s->version++;
+  s->readers.clear(); s->has_write = false;
+  return FRG_OK;
+}
+
+int frg_store_read_host(frg_store* s, int64_t row0, int64_t n, float* vecs, int32_t* tags) {
+  if (!s || n < 0 || row0 < 0) { set_error("read_host: bad argument"); return FRG_ERR_INVALID; }
+  DeviceGuard g(s->device);
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (row0 + n > s->rows) { set_error("read_host: rows [%lld, %lld) beyond %lld", (long long)row0, (long long)(row0 + n), (long long)s->rows); return FRG_ERR_STATE; }
+  FRG_CUDA(cudaDeviceSynchronize());
+  if (n == 0) return FRG_OK;
+  if (vecs) FRG_CUDA(cudaMemcpy(vecs, s->master + row0 * s->dim, size_t(n) * s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+  if (tags) FRG_CUDA(cudaMemcpy(tags, s->tags + row0, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return FRG_OK;
+}
+
+int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint64_t seed, int32_t tag,
+                             void* stream) {
+  if (!s || n < 0) { set_error("fill_synthetic: bad argument"); return FRG_ERR_INVALID; }
+  if (s->dim > 1024) { set_error("fill_synthetic: dim > 1024 not built"); return FRG_ERR_UNSUPPORTED; }
+  if (n == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->rows + n > s->capacity) FRG_CHECK(grow_locked(s, s->rows + n));
+  FRG_CHECK(store_begin_write(s, st));
+  FRG_CHECK(launch_synth(n, s->rows, global_row0, seed, tag, s->dim, s->master, s->plane, s->tags, st));
+  s->rows += n;
+  if (s->live >= 0 && tag >= 0) s->live += n;
+  return store_end_write(s, st);
+}
+
+// --------------------------------------------------------------------------------------------- match
+static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq) {
+  (void)s; (void)nq;
+  if (p->variant != FRG_VARIANT_AUTO) return p->variant;
+  return FRG_VARIANT_SCAN_F32;
+}
+
+int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+              int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
+  reset_launches();
+  if (!s || !p || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("match: bad argument"); return FRG_ERR_INVALID; }
+  if (k < 1 || k > FRG_MAX_K) { set_error("match: k=%d out of range 1..%d", k, FRG_MAX_K); return FRG_ERR_INVALID; }
+  if (p->metric != FRG_METRIC_COSINE && p->metric != FRG_METRIC_EUCLIDEAN) { set_error("match: unknown metric %d", p->metric); return FRG_ERR_INVALID; }
+  if (nq == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  if (!g.ok) { set_error("cannot select device %d", s->device); return FRG_ERR_CUDA; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceInfo di;
+  FRG_CHECK(device_info(s->device, &di));
+
+  std::lock_guard<std::mutex> lk(s->mu);   // enqueue under the lock: the snapshot a match sees is the
+                                           // store as of this call (peopleCount.py:816-819 semantics)
+  FRG_CHECK(store_begin_read(s, st));
+  const int variant = pick_variant(s, p, nq);
+  if (variant != FRG_VARIANT_SCAN_F32) {
+    set_error("match: variant %d not built in this library", variant);
+    return FRG_ERR_UNSUPPORTED;
+  }
+
+  ScanArgs a;
+  a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
+  a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = di.sm_count;
+  size_t part_bytes = 0;
+  FRG_CHECK(scan_f32_workspace_bytes(a, &part_bytes));
+  const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
+  unsigned char* ws = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + part_bytes, st));
+  float* qn = reinterpret_cast<float*>(ws);
+  a.qn = qn;
+  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE, qn, nullptr, st);
+  if (rc == FRG_OK)
+    rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
+  note_launch("scan_f32");
+  --g_launches;  // note_launch above only records the variant name
+  cudaError_t e = cudaFreeAsync(ws, st);
+  if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
+  return rc;
+}
+
+int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+                   int64_t* out_rows, float* out_scores, uint8_t* out_accept) {
+  if (!s || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("match_host: bad argument"); return FRG_ERR_INVALID; }
+  if (k < 1 || k > FRG_MAX_K) { set_error("match: k=%d out of range 1..%d", k, FRG_MAX_K); return FRG_ERR_INVALID; }
+  if (nq == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t st = cudaStreamPerThread;
+  const size_t qb = size_t(nq) * s->dim * sizeof(float);
+  const size_t rb = size_t(nq) * k * sizeof(int64_t), sb = size_t(nq) * k * sizeof(float), ab = size_t(nq);
+  const size_t o_r = (qb + 255) & ~size_t(255), o_s = (o_r + rb + 255) & ~size_t(255), o_a = (o_s + sb + 255) & ~size_t(255);
+  unsigned char* d = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d), o_a + ab, st));
+  int rc = FRG_OK;
+  cudaError_t e = cudaMemcpyAsync(d, q, qb, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) rc = cuda_fail(e, "H2D queries", __FILE__, __LINE__);
+  if (rc == FRG_OK)
+    rc = frg_match(s, reinterpret_cast<float*>(d), nq, k, p, reinterpret_cast<int64_t*>(d + o_r),
+                   reinterpret_cast<float*>(d + o_s), d + o_a, st);
+  if (rc == FRG_OK) {
+    e = cudaMemcpyAsync(out_rows, d + o_r, rb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d + o_s, sb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_accept) e = cudaMemcpyAsync(out_accept, d + o_a, ab, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "D2H results", __FILE__, __LINE__);
+  }
+  cudaFreeAsync(d, st);
+  return rc;
+}
+
+int frg_merge_topk(int32_t device, const float* scores, const int64_t* rows, int32_t parts,
+                   int32_t nq, int32_t k, int32_t metric, float threshold,
+                   int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
+  reset_launches();
+  if (parts < 0 || nq < 0 || (nq > 0 && (!out_rows || !out_scores)) || (parts > 0 && nq > 0 && (!scores || !rows))) {
+    set_error("merge_topk: bad argument");
+    return FRG_ERR_INVALID;
+  }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
+  return launch_merge_i64(scores, rows, parts, nq, k, k, metric, threshold, 0, false, out_rows, out_scores,
+                          out_accept, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Internal declarations shared by the translation units of libfrg.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "frg.h"
+
+namespace frg {
+
+constexpr int kWarp = 32;
+constexpr float kNoScore = -1.0f;   // the scan's initial best_score (infrenceServer.py:536)
+constexpr int32_t kNoRow = -1;
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FRG_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return ::frg::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define FRG_CHECK(expr)                     \
+  do {                                      \
+    int rc__ = (expr);                      \
+    if (rc__ != FRG_OK) return rc__;        \
+  } while (0)
+
+void note_launch(const char* variant_or_null);   // launch accounting for frg_last_launch_count()
+void reset_launches();
+// bench-only timing of the dominant kernel(s): bracket them with profile_begin/profile_end
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st, int launches);
+
+struct DeviceInfo {
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t smem_optin = 0;
+};
+int device_info(int device, DeviceInfo* out);
+
+// RAII device switch
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace frg
+
+// ---- the store ------------------------------------------------------------------------------
+struct frg_store {
+  int device = 0;
+  int dim = 0;
+  uint32_t flags = 0;
+  int64_t capacity = 0;
+  int64_t rows = 0;       // next append position
+  int64_t live = 0;       // maintained on the host from upsert/remove arguments when possible (-1 = unknown)
+  int64_t version = 0;
+  float* master = nullptr;            // [capacity][dim] fp32, unit rows
+  __nv_bfloat16* plane = nullptr;     // [capacity][dim] bf16 image (scan plane) or null
+  int32_t* tags = nullptr;            // [capacity]
+  std::mutex mu;                      // guards the fields above and the stream bookkeeping
+  cudaEvent_t last_write = nullptr;   // recorded after every mutation
+  bool has_write = false;
+  std::vector<cudaStream_t> readers;  // streams that matched since the last mutation
+  // tensor-map cache for the TC variants (rebuilt when the plane pointer / row count changes)
+  void* tmap_plane = nullptr;         // opaque CUtensorMap storage (128 B)
+  int64_t tmap_rows = -1;
+  const void* tmap_ptr = nullptr;
+};
+
+namespace frg {
+
+// order a mutation on `stream` after every match enqueued so far; call with s->mu held
+int store_begin_write(frg_store* s, cudaStream_t stream);
+int store_end_write(frg_store* s, cudaStream_t stream);
+// order a match on `stream` after the last mutation; call with s->mu held
+int store_begin_read(frg_store* s, cudaStream_t stream);
+
+// ---- kernels' host launchers (defined in the .cu named in the comment) ----------------------
+// queries.cu: qn[f] = q[f] / ||q[f]|| (fp32), optional bf16 image
+int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
+                             __nv_bfloat16* qn_bf16, cudaStream_t st);
+
+// scan_f32.cu: exact scan; writes nq x k best (score desc, row asc) into rows32/scores
+struct ScanArgs {
+  const float* master; const int32_t* tags; int64_t rows; int dim;
+  const float* qn; int nq; int k; int metric; int32_t tenant;
+  int sm_count;
+};
+int scan_f32_workspace_bytes(const ScanArgs& a, size_t* bytes);
+int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, float threshold,
+                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
+
+// merge.cu: generic k-way merge of sorted partial lists
+int launch_merge_i64(const float* scores, const int64_t* rows, int parts, int nq, int k_in, int k_out,
+                     int metric, float threshold, int64_t row_offset, bool finalize_euclid,
+                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
+int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq, int k_in, int k_out,
+                     int metric, float threshold, int64_t row_offset, bool finalize_euclid,
+                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
+
+// store_kernels.cu
+int launch_ingest(const float* vecs, const int64_t* rows, const int32_t* tags, int64_t n, int64_t append_at,
+                  int dim, bool normalise, float* master, __nv_bfloat16* plane, int32_t* tag_out,
+                  cudaStream_t st);
+int launch_tombstone(const int64_t* rows, int64_t n, int64_t limit, int32_t* tags, cudaStream_t st);
+int launch_synth(int64_t n, int64_t append_at, int64_t global_row0, uint64_t seed, int32_t tag, int dim,
+                 float* master, __nv_bfloat16* plane, int32_t* tag_out, cudaStream_t st);
+int launch_gather_rows(const int64_t* src_rows, int64_t n, int dim, const float* master_in,
+                       const __nv_bfloat16* plane_in, const int32_t* tags_in, float* master_out,
+                       __nv_bfloat16* plane_out, int32_t* tags_out, cudaStream_t st);
+
+}  // namespace frg

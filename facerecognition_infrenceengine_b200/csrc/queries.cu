@@ -1,0 +1,57 @@
+// Query preparation: the reference re-normalises every face embedding before the scan
+// (`face.normed_embedding / np.linalg.norm(face.normed_embedding)`, infrenceServer.py:532,
+// peopleCount.py:863).  One warp per query; writes the fp32 unit query and, for the tensor-core
+// variants, its bf16 image.
+#include "frg_internal.cuh"
+
+namespace frg {
+
+__global__ void __launch_bounds__(128)
+normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int normalise,
+                         float* __restrict__ qn, __nv_bfloat16* __restrict__ qb) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nq) return;
+  const float4* src = reinterpret_cast<const float4*>(q + size_t(w) * dim);
+  const int nvec = dim >> 2;
+  float norm = 1.0f;
+  if (normalise) {
+    float ss = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      float4 x = __ldg(src + v);
+      ss = fmaf(x.x, x.x, ss); ss = fmaf(x.y, x.y, ss); ss = fmaf(x.z, x.z, ss); ss = fmaf(x.w, x.w, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    norm = __fsqrt_rn(ss);
+  }
+  for (int v = lane; v < nvec; v += 32) {
+    float4 x = __ldg(src + v);
+    if (normalise) {
+      x.x = __fdiv_rn(x.x, norm); x.y = __fdiv_rn(x.y, norm);
+      x.z = __fdiv_rn(x.z, norm); x.w = __fdiv_rn(x.w, norm);
+    }
+    reinterpret_cast<float4*>(qn + size_t(w) * dim)[v] = x;
+    if (qb) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(x.z, x.w);
+      uint2 p;
+      p.x = *reinterpret_cast<uint32_t*>(&lo);
+      p.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(qb + size_t(w) * dim)[v] = p;
+    }
+  }
+}
+
+int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
+                             __nv_bfloat16* qn_bf16, cudaStream_t st) {
+  if (nq <= 0) return FRG_OK;
+  const int warps_per_block = 4;
+  normalise_queries_kernel<<<(nq + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(
+      q, nq, dim, normalise ? 1 : 0, qn, qn_bf16);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+}  // namespace frg

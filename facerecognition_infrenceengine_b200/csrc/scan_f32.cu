@@ -1,0 +1,283 @@
+// Exact fp32 streaming scan (FRG_VARIANT_SCAN_F32): the reference's inner loop
+//   for person_id, g in embeddings.items(): s = np.dot(q, g); if s > best: ...
+// (infrenceServer.py:538-542, peopleCount.py:869-873) for up to QB queries per pass, on CUDA cores.
+//
+// HBM-bound by construction: every gallery row (dim * 4 B) is read exactly once per pass with
+// 16-byte streaming loads, a warp owning whole rows (512 B per load instruction, fully coalesced);
+// the QB unit queries live in registers (lane L holds elements j*128 + 4L .. +3 of each), the QB
+// row-dots are reduced with a halving butterfly (QB + log2(32/QB) shuffles instead of 5*QB) and the
+// running top-k of each (warp, query) sits in shared memory, touched only when a score beats the
+// current k-th best.  Per-CTA lists go to a small partial buffer folded by merge.cu, so no score
+// matrix ever reaches HBM.
+//
+// Algorithmic bytes per launch = rows * dim * 4; grid = 2 CTAs x SM count.
+#include "frg_internal.cuh"
+
+namespace frg {
+
+constexpr int kScanWarps = 8;
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// Reduce QB per-lane partial dots across the warp.  After the call, the returned value on lane L is
+// the full dot for query `lane_query<QB>(L)`, replicated on the 32/QB lanes that share it.
+template <int QB>
+__device__ __forceinline__ float butterfly(float (&acc)[QB], int lane) {
+  int width = 16;
+#pragma unroll
+  for (int n = QB; n > 1; n >>= 1) {
+    const bool upper = (lane & width) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = upper ? acc[i + n / 2] : acc[i];
+      const float send = upper ? acc[i] : acc[i + n / 2];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+    }
+    width >>= 1;
+  }
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1)
+    if (w <= width) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], w);
+  return acc[0];
+}
+
+template <int QB>
+__device__ __forceinline__ int lane_query(int lane) {
+  int q = 0, width = 16;
+#pragma unroll
+  for (int n = QB; n > 1; n >>= 1) {
+    if (lane & width) q += n / 2;
+    width >>= 1;
+  }
+  return q;
+}
+
+template <int QB>
+__device__ __forceinline__ bool lane_is_rep(int lane) {
+  // lowest lane of the group sharing a query: all non-query bits clear
+  int mask = 0, width = 16;
+#pragma unroll
+  for (int n = QB; n > 1; n >>= 1) { mask |= width; width >>= 1; }
+  return (lane & ~mask) == 0;
+}
+
+template <int NJ, int QB, int METRIC>
+__device__ __forceinline__ void row_dots(const float4 (&g)[NJ], const float4 (&q)[QB][NJ], float (&acc)[QB]) {
+#pragma unroll
+  for (int b = 0; b < QB; ++b) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (METRIC == FRG_METRIC_COSINE) {
+        a = fmaf(g[j].x, q[b][j].x, a); a = fmaf(g[j].y, q[b][j].y, a);
+        a = fmaf(g[j].z, q[b][j].z, a); a = fmaf(g[j].w, q[b][j].w, a);
+      } else {
+        float d;
+        d = g[j].x - q[b][j].x; a = fmaf(d, d, a);
+        d = g[j].y - q[b][j].y; a = fmaf(d, d, a);
+        d = g[j].z - q[b][j].z; a = fmaf(d, d, a);
+        d = g[j].w - q[b][j].w; a = fmaf(d, d, a);
+      }
+    }
+    acc[b] = a;
+  }
+}
+
+// Insert (s, row) into the descending list [sc, ix] of length K held in shared memory.  Rows reach a
+// warp in increasing order, so strict '>' keeps the earliest row on exact ties.
+__device__ __forceinline__ void list_insert(float* sc, int32_t* ix, int K, float s, int32_t row) {
+  int t = K - 1;
+  while (t > 0 && s > sc[t - 1]) { sc[t] = sc[t - 1]; ix[t] = ix[t - 1]; --t; }
+  sc[t] = s; ix[t] = row;
+}
+
+template <int NJ, int QB, int METRIC>
+__global__ void __launch_bounds__(kScanWarps * 32, 2)
+scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
+                const float* __restrict__ qn, int nq_total, int q0, int nq_pass, int K, int32_t tenant,
+                float* __restrict__ part_sc, int32_t* __restrict__ part_ix) {
+  constexpr int DIM = NJ * 128;
+  extern __shared__ unsigned char smem_raw[];
+  // [warp][query][K]
+  float* l_sc = reinterpret_cast<float*>(smem_raw);
+  int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float sentinel = METRIC == FRG_METRIC_COSINE ? kNoScore : -INFINITY;
+
+  for (int i = threadIdx.x; i < kScanWarps * QB * K; i += blockDim.x) { l_sc[i] = sentinel; l_ix[i] = 0x7fffffff; }
+
+  float4 q[QB][NJ];
+#pragma unroll
+  for (int b = 0; b < QB; ++b) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      q[b][j] = (b < nq_pass)
+                    ? __ldg(reinterpret_cast<const float4*>(qn + size_t(q0 + b) * DIM) + j * 32 + lane)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+
+  const int my_q = lane_query<QB>(lane);
+  const bool rep = lane_is_rep<QB>(lane);
+  float* my_sc = l_sc + (warp * QB + my_q) * K;
+  int32_t* my_ix = l_ix + (warp * QB + my_q) * K;
+  float kth = sentinel;
+
+  const int64_t gw = int64_t(blockIdx.x) * kScanWarps + warp;
+  const int64_t tw = int64_t(gridDim.x) * kScanWarps;
+
+  for (int64_t r0 = gw; r0 < rows; r0 += 2 * tw) {
+    const int64_t r1 = r0 + tw;
+    const bool has1 = r1 < rows;
+    float4 g0[NJ], g1[NJ];
+    const float4* p0 = reinterpret_cast<const float4*>(master + r0 * DIM) + lane;
+    const float4* p1 = reinterpret_cast<const float4*>(master + (has1 ? r1 : r0) * DIM) + lane;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) g0[j] = ldg_stream(p0 + j * 32);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) g1[j] = ldg_stream(p1 + j * 32);
+    const int32_t t0 = __ldg(tags + r0);
+    const int32_t t1 = has1 ? __ldg(tags + r1) : -1;
+
+    float a0[QB], a1[QB];
+    row_dots<NJ, QB, METRIC>(g0, q, a0);
+    row_dots<NJ, QB, METRIC>(g1, q, a1);
+    float s0 = butterfly<QB>(a0, lane);
+    float s1 = butterfly<QB>(a1, lane);
+    if (METRIC == FRG_METRIC_EUCLIDEAN) { s0 = -s0; s1 = -s1; }
+    // removed rows (tag -1) and other tenants never take part (infrenceServer.py:343-380)
+    const bool v0 = t0 >= 0 && (tenant < 0 || t0 == tenant);
+    const bool v1 = t1 >= 0 && (tenant < 0 || t1 == tenant);
+    const bool in0 = v0 && s0 > kth;          // false for NaN
+    if (__any_sync(0xffffffffu, in0)) {
+      if (in0 && rep) list_insert(my_sc, my_ix, K, s0, int32_t(r0));
+      __syncwarp();
+      kth = my_sc[K - 1];
+    }
+    const bool in1 = v1 && s1 > kth;
+    if (__any_sync(0xffffffffu, in1)) {
+      if (in1 && rep) list_insert(my_sc, my_ix, K, s1, int32_t(r1));
+      __syncwarp();
+      kth = my_sc[K - 1];
+    }
+  }
+  __syncthreads();
+
+  // fold the kScanWarps lists of each query: thread b < nq_pass walks the heads
+  if (threadIdx.x < nq_pass) {
+    const int b = threadIdx.x;
+    int head[kScanWarps];
+#pragma unroll
+    for (int w = 0; w < kScanWarps; ++w) head[w] = 0;
+    float* o_sc = part_sc + (size_t(blockIdx.x) * nq_total + q0 + b) * K;
+    int32_t* o_ix = part_ix + (size_t(blockIdx.x) * nq_total + q0 + b) * K;
+    for (int j = 0; j < K; ++j) {
+      float bs = sentinel; int32_t br = 0x7fffffff; int bw = -1;
+#pragma unroll
+      for (int w = 0; w < kScanWarps; ++w) {
+        if (head[w] < K) {
+          const float s = l_sc[(w * QB + b) * K + head[w]];
+          const int32_t r = l_ix[(w * QB + b) * K + head[w]];
+          if (s > bs || (s == bs && r < br)) { bs = s; br = r; bw = w; }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < kScanWarps; ++w) if (w == bw) head[w]++;
+      o_sc[j] = bs;
+      o_ix[j] = (br == 0x7fffffff) ? -1 : br;
+    }
+  }
+}
+
+static int scan_grid(const ScanArgs& a) {
+  int64_t want = (a.rows + kScanWarps * 2 - 1) / (kScanWarps * 2);
+  int64_t cap = int64_t(a.sm_count) * 2;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return int(want);
+}
+
+static int scan_qb(int dim, int nq) {
+  const int nj = dim / 128;
+  int qb = 16 / nj;                 // register budget: QB * NJ float4 <= 16 (64 registers of queries)
+  if (qb > 4) qb = 4;
+  if (qb < 1) qb = 1;
+  while (qb > 1 && qb / 2 >= nq) qb /= 2;
+  return qb;
+}
+
+int scan_f32_workspace_bytes(const ScanArgs& a, size_t* bytes) {
+  const int grid = scan_grid(a);
+  *bytes = size_t(grid) * size_t(a.nq > 0 ? a.nq : 1) * a.k * (sizeof(float) + sizeof(int32_t));
+  return FRG_OK;
+}
+
+template <int NJ, int QB, int METRIC>
+static int launch_one(const ScanArgs& a, int grid, int q0, int nq_pass, float* part_sc, int32_t* part_ix,
+                      cudaStream_t st) {
+  const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
+  scan_f32_kernel<NJ, QB, METRIC><<<grid, kScanWarps * 32, smem, st>>>(
+      a.master, a.tags, a.rows, a.qn, a.nq, q0, nq_pass, a.k, a.tenant, part_sc, part_ix);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+template <int NJ, int QB>
+static int launch_metric(const ScanArgs& a, int grid, int q0, int nq_pass, float* ps, int32_t* pi, cudaStream_t st) {
+  if (a.metric == FRG_METRIC_COSINE) return launch_one<NJ, QB, FRG_METRIC_COSINE>(a, grid, q0, nq_pass, ps, pi, st);
+  return launch_one<NJ, QB, FRG_METRIC_EUCLIDEAN>(a, grid, q0, nq_pass, ps, pi, st);
+}
+
+template <int NJ>
+static int launch_qb(const ScanArgs& a, int qb, int grid, int q0, int nq_pass, float* ps, int32_t* pi, cudaStream_t st) {
+  if (qb == 1) return launch_metric<NJ, 1>(a, grid, q0, nq_pass, ps, pi, st);
+  if (qb == 2) return launch_metric<NJ, 2>(a, grid, q0, nq_pass, ps, pi, st);
+  if constexpr (NJ <= 4) { if (qb == 4) return launch_metric<NJ, 4>(a, grid, q0, nq_pass, ps, pi, st); }
+  set_error("scan_f32: unsupported queries-per-pass %d for dim %d", qb, NJ * 128);
+  return FRG_ERR_UNSUPPORTED;
+}
+
+int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, float threshold,
+                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+  if (a.dim != 128 && a.dim != 256 && a.dim != 512 && a.dim != 1024) {
+    set_error("scan_f32: dim %d not built (128, 256, 512, 1024)", a.dim);
+    return FRG_ERR_UNSUPPORTED;
+  }
+  if (a.k < 1 || a.k > FRG_MAX_K) { set_error("k=%d out of range 1..%d", a.k, FRG_MAX_K); return FRG_ERR_INVALID; }
+  if (a.rows > 0x7fffffff) { set_error("scan_f32: more than 2^31-1 rows in one shard"); return FRG_ERR_UNSUPPORTED; }
+  const int grid = a.rows > 0 ? scan_grid(a) : 0;
+  float* part_sc = static_cast<float*>(workspace);
+  int32_t* part_ix = reinterpret_cast<int32_t*>(part_sc + size_t(grid > 0 ? grid : 1) * a.nq * a.k);
+  if (a.rows > 0) {
+    const int qb = scan_qb(a.dim, a.nq);
+    profile_begin(st);
+    int passes = 0;
+    for (int q0 = 0; q0 < a.nq; q0 += qb) {
+      ++passes;
+      const int nq_pass = a.nq - q0 < qb ? a.nq - q0 : qb;
+      int rc;
+      switch (a.dim) {
+        case 128: rc = launch_qb<1>(a, qb, grid, q0, nq_pass, part_sc, part_ix, st); break;
+        case 256: rc = launch_qb<2>(a, qb, grid, q0, nq_pass, part_sc, part_ix, st); break;
+        case 512: rc = launch_qb<4>(a, qb, grid, q0, nq_pass, part_sc, part_ix, st); break;
+        default:  rc = launch_qb<8>(a, qb, grid, q0, nq_pass, part_sc, part_ix, st); break;
+      }
+      FRG_CHECK(rc);
+    }
+    profile_end(st, passes);
+  }
+  return launch_merge_i32(part_sc, part_ix, grid, a.nq, a.k, a.k, a.metric, threshold, row_offset,
+                          /*finalize_euclid=*/a.metric == FRG_METRIC_EUCLIDEAN, out_rows, out_scores,
+                          out_accept, st);
+}
+
+}  // namespace frg

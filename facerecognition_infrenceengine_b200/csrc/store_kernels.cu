@@ -1,0 +1,213 @@
+// Gallery-store kernels: ingest (normalise + write master / bf16 plane / tag), tombstone, stable
+// gather (compaction) and the synthetic generator.  All are HBM-bound row movers: one warp per
+// row, 16-byte accesses, no shared memory.
+#include "frg_internal.cuh"
+
+namespace frg {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 packed;
+  packed.x = *reinterpret_cast<uint32_t*>(&lo);
+  packed.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = packed;
+}
+
+// `embedding / np.linalg.norm(embedding)` at load time: infrenceServer.py:271,324; peopleCount.py:788,806.
+// norm = sqrt(sum x^2) in fp32 (numpy's sdot-based norm; summation order differs by a few ulp).
+__global__ void __launch_bounds__(256)
+ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
+              const int32_t* __restrict__ tags, int64_t n, int64_t append_at, int64_t limit, int dim,
+              int normalise, float* __restrict__ master, __nv_bfloat16* __restrict__ plane,
+              int32_t* __restrict__ tag_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = dim >> 2;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t dst = rows ? rows[i] : append_at + i;
+    if (dst < 0 || dst >= limit) continue;   // host-side entry points validate; device callers are skipped
+    const float4* src = reinterpret_cast<const float4*>(vecs + i * dim);
+    float inv_or_norm = 1.0f;
+    if (normalise) {
+      float ss = 0.f;
+      for (int v = lane; v < nvec; v += 32) {
+        float4 x = __ldg(src + v);
+        ss = fmaf(x.x, x.x, ss); ss = fmaf(x.y, x.y, ss); ss = fmaf(x.z, x.z, ss); ss = fmaf(x.w, x.w, ss);
+      }
+      inv_or_norm = __fsqrt_rn(warp_sum(ss));
+    }
+    float4* m = reinterpret_cast<float4*>(master + dst * dim);
+    for (int v = lane; v < nvec; v += 32) {
+      float4 x = __ldg(src + v);
+      if (normalise) {
+        x.x = __fdiv_rn(x.x, inv_or_norm); x.y = __fdiv_rn(x.y, inv_or_norm);
+        x.z = __fdiv_rn(x.z, inv_or_norm); x.w = __fdiv_rn(x.w, inv_or_norm);
+      }
+      m[v] = x;
+      if (plane) store_bf16x4(plane + dst * dim + v * 4, x);
+    }
+    if (lane == 0) tag_out[dst] = tags ? tags[i] : 0;
+  }
+}
+
+__global__ void tombstone_kernel(const int64_t* __restrict__ rows, int64_t n, int64_t limit,
+                                 int32_t* __restrict__ tags) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int64_t r = rows[i];
+    if (r >= 0 && r < limit) tags[r] = -1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const int64_t* __restrict__ src_rows, int64_t n, int dim,
+                   const float* __restrict__ master_in, const __nv_bfloat16* __restrict__ plane_in,
+                   const int32_t* __restrict__ tags_in, float* __restrict__ master_out,
+                   __nv_bfloat16* __restrict__ plane_out, int32_t* __restrict__ tags_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = dim >> 2;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t s = src_rows[i];
+    const float4* mi = reinterpret_cast<const float4*>(master_in + s * dim);
+    float4* mo = reinterpret_cast<float4*>(master_out + i * dim);
+    for (int v = lane; v < nvec; v += 32) mo[v] = mi[v];
+    if (plane_in) {
+      const uint2* pi = reinterpret_cast<const uint2*>(plane_in + s * dim);
+      uint2* po = reinterpret_cast<uint2*>(plane_out + i * dim);
+      for (int v = lane; v < nvec; v += 32) po[v] = pi[v];
+    }
+    if (lane == 0) tags_out[i] = tags_in[s];
+  }
+}
+
+// ---- synthetic gallery "frg-synth-v1" (CPU twin: oracle/synth.py) ----------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ int nibble_sum(uint32_t h) {
+  return int(h & 0xF) + int((h >> 4) & 0xF) + int((h >> 8) & 0xF) + int((h >> 12) & 0xF) - 30;
+}
+
+// one warp per row; lane handles 8-element blocks lane, lane+32, ... (dim/8 blocks, <= 4 per lane
+// for dim <= 1024).  sum(x^2) is an exact integer, so norm and quotients are bit-identical to numpy.
+__global__ void __launch_bounds__(256)
+synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uint32_t k1, int32_t tag,
+             int dim, float* __restrict__ master, __nv_bfloat16* __restrict__ plane,
+             int32_t* __restrict__ tag_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int nblk = dim >> 3;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const uint64_t g = uint64_t(global_row0 + i);
+    const int64_t dst = append_at + i;
+    int x[4][8];
+    int ss = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = lane + 32 * j;
+      if (b < nblk) {
+        uint32_t w[4];
+        philox4x32_10(uint32_t(g), uint32_t(g >> 32), uint32_t(b), 0u /* stream: gallery */, k0, k1, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int v = nibble_sum((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+          x[j][e] = v;
+          ss += v * v;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float norm = __fsqrt_rn(float(ss));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = lane + 32 * j;
+      if (b < nblk) {
+        float4 lo, hi;
+        lo.x = __fdiv_rn(float(x[j][0]), norm); lo.y = __fdiv_rn(float(x[j][1]), norm);
+        lo.z = __fdiv_rn(float(x[j][2]), norm); lo.w = __fdiv_rn(float(x[j][3]), norm);
+        hi.x = __fdiv_rn(float(x[j][4]), norm); hi.y = __fdiv_rn(float(x[j][5]), norm);
+        hi.z = __fdiv_rn(float(x[j][6]), norm); hi.w = __fdiv_rn(float(x[j][7]), norm);
+        float4* m = reinterpret_cast<float4*>(master + dst * dim + b * 8);
+        m[0] = lo; m[1] = hi;
+        if (plane) {
+          store_bf16x4(plane + dst * dim + b * 8, lo);
+          store_bf16x4(plane + dst * dim + b * 8 + 4, hi);
+        }
+      }
+    }
+    if (lane == 0) tag_out[dst] = tag;
+  }
+}
+
+static int grid_for_rows(int64_t n, int warps_per_block) {
+  int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+int launch_ingest(const float* vecs, const int64_t* rows, const int32_t* tags, int64_t n, int64_t append_at,
+                  int dim, bool normalise, float* master, __nv_bfloat16* plane, int32_t* tag_out,
+                  cudaStream_t st) {
+  if (n <= 0) return FRG_OK;
+  // limit: appended rows land below append_at + n, in-place rows below append_at
+  const int64_t limit = rows ? append_at : append_at + n;
+  ingest_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(vecs, rows, tags, n, append_at, limit, dim,
+                                                     normalise ? 1 : 0, master, plane, tag_out);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+int launch_tombstone(const int64_t* rows, int64_t n, int64_t limit, int32_t* tags, cudaStream_t st) {
+  if (n <= 0) return FRG_OK;
+  tombstone_kernel<<<int((n + 255) / 256), 256, 0, st>>>(rows, n, limit, tags);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+int launch_synth(int64_t n, int64_t append_at, int64_t global_row0, uint64_t seed, int32_t tag, int dim,
+                 float* master, __nv_bfloat16* plane, int32_t* tag_out, cudaStream_t st) {
+  if (n <= 0) return FRG_OK;
+  synth_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(n, append_at, global_row0, uint32_t(seed),
+                                                    uint32_t(seed >> 32), tag, dim, master, plane, tag_out);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+int launch_gather_rows(const int64_t* src_rows, int64_t n, int dim, const float* master_in,
+                       const __nv_bfloat16* plane_in, const int32_t* tags_in, float* master_out,
+                       __nv_bfloat16* plane_out, int32_t* tags_out, cudaStream_t st) {
+  if (n <= 0) return FRG_OK;
+  gather_rows_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(src_rows, n, dim, master_in, plane_in, tags_in,
+                                                          master_out, plane_out, tags_out);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+}  // namespace frg

@@ -1,0 +1,226 @@
+"""GPU-resident gallery store: the replacement for ``EmbeddingManager.embeddings`` - the
+``Dict[str, np.ndarray]`` both reference servers keep in process memory
+(infrenceServer.py:48-51, peopleCount.py:706-708).
+
+The device side (libfrg.so) holds, per row, the unit fp32 vector, its bf16 image and an int32 tag
+(tenant code, -1 = removed).  The host side, here, keeps what the dict keys and the metadata dict
+carried: ``row <-> id string <-> metadata``.  Row order is dict insertion order, because the
+reference's strict ``>`` scan resolves exact ties by that order (infrenceServer.py:538-542):
+
+  * a new id appends a row; an existing id is overwritten in place (dict assignment keeps position);
+  * a removed id leaves a tombstone; if it is enrolled again later it appends at the END, exactly
+    as ``del d[k]; d[k] = v`` does.  ``compact()`` squeezes tombstones out without reordering.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class GalleryStore:
+    def __init__(self, dim: int = 512, capacity: int = 1024, device: int = 0, bf16_plane: bool = True,
+                 raw: bool = False):
+        self.dim = int(dim)
+        self.device = int(device)
+        flags = (N.STORE_BF16_PLANE if bf16_plane else 0) | (N.STORE_RAW if raw else 0)
+        h = C.c_void_p()
+        N.check(N.lib.frg_store_create(self.device, self.dim, int(capacity), flags, C.byref(h)))
+        self._h = h
+        self._lock = threading.RLock()               # the reference's embeddings_lock
+        self._row_of: Dict[str, int] = {}
+        self._id_of: Dict[int, str] = {}
+        self._meta: Dict[str, Dict] = {}
+        self._tenants: Dict[str, int] = {}
+        self._anon: List[Tuple[int, int, int]] = []  # (row0, n, global_row0) ranges filled synthetically
+        self._rows = 0                               # mirror of stats.rows
+
+    # ------------------------------------------------------------------ life-cycle
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib.frg_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("store is closed")
+        return self._h
+
+    # ------------------------------------------------------------------ tenants
+    def tenant_code(self, company_id: Optional[str], create: bool = True) -> int:
+        """Small int standing for a company id (the tag stored per row).  None -> 0."""
+        if company_id is None:
+            return 0
+        key = str(company_id)
+        with self._lock:
+            if key not in self._tenants:
+                if not create:
+                    return -2          # matches no row
+                self._tenants[key] = len(self._tenants) + 1
+            return self._tenants[key]
+
+    # ------------------------------------------------------------------ raw row API
+    def stats(self) -> N.StoreStats:
+        st = N.StoreStats()
+        N.check(N.lib.frg_store_stats(self.handle, C.byref(st)))
+        return st
+
+    def reserve(self, capacity: int):
+        N.check(N.lib.frg_store_reserve(self.handle, int(capacity)))
+
+    def append_rows(self, vecs: np.ndarray, tags: Optional[np.ndarray] = None, prenormalised: bool = False) -> int:
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
+        t = None if tags is None else np.ascontiguousarray(tags, dtype=np.int32)
+        with self._lock:
+            first = self._rows
+            N.check(N.lib.frg_store_upsert_host(self.handle, None, _ptr(vecs), _ptr(t), len(vecs),
+                                                N.ROWS_PRENORMALISED if prenormalised else 0))
+            self._rows += len(vecs)
+            return first
+
+    def overwrite_rows(self, rows: Sequence[int], vecs: np.ndarray, tags: Optional[np.ndarray] = None,
+                       prenormalised: bool = False):
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
+        t = None if tags is None else np.ascontiguousarray(tags, dtype=np.int32)
+        with self._lock:
+            N.check(N.lib.frg_store_upsert_host(self.handle, _ptr(r), _ptr(vecs), _ptr(t), len(r),
+                                                N.ROWS_PRENORMALISED if prenormalised else 0))
+
+    def remove_rows(self, rows: Sequence[int]):
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        if len(r):
+            with self._lock:
+                N.check(N.lib.frg_store_remove_host(self.handle, _ptr(r), len(r)))
+
+    def read_rows(self, row0: int = 0, n: Optional[int] = None):
+        with self._lock:
+            n = self._rows - row0 if n is None else n
+            vecs = np.empty((n, self.dim), np.float32)
+            tags = np.empty(n, np.int32)
+            N.check(N.lib.frg_store_read_host(self.handle, int(row0), int(n), _ptr(vecs), _ptr(tags)))
+            return vecs, tags
+
+    def fill_synthetic(self, n: int, global_row0: int = 0, seed: int = 1234, tag: int = 0, stream=None):
+        """Append n rows of the frg-synth-v1 gallery (bench / scale tests; oracle.synth is the CPU twin).
+        Their ids are implicit: ``"%024x" % global_row``."""
+        with self._lock:
+            N.check(N.lib.frg_store_fill_synthetic(self.handle, int(n), int(global_row0), int(seed), int(tag),
+                                                   C.c_void_p(stream or 0)))
+            self._anon.append((self._rows, int(n), int(global_row0)))
+            self._rows += int(n)
+
+    # ------------------------------------------------------------------ id-level API (the dict)
+    def __len__(self):
+        with self._lock:
+            return len(self._row_of) + sum(n for _, n, _ in self._anon)
+
+    def __contains__(self, pid: str):
+        return str(pid) in self._row_of
+
+    @property
+    def rows(self) -> int:
+        return self._rows
+
+    def ids(self) -> List[str]:
+        """Live ids in gallery (= dict) order."""
+        with self._lock:
+            return [self._id_of[r] for r in sorted(self._id_of)]
+
+    def row_of(self, pid: str) -> int:
+        return self._row_of.get(str(pid), -1)
+
+    def id_of(self, row: int) -> Optional[str]:
+        row = int(row)
+        if row < 0:
+            return None
+        pid = self._id_of.get(row)
+        if pid is not None:
+            return pid
+        for r0, n, g0 in self._anon:
+            if r0 <= row < r0 + n:
+                return "%024x" % (g0 + row - r0)
+        return None
+
+    def metadata(self, pid: str) -> Optional[Dict]:
+        return self._meta.get(str(pid))
+
+    def upsert(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
+               meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
+        """``self.embeddings[id] = v / ||v||`` for a batch, in the given order
+        (infrenceServer.py:273,326; peopleCount.py:790,808)."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
+        if len(ids) != len(vecs):
+            raise ValueError("ids and vecs differ in length")
+        with self._lock:
+            tags = np.array([self.tenant_code(c) for c in (company_ids or [None] * len(ids))], np.int32)
+            # repeated dict assignment: position is fixed by the FIRST occurrence of an id in the
+            # batch, content by the LAST
+            last = {str(p): i for i, p in enumerate(ids)}
+            new_i, old_i = [], []
+            for p in dict.fromkeys(str(p) for p in ids):
+                (old_i if p in self._row_of else new_i).append(last[p])
+            if old_i:
+                rows = [self._row_of[str(ids[i])] for i in old_i]
+                self.overwrite_rows(rows, vecs[old_i], tags[old_i], prenormalised)
+            if new_i:
+                first = self.append_rows(vecs[new_i], tags[new_i], prenormalised)
+                for j, i in enumerate(new_i):
+                    p = str(ids[i])
+                    self._row_of[p] = first + j
+                    self._id_of[first + j] = p
+            if meta is not None:
+                for p, m in zip(ids, meta):
+                    self._meta[str(p)] = m
+
+    def remove(self, ids: Iterable[str]) -> int:
+        """``del self.embeddings[id]`` (infrenceServer.py:248-251).  Unknown ids are ignored."""
+        with self._lock:
+            rows = []
+            for p in ids:
+                p = str(p)
+                r = self._row_of.pop(p, None)
+                if r is not None:
+                    rows.append(r)
+                    self._id_of.pop(r, None)
+                    self._meta.pop(p, None)
+            self.remove_rows(rows)
+            return len(rows)
+
+    def compact(self):
+        """Drop tombstones; order (hence tie behaviour) is unchanged."""
+        with self._lock:
+            n = self._rows
+            mapping = np.empty(n, np.int64)
+            N.check(N.lib.frg_store_compact(self.handle, _ptr(mapping)))
+            new_row_of, new_id_of = {}, {}
+            for p, r in self._row_of.items():
+                nr = int(mapping[r])
+                new_row_of[p] = nr
+                new_id_of[nr] = p
+            self._row_of, self._id_of = new_row_of, new_id_of
+            self._anon = [(int(mapping[r0]), cnt, g0) for r0, cnt, g0 in self._anon if cnt and mapping[r0] >= 0]
+            self._rows = int((mapping >= 0).sum())
+
+    def snapshot_arrays(self):
+        """(ids, G fp32[n, dim], tags) of the LIVE rows in gallery order - what get_all() returned
+        as dict copies (peopleCount.py:816-819).  For tests and export, not for matching."""
+        with self._lock:
+            vecs, tags = self.read_rows(0, self._rows)
+            live = np.nonzero(tags >= 0)[0]
+            return [self.id_of(int(r)) for r in live], vecs[live], tags[live]

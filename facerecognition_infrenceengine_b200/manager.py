@@ -1,0 +1,203 @@
+"""``EmbeddingManager`` - same name, methods and sync semantics as the reference's two managers
+(infrenceServer.py:36-398 "live", peopleCount.py:695-819 "campus"), over the GPU-resident store.
+
+What changes: the per-frame cost.  ``get_embeddings_for_company`` no longer runs two Mongo
+queries and rebuilds a dict per frame (infrenceServer.py:343-380) and ``get_all`` no longer copies
+the dict (peopleCount.py:816-819); both return a :class:`GalleryView` - (store, tenant) - that the
+matcher turns into a per-row tag comparison inside the kernel.
+
+Where records come from is pluggable (``source``): the reference reads Mongo + GridFS; this
+environment has neither, so a source is any object with the three methods of :class:`ListSource`.
+Records are plain dicts shaped like the reference's documents, with the unpickled vector inline
+under ``'embedding'``.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from datetime import datetime
+from typing import Dict, Iterable, List, Optional
+
+import numpy as np
+
+from .gallery import GalleryStore
+
+
+# ---- eligibility filters: the Mongo queries of the loaders, restated on dict records ----------
+def eligible_employee(doc: Dict) -> bool:
+    """infrenceServer.py:95-99 == peopleCount.py:738-742."""
+    return (doc.get("status") == "active" and doc.get("blacklisted") is False
+            and doc.get("embedding_status", "done") == "done" and doc.get("embedding") is not None)
+
+
+def eligible_visitor(doc: Dict) -> bool:
+    """infrenceServer.py:126 == peopleCount.py:747."""
+    return doc.get("embedding_status", "done") == "done" and doc.get("embedding") is not None
+
+
+def inactive_employee(doc: Dict) -> bool:
+    """infrenceServer.py:238-243: status != 'active' OR blacklisted."""
+    return doc.get("status") != "active" or doc.get("blacklisted") is True
+
+
+class ListSource:
+    """In-memory record source (tests, examples).  A Mongo-backed source implements the same three
+    methods with the reference's queries."""
+
+    def __init__(self, employees: Optional[List[Dict]] = None, visitors: Optional[List[Dict]] = None):
+        self.employees = employees or []
+        self.visitors = visitors or []
+
+    def employee_docs(self, since: Optional[datetime] = None) -> List[Dict]:
+        return [d for d in self.employees if eligible_employee(d) and (since is None or d.get("lastUpdated") >= since)]
+
+    def visitor_docs(self, since: Optional[datetime] = None) -> List[Dict]:
+        return [d for d in self.visitors if eligible_visitor(d) and (since is None or d.get("lastUpdated") >= since)]
+
+    def inactive_employee_ids(self) -> List[str]:
+        return [str(d["_id"]) for d in self.employees if inactive_employee(d)]
+
+
+class GalleryView:
+    """What the matcher needs instead of a dict copy: the store and an optional tenant filter."""
+
+    def __init__(self, store: GalleryStore, company_id: Optional[str] = None):
+        self.store = store
+        self.company_id = company_id
+
+    def __len__(self):
+        if self.company_id is None:
+            return len(self.store)
+        code = self.store.tenant_code(self.company_id, create=False)
+        _, _, tags = self.store.snapshot_arrays()
+        return int((tags == code).sum())
+
+    def __bool__(self):
+        return len(self.store) > 0
+
+
+class EmbeddingManager:
+    """mode='live'  : incremental sync by lastUpdated every 30 s + eviction (infrenceServer.py:175-258)
+    mode='campus': full reload every 60 s, never evicts (peopleCount.py:766-776)."""
+
+    def __init__(self, source, dim: int = 512, device: int = 0, mode: str = "live",
+                 sync_interval: Optional[float] = None, capacity: int = 1024, bf16_plane: bool = True):
+        assert mode in ("live", "campus")
+        self.source = source
+        self.mode = mode
+        self.store = GalleryStore(dim, capacity, device, bf16_plane)
+        self.embeddings_lock = threading.Lock()
+        self.last_sync_time: Optional[datetime] = None
+        self.is_initial_load = True
+        self.sync_interval = sync_interval if sync_interval is not None else (30 if mode == "live" else 60)
+        self.running = False
+        self.sync_thread: Optional[threading.Thread] = None
+        self._initial_load()
+
+    # ---- loading ----------------------------------------------------------------------------
+    def _initial_load(self):
+        """infrenceServer.py:62-91 / peopleCount.py:716-734."""
+        self._load_updated_embeddings(self.source.employee_docs(), self.source.visitor_docs())
+        self.last_sync_time = datetime.utcnow()
+        self.is_initial_load = False
+
+    def _load_updated_embeddings(self, employees: Iterable[Dict], visitors: Iterable[Dict]):
+        """infrenceServer.py:260-341 / peopleCount.py:778-814: employees first, then visitors; each
+        vector is divided by its norm on ingest (done on the device)."""
+        ids, vecs, comps, meta = [], [], [], []
+        for e in employees:
+            ids.append(str(e["_id"]))
+            vecs.append(np.asarray(e["embedding"], dtype=np.float32))
+            comps.append(None if e.get("companyId") is None else str(e["companyId"]))
+            meta.append({"name": e.get("employeeName", "Unknown"), "employeeId": e.get("employeeId", "Unknown"),
+                         "email": e.get("employeeEmail", ""), "mobile": e.get("employeeMobile", ""),
+                         "type": "employee", "lastUpdated": e.get("lastUpdated")})
+        for v in visitors:
+            ids.append(str(v["_id"]))
+            vecs.append(np.asarray(v["embedding"], dtype=np.float32))
+            comps.append(None if v.get("companyId") is None else str(v["companyId"]))
+            meta.append({"name": v.get("visitorName", "Unknown"), "type": "visitor",
+                         "lastUpdated": v.get("lastUpdated")})
+        if ids:
+            with self.embeddings_lock:
+                self.store.upsert(ids, np.stack(vecs), comps, meta)
+
+    def _remove_inactive_employees(self):
+        """infrenceServer.py:234-258."""
+        with self.embeddings_lock:
+            return self.store.remove(self.source.inactive_employee_ids())
+
+    def _sync_embeddings(self):
+        if self.mode == "live":
+            if self.last_sync_time is None:
+                return
+            since = self.last_sync_time
+            employees = self.source.employee_docs(since)
+            visitors = self.source.visitor_docs(since)
+            self._remove_inactive_employees()
+            if employees or visitors:
+                self._load_updated_embeddings(employees, visitors)
+            self.last_sync_time = datetime.utcnow()
+        else:
+            self._load_updated_embeddings(self.source.employee_docs(), self.source.visitor_docs())
+            self.last_sync_time = datetime.utcnow()
+
+    def force_sync(self):
+        """infrenceServer.py:382-384."""
+        self._sync_embeddings()
+
+    def start_sync(self):
+        """infrenceServer.py:158-166 / peopleCount.py:750-758."""
+        if self.running:
+            return
+        self.running = True
+        self.sync_thread = threading.Thread(target=self._sync_loop, daemon=True)
+        self.sync_thread.start()
+
+    def stop_sync(self):
+        self.running = False
+        if self.sync_thread:
+            self.sync_thread.join(timeout=5)
+
+    def _sync_loop(self):
+        while self.running:
+            try:
+                if self.mode == "campus":
+                    self._sleep(self.sync_interval)
+                    if not self.running:
+                        break
+                    self._sync_embeddings()
+                else:
+                    self._sync_embeddings()
+                    self._sleep(self.sync_interval)
+            except Exception:                       # log-and-retry, infrenceServer.py:181-183
+                self._sleep(5)
+
+    def _sleep(self, seconds: float):
+        end = time.time() + seconds
+        while self.running and time.time() < end:
+            time.sleep(min(0.05, max(0.0, end - time.time())))
+
+    # ---- what the matchers ask for -------------------------------------------------------------
+    def get_embeddings_for_company(self, company_id: str) -> GalleryView:
+        """infrenceServer.py:343-380 -> a tenant filter, not a dict rebuild."""
+        return GalleryView(self.store, str(company_id))
+
+    def get_all(self) -> GalleryView:
+        """peopleCount.py:816-819 -> a handle, not a copy."""
+        return GalleryView(self.store, None)
+
+    def get_stats(self) -> Dict:
+        """infrenceServer.py:386-398 (same keys) + device-side figures."""
+        with self.embeddings_lock:
+            metas = [self.store.metadata(i) or {} for i in self.store.ids()]
+            st = self.store.stats()
+            return {
+                "total_embeddings": len(metas),
+                "employees": sum(1 for m in metas if m.get("type") == "employee"),
+                "visitors": sum(1 for m in metas if m.get("type") == "visitor"),
+                "last_sync": self.last_sync_time.isoformat() if self.last_sync_time else None,
+                "initial_load_complete": not self.is_initial_load,
+                "device_rows": int(st.rows), "device_live_rows": int(st.live),
+                "device_capacity": int(st.capacity), "device_bytes": int(st.bytes), "version": int(st.version),
+            }

@@ -1,0 +1,149 @@
+"""The matching service: query embeddings in; identity ids, scores and accept/reject out.
+
+Replaces the inline per-face loop of the reference -
+``FaceRecognitionProcessor.recognize_faces`` (infrenceServer.py:530-552) and
+``CameraProcessor.process_frame`` (peopleCount.py:860-887) - with one batched call into
+libfrg.so.  The two thin classes at the bottom keep the reference's own names, thresholds and
+result shapes so a call site can be switched over line for line.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .gallery import GalleryStore
+
+LIVE_THRESHOLD = 0.4         # infrenceServer.py:407
+CAMPUS_THRESHOLD = 0.45      # peopleCount.py:829
+CAMPUS_UNKNOWN = 0.35        # peopleCount.py:830
+
+
+@dataclass
+class MatchResult:
+    rows: np.ndarray      # int64 [F, k]   gallery rows, -1 = none
+    scores: np.ndarray    # fp32  [F, k]   cosine score (or Euclidean distance), -1.0 / +inf = none
+    accept: np.ndarray    # bool  [F]      decision on slot 0 at the call's threshold
+    ids: Optional[List[List[Optional[str]]]] = None
+    variant: str = ""
+    launches: int = 0
+
+
+def _params(metric: str, variant: str, threshold: float, tenant: int, row_offset: int) -> N.MatchParams:
+    return N.MatchParams(metric=N.METRICS[metric], variant=N.VARIANTS[variant], threshold=float(np.float32(threshold)),
+                         tenant=int(tenant), row_offset=int(row_offset), flags=0, reserved=0)
+
+
+class Matcher:
+    """``match(Q)`` for host (numpy) batches, ``match_device(Q)`` for batches already on the GPU."""
+
+    def __init__(self, store: GalleryStore, metric: str = "cosine"):
+        self.store = store
+        self.metric = metric
+
+    # ---- host buffers in, host buffers out: H2D + kernels + D2H inside one C call
+    def match(self, Q: np.ndarray, k: int = 1, threshold: float = LIVE_THRESHOLD,
+              company_id: Optional[str] = None, variant: str = "auto", row_offset: int = 0,
+              with_ids: bool = True, out: Optional[MatchResult] = None) -> MatchResult:
+        Q = np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.store.dim)
+        F = len(Q)
+        if out is None:
+            out = MatchResult(np.empty((F, k), np.int64), np.empty((F, k), np.float32), np.zeros(F, np.uint8))
+        tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
+        p = _params(self.metric, variant, threshold, tenant, row_offset)
+        N.check(N.lib.frg_match_host(self.store.handle, Q.ctypes.data_as(C.c_void_p), F, int(k), C.byref(p),
+                                     out.rows.ctypes.data_as(C.c_void_p), out.scores.ctypes.data_as(C.c_void_p),
+                                     out.accept.ctypes.data_as(C.c_void_p)))
+        out.variant, out.launches = N.last_variant(), N.last_launch_count()
+        if out.accept.dtype != np.bool_:
+            out.accept = out.accept.view(np.bool_)
+        if with_ids:
+            out.ids = [[self.store.id_of(r) for r in rr] for rr in out.rows]
+        return out
+
+    # ---- device tensors in/out, enqueued on the caller's stream (torch is only the allocator here)
+    def match_device(self, Q, k: int = 1, threshold: float = LIVE_THRESHOLD, company_id: Optional[str] = None,
+                     variant: str = "auto", row_offset: int = 0, out=None, stream: Optional[int] = None):
+        import torch
+        assert Q.is_cuda and Q.dtype == torch.float32 and Q.is_contiguous()
+        F = Q.shape[0]
+        if out is None:
+            out = (torch.empty((F, k), dtype=torch.int64, device=Q.device),
+                   torch.empty((F, k), dtype=torch.float32, device=Q.device),
+                   torch.empty((F,), dtype=torch.uint8, device=Q.device))
+        rows, scores, accept = out
+        if stream is None:
+            stream = torch.cuda.current_stream(Q.device).cuda_stream
+        tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
+        p = _params(self.metric, variant, threshold, tenant, row_offset)
+        N.check(N.lib.frg_match(self.store.handle, C.c_void_p(Q.data_ptr()), F, int(k), C.byref(p),
+                                C.c_void_p(rows.data_ptr()), C.c_void_p(scores.data_ptr()),
+                                C.c_void_p(accept.data_ptr()), C.c_void_p(stream)))
+        return rows, scores, accept
+
+
+class FaceRecognitionProcessor:
+    """Drop-in for the matching half of infrenceServer.FaceRecognitionProcessor (:400-563).
+
+    ``recognize(embeddings, company_id)`` takes the ``face.normed_embedding`` of every detected
+    face and returns, per face, what the reference passes to its draw call (:545-558):
+    ``person_info`` (metadata, or ``{'name': 'Unknown', 'type': 'unknown'}``), the reported score
+    (0 when rejected) and the matched id (None when rejected)."""
+
+    def __init__(self, store: GalleryStore, recognition_threshold: float = LIVE_THRESHOLD):
+        self.matcher = Matcher(store)
+        self.recognition_threshold = recognition_threshold
+
+    def recognize(self, embeddings: np.ndarray, company_id: Optional[str] = None) -> List[Dict]:
+        store = self.matcher.store
+        if len(embeddings) == 0 or len(store) == 0:      # `if not embeddings: return frame` (:523-525)
+            return []
+        r = self.matcher.match(embeddings, 1, self.recognition_threshold, company_id)
+        out = []
+        for f in range(len(embeddings)):
+            if r.accept[f]:
+                pid = r.ids[f][0]
+                info = store.metadata(pid) or {"name": pid, "type": "employee"}
+                out.append({"person_id": pid, "person_info": info, "recognition_score": r.scores[f, 0]})
+            else:
+                out.append({"person_id": None, "person_info": {"name": "Unknown", "type": "unknown"},
+                            "recognition_score": 0})
+        return out
+
+
+class CameraProcessor:
+    """Drop-in for the matching half of peopleCount.CameraProcessor (:822-896): three-way decision
+    at 0.45 / 0.35 over ALL tenants, and the same stats dict."""
+
+    def __init__(self, store: GalleryStore, recognition_threshold: float = CAMPUS_THRESHOLD,
+                 unknown_threshold: float = CAMPUS_UNKNOWN):
+        self.matcher = Matcher(store)
+        self.recognition_threshold = recognition_threshold
+        self.unknown_threshold = unknown_threshold
+
+    def process(self, embeddings: np.ndarray):
+        """Returns (events, stats): events[f] is ('recognized', id, float score) |
+        ('unknown', None, None) | ('ignored', None, None)."""
+        stats = {"faces": 0, "recognized": 0, "unknown": 0}
+        store = self.matcher.store
+        if len(store) == 0:                               # peopleCount.py:850-851
+            return [], stats
+        stats["faces"] = len(embeddings)
+        if len(embeddings) == 0:
+            return [], stats
+        r = self.matcher.match(embeddings, 1, self.recognition_threshold)
+        unknown_thr = np.float32(self.unknown_threshold)
+        events = []
+        for f in range(len(embeddings)):
+            if r.accept[f]:
+                events.append(("recognized", r.ids[f][0], float(r.scores[f, 0])))
+                stats["recognized"] += 1
+            elif r.scores[f, 0] < unknown_thr:            # best_score stays -1 when nothing matched
+                events.append(("unknown", None, None))
+                stats["unknown"] += 1
+            else:
+                events.append(("ignored", None, None))
+        return events, stats

@@ -1,0 +1,163 @@
+/*
+ * frg.h - C ABI of the B200-native face-gallery matcher (libfrg.so).
+ *
+ * This is the drop-in boundary for ONE path of bharatlytics/faceRecognition_InfrenceEngine:
+ * matching query face embeddings against the enrolled gallery.  The reference has no native
+ * code and no FFI; its path is an inline Python loop plus an in-process dict cache.  Each
+ * entry point below names the reference lines it replaces (paths relative to the reference
+ * root).  A ctypes binding for the reference's two call sites is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns an int status (FRG_OK = 0); frg_last_error() returns a
+ *     thread-local description of the last failure.  Nothing throws or aborts across the ABI.
+ *   - "_host" entry points take HOST pointers, copy in/out themselves and return when the
+ *     result is in the caller's buffers.  The others take DEVICE pointers plus a CUDA stream
+ *     (cudaStream_t passed as void*; NULL = legacy default stream) and only enqueue work.
+ *   - the caller owns every buffer it passes; the library owns only the store handle.
+ *   - a "row" is a position in gallery order = insertion order of the reference's dict
+ *     (infrenceServer.py:49, peopleCount.py:707).  Exact score ties resolve to the LOWER row,
+ *     which is the reference's strict '>' scan (infrenceServer.py:540, peopleCount.py:871).
+ *   - no match: row = -1, score = -1.0f (the scan's initial best_score; infrenceServer.py:536).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef FRG_H_
+#define FRG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FRG_API __attribute__((visibility("default")))
+#else
+#define FRG_API
+#endif
+
+/* status codes */
+#define FRG_OK               0
+#define FRG_ERR_INVALID      1   /* bad argument */
+#define FRG_ERR_CUDA         2   /* a CUDA call failed; see frg_last_error() */
+#define FRG_ERR_NOMEM        3
+#define FRG_ERR_UNSUPPORTED  4   /* shape / mode not built (e.g. dim not in {128,256,512,1024}) */
+#define FRG_ERR_STATE        5   /* e.g. row out of range, store full and not growable */
+
+/* metric */
+#define FRG_METRIC_COSINE    0   /* dot of unit vectors: infrenceServer.py:539, peopleCount.py:870 */
+#define FRG_METRIC_EUCLIDEAN 1   /* ||g - q||_2, smallest wins.  NOT in the reference (BASELINE config 3) */
+
+/* kernel variant */
+#define FRG_VARIANT_AUTO      0  /* dispatch table by batch size */
+#define FRG_VARIANT_SCAN_F32  1  /* exact fp32 streaming scan on CUDA cores, reads the fp32 master */
+#define FRG_VARIANT_TC_EXACT  2  /* tcgen05 bf16 filter over the scan plane + exact fp32 rescoring */
+#define FRG_VARIANT_TC_BF16   3  /* tcgen05 bf16 scores returned as-is ("bf16 gallery mode", own tolerance) */
+
+/* frg_store_create flags */
+#define FRG_STORE_BF16_PLANE  1u /* keep the bf16 scan plane next to the fp32 master (needed by TC variants) */
+#define FRG_STORE_RAW         2u /* never normalise on ingest (Euclidean galleries) */
+
+/* upsert flags */
+#define FRG_ROWS_PRENORMALISED 1u /* store vectors as given (snapshot reload; exact-score fixtures) */
+
+#define FRG_MAX_K 16
+
+typedef struct frg_store frg_store;
+
+typedef struct frg_store_stats_t {
+  int64_t rows;        /* rows in use, including tombstones (= next append position) */
+  int64_t live;        /* rows that can match (tag >= 0) */
+  int64_t capacity;    /* rows allocated */
+  int64_t version;     /* bumped by every mutation: the snapshot epoch a match observes */
+  int64_t bytes;       /* device bytes held */
+  int32_t dim;
+  int32_t device;
+  uint32_t flags;
+  uint32_t reserved;
+} frg_store_stats_t;
+
+typedef struct frg_match_params_t {
+  int32_t metric;      /* FRG_METRIC_* */
+  int32_t variant;     /* FRG_VARIANT_* */
+  float   threshold;   /* cosine: accept iff score >= threshold, compared in fp32 (NumPy>=2 semantics of
+                          infrenceServer.py:545 / peopleCount.py:876); euclidean: accept iff dist <= threshold */
+  int32_t tenant;      /* < 0: all tenants (peopleCount.py:848); else only rows with this tag
+                          (company subset, infrenceServer.py:343-380) */
+  int64_t row_offset;  /* added to every returned row (global row of a shard's first row) */
+  uint32_t flags;      /* reserved, 0 */
+  uint32_t reserved;
+} frg_match_params_t;
+
+FRG_API int         frg_abi_version(void);
+FRG_API const char* frg_last_error(void);
+/* number of CUDA devices visible; FRG_ERR_CUDA when the driver / device is missing */
+FRG_API int         frg_device_count(int32_t* count);
+
+/* ---- gallery store: replaces EmbeddingManager.embeddings, the Dict[str, np.ndarray] cache
+ *      (infrenceServer.py:36-60, peopleCount.py:695-714).  Holds, per row: the unit fp32 vector
+ *      (master), optionally its bf16 image (scan plane), and an int32 tag (tenant >= 0, -1 = removed). */
+FRG_API int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t flags, frg_store** out);
+FRG_API int frg_store_destroy(frg_store* s);
+FRG_API int frg_store_reserve(frg_store* s, int64_t capacity);           /* grow; contents and order kept */
+FRG_API int frg_store_stats(frg_store* s, frg_store_stats_t* out);       /* get_stats(): infrenceServer.py:386-398 */
+
+/* Upsert n rows.  rows == NULL: append at [stats.rows, stats.rows + n) (a NEW id in the dict);
+ * else rows[i] < stats.rows is overwritten in place (an EXISTING id keeps its position).
+ * Vectors are divided by their L2 norm on ingest unless FRG_ROWS_PRENORMALISED / FRG_STORE_RAW:
+ * `embedding / np.linalg.norm(embedding)`, infrenceServer.py:271,324; peopleCount.py:788,806
+ * (a zero vector becomes a NaN row that never matches).  tags == NULL: tag 0. */
+FRG_API int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
+                     int64_t n, uint32_t flags, void* stream);
+FRG_API int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
+                          int64_t n, uint32_t flags);
+/* Tombstone rows (tag := -1): `del self.embeddings[id]`, infrenceServer.py:234-258. */
+FRG_API int frg_store_remove(frg_store* s, const int64_t* rows, int64_t n, void* stream);
+FRG_API int frg_store_remove_host(frg_store* s, const int64_t* rows, int64_t n);
+/* Stable compaction: drops tombstones, keeps order.  old_to_new (host, stats.rows entries, may be
+ * NULL) receives the new row of every old row or -1. */
+FRG_API int frg_store_compact(frg_store* s, int64_t* old_to_new);
+/* Copy rows [row0, row0+n) back to the host (snapshot / verification): get_all(), peopleCount.py:816. */
+FRG_API int frg_store_read_host(frg_store* s, int64_t row0, int64_t n, float* vecs, int32_t* tags);
+/* Append n rows of the counter-based synthetic gallery "frg-synth-v1" (oracle/synth.py is the
+ * bit-identical CPU twin): row i is generated from (seed, global_row0 + i) only. */
+FRG_API int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint64_t seed,
+                             int32_t tag, void* stream);
+
+/* ---- match: replaces the per-face loop of FaceRecognitionProcessor.recognize_faces
+ *      (infrenceServer.py:530-552) and CameraProcessor.process_frame (peopleCount.py:860-887).
+ * q: nq x dim RAW query embeddings (face.normed_embedding); they are re-normalised inside,
+ *    as the reference does (infrenceServer.py:532, peopleCount.py:863).
+ * out_rows [nq*k] int64, out_scores [nq*k] fp32: the k best rows per query, best first
+ *    (k = 1 is the reference's scan; k > 1 is its stable-sort extension).
+ * out_accept [nq] uint8: the decision on slot 0 (infrenceServer.py:545; peopleCount.py:876).
+ * An empty gallery is not an error: every query gets row -1 / reject (infrenceServer.py:523-525). */
+FRG_API int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+              int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
+FRG_API int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+                   int64_t* out_rows, float* out_scores, uint8_t* out_accept);
+
+/* ---- k-way merge of per-shard results (multi-GPU tail).
+ * scores/rows: [parts][nq][k] (each list best-first, unfilled slots row -1), e.g. the output of an
+ * all-gather of every rank's frg_match result.  Order: score desc (euclidean: asc), then row asc. */
+FRG_API int frg_merge_topk(int32_t device, const float* scores, const int64_t* rows, int32_t parts,
+                   int32_t nq, int32_t k, int32_t metric, float threshold,
+                   int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
+
+/* ---- introspection for tests / bench: name and launch count of the kernels the LAST frg_match /
+ * frg_match_host on this thread enqueued (bench.py reports it as gpu_launches). */
+FRG_API int frg_last_launch_count(void);
+FRG_API const char* frg_last_variant(void);
+
+/* ---- kernel timing for bench.py's roofline: while enabled, every frg_match brackets its DOMINANT
+ * kernel launches (the gallery scan / tensor-core pass, not the query prep or the merge) with CUDA
+ * events on the caller's stream.  frg_profile_collect waits for those events, returns the summed
+ * device time and launch count since the last collect, and clears them.  Thread-local. */
+FRG_API int frg_profile_enable(int32_t on);
+FRG_API int frg_profile_collect(float* dominant_ms, int32_t* dominant_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FRG_H_ */

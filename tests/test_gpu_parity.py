@@ -1,0 +1,425 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors.
+Every test here needs a B200; tolerances are stated where used:
+  * rows (identity ids): exact wherever adjacent oracle scores differ by more than TOL
+  * scores: |delta| <= TOL = 1e-4 (BASELINE.json, fp32 storage) - observed ~1e-7
+  * accept / three-way decisions: identical
+"""
+import numpy as np
+import pytest
+
+from oracle import matcher_oracle as mo
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+KIND = {"recognized": 0, "unknown": 1, "ignored": 2}
+VARIANTS = ["scan_f32", "auto"]
+
+
+@pytest.fixture(scope="module")
+def frg():
+    import __graft_entry__ as g
+    g.build()
+    import facerecognition_infrenceengine_b200 as frg
+    assert frg._native.device_count() >= 1
+    return frg
+
+
+def hex_ids(n, base=0):
+    return ["%024x" % (base + i) for i in range(n)]
+
+
+def check_against_oracle(frg, store, Q, G, k, threshold, tags=None, tenant=None, company=None, variant="auto",
+                         metric="cosine"):
+    m = frg.Matcher(store, metric=metric)
+    r = m.match(Q, k, threshold, company_id=company, variant=variant)
+    assert r.launches > 0
+    kk = min(k + 1, max(len(G), 1))
+    if metric == "cosine":
+        ref_rows, ref_scores, ref_acc = mo.match_topk(Q, G, max(kk, k), threshold, tags, tenant)
+        assert mo.ids_match_with_gap(ref_rows, ref_scores, r.rows, TOL).all()
+        filled = ref_rows[:, :k] >= 0
+        assert np.abs(r.scores[filled] - ref_scores[:, :k][filled]).max(initial=0) <= TOL
+        assert (r.scores[~filled] == -1).all() and (r.rows[~filled] == -1).all()
+    else:
+        ref_rows, ref_scores, ref_acc = mo.euclidean_topk(Q, G, max(kk, k), threshold, tags, tenant)
+        assert mo.ids_match_with_gap(ref_rows, -ref_scores, r.rows, TOL).all()
+        filled = ref_rows[:, :k] >= 0
+        assert np.abs(r.scores[filled] - ref_scores[:, :k][filled]).max(initial=0) <= TOL
+    # decisions identical except where the oracle score sits within TOL of the threshold
+    near = np.abs(ref_scores[:, 0].astype(np.float64) - threshold) <= TOL
+    assert (r.accept[~near] == ref_acc[~near]).all()
+    return r
+
+
+@pytest.mark.parametrize("dim", [128, 256, 512, 1024])
+def test_device_generator_is_the_cpu_twin(frg, dim):
+    n = 3001
+    store = frg.GalleryStore(dim=dim, capacity=16)           # also exercises growth
+    store.fill_synthetic(n, 7_000_000_123, 99)
+    G, tags = store.read_rows()
+    ref = synth.unit_rows(np.arange(7_000_000_123, 7_000_000_123 + n), dim, 99)
+    assert np.array_equal(G, ref)
+    assert (tags == 0).all()
+    store.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_cfg1_golden(frg, golden, variant):
+    """BASELINE config 1 against the reference's own outputs (tests/golden/cfg1_10k_x_64.npz)."""
+    g = golden("cfg1_10k_x_64.npz")
+    n, f, d = int(g["n"]), int(g["f"]), int(g["dim"])
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.fill_synthetic(n, 0, int(g["gallery_seed"]))
+    Q, _ = synth.queries(f, n, d, int(g["query_seed"]), int(g["gallery_seed"]))
+    r = frg.Matcher(store).match(Q, 1, frg.CAMPUS_THRESHOLD, variant=variant)
+    assert (r.rows[:, 0] == g["ref_best_row"]).all()
+    assert np.abs(r.scores[:, 0] - g["ref_best_score"]).max() <= TOL
+    assert np.abs(r.scores[:, 0] - g["ref_best_score"]).max() <= 2e-6     # what we actually expect
+    # peopleCount three-way decision
+    events, stats = frg.CameraProcessor(store).process(Q)
+    assert [KIND[e[0]] for e in events] == list(g["ref_campus_kind"])
+    assert [stats["faces"], stats["recognized"], stats["unknown"]] == list(g["ref_campus_stats"])
+    rec = g["ref_campus_kind"] == 0
+    assert [e[1] for e, ok in zip(events, rec) if ok] == [hex_ids(n)[i] for i in g["ref_campus_row"][rec]]
+    # infrenceServer decision and reported score
+    live = frg.FaceRecognitionProcessor(store).recognize(Q)
+    got_row = np.array([int(x["person_id"], 16) if x["person_id"] else -1 for x in live])
+    assert (got_row == g["ref_live_row"]).all()
+    assert np.abs(np.array([x["recognition_score"] for x in live], np.float32) - g["ref_live_score"]).max() <= TOL
+    store.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_edge_cases_golden(frg, golden, variant):
+    g = golden("edge_cases.npz")
+    G, Q = g["gallery"], g["queries"]
+    store = frg.GalleryStore(dim=512, capacity=len(G))
+    store.upsert(hex_ids(len(G)), G, prenormalised=True)      # rows exactly as the reference's dict held them
+    Gd, _ = store.read_rows()
+    assert np.array_equal(Gd, G, equal_nan=True)
+    r = frg.Matcher(store).match(Q, 1, frg.CAMPUS_THRESHOLD, variant=variant)
+    assert (r.rows[:, 0] == g["ref_best_row"]).all()          # incl. exact tie -> first row, NaN row never
+    ne = int(g["n_edge"])
+    assert (r.scores[:ne, 0] == g["edge_scores"]).all()       # one non-zero product: exact in any fp32 order
+    events, _ = frg.CameraProcessor(store).process(Q)
+    assert [KIND[e[0]] for e in events] == list(g["ref_campus_kind"])     # >= fp32(0.45), < fp32(0.35) at 1 ulp
+    live = frg.FaceRecognitionProcessor(store).recognize(Q)
+    got_row = np.array([int(x["person_id"], 16) if x["person_id"] else -1 for x in live])
+    assert (got_row == g["ref_live_row"]).all()               # >= fp32(0.4) at 1 ulp
+    # top-3 of the tie query: the identical rows in gallery order
+    r3 = frg.Matcher(store).match(Q[ne:ne + 1], 3, 0.4, variant=variant)
+    assert list(r3.rows[0]) == [ne + 1, ne + 2, ne + 4]
+    store.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_nothing_matches(frg, golden, variant):
+    g = golden("edge_cases.npz")
+    G = g["gallery"][-2:][::-1].copy()                         # antipode (score exactly -1) + NaN row
+    Q = g["queries"][-1:]
+    store = frg.GalleryStore(dim=512, capacity=4)
+    store.upsert(hex_ids(2), G, prenormalised=True)
+    r = frg.Matcher(store).match(Q, 2, 0.45, variant=variant)
+    assert (r.rows == -1).all() and (r.scores == np.float32(-1)).all() and not r.accept.any()
+    events, stats = frg.CameraProcessor(store).process(Q)
+    assert KIND[events[0][0]] == int(g["nomatch_ref_campus_kind"][0])     # -1 < 0.35 -> 'unknown'
+    live = frg.FaceRecognitionProcessor(store).recognize(Q)
+    assert live[0]["person_id"] is None and live[0]["recognition_score"] == 0
+    store.close()
+
+
+def test_empty_gallery_is_not_an_error(frg):
+    store = frg.GalleryStore(dim=512, capacity=0)
+    Q, _ = synth.queries(5, 0, 512)
+    r = frg.Matcher(store).match(Q, 3, 0.4)
+    assert (r.rows == -1).all() and (r.scores == -1).all() and not r.accept.any()
+    assert frg.FaceRecognitionProcessor(store).recognize(Q) == []         # infrenceServer.py:523-525
+    ev, stats = frg.CameraProcessor(store).process(Q)
+    assert ev == [] and stats == {"faces": 0, "recognized": 0, "unknown": 0}   # peopleCount.py:850-851
+    store.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("dim,n,f,k", [(512, 12345, 1, 1), (512, 12345, 2, 5), (512, 40001, 3, 10),
+                                        (512, 40001, 7, 16), (512, 33, 33, 5), (512, 7, 4, 10),
+                                        (128, 50000, 9, 1), (256, 9999, 5, 5), (1024, 5000, 3, 5),
+                                        (512, 100000, 64, 5), (512, 30000, 129, 5), (512, 20000, 300, 10)])
+def test_topk_vs_oracle(frg, variant, dim, n, f, k):
+    store = frg.GalleryStore(dim=dim, capacity=n)
+    store.fill_synthetic(n, 0, 4242)
+    G = synth.gallery(n, dim, 4242)
+    Q, target = synth.queries(f, n, dim, seed=17, gallery_seed=4242)
+    r = check_against_oracle(frg, store, Q, G, k, 0.4, variant=variant)
+    hit = target >= 0
+    assert (r.rows[hit, 0] == target[hit]).all()
+    store.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_raw_vectors_are_normalised_on_ingest(frg, variant):
+    """Templates arrive un-normalised (mean of <= 3 poses, trainingServer.py:355) and queries are
+    re-normalised (infrenceServer.py:532): both divisions happen on the device."""
+    rng = np.random.default_rng(5)
+    n, d = 5000, 512
+    raw = (rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)
+    raw[123] = 0.0                                             # zero template -> NaN row, never matches
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.upsert(hex_ids(n), raw)
+    G = mo.normalise_rows(raw)
+    Gd, _ = store.read_rows()
+    assert np.isnan(Gd[123]).all()
+    assert np.nanmax(np.abs(Gd - G)) <= 2e-7                   # fp32 norm: summation order differs by ulps
+    Q = (raw[[5, 77, 123, 4000]] * 2.5 + 0.01 * rng.standard_normal((4, d))).astype(np.float32)
+    r = check_against_oracle(frg, store, Q, G, 5, 0.4, variant=variant)
+    assert list(r.rows[[0, 1, 3], 0]) == [5, 77, 4000]
+    assert (r.rows != 123).all()
+    store.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_store_semantics_follow_the_dict(frg, variant):
+    """upsert in place / append, remove -> tombstone, re-enrol -> END, tenant filter, compaction:
+    replayed against oracle.GalleryOracle (which tests/test_oracle_golden.py pins to the reference)."""
+    d = 512
+    rng = np.random.default_rng(11)
+    vec = rng.standard_normal((400, d)).astype(np.float32)
+    o = mo.GalleryOracle(d)
+    store = frg.GalleryStore(dim=d, capacity=8)
+    comp = lambda i: "A" if i % 3 else "B"
+
+    def both_upsert(idx, src):
+        ids = ["p%03d" % i for i in idx]
+        store.upsert(ids, vec[src], [comp(i) for i in idx])
+        for i, s in zip(idx, src):
+            o.upsert("p%03d" % i, vec[s], store.tenant_code(comp(i)))
+
+    def both_remove(idx):
+        store.remove(["p%03d" % i for i in idx])
+        for i in idx:
+            o.remove("p%03d" % i)
+
+    def compare():
+        ids, G, tags = o.snapshot()
+        sids, sG, stags = store.snapshot_arrays()
+        assert sids == ids
+        assert np.nanmax(np.abs(sG - G), initial=0) <= 2e-7
+        assert (stags == tags).all()
+        Q = (vec[[3, 10, 150, 299, 57]] + 0.05 * rng.standard_normal((5, d))).astype(np.float32)
+        rows_all, _, stags_all = None, None, None
+        allG, alltags = store.read_rows()
+        Gn = allG.copy()
+        for tenant, company in ((None, None), (store.tenant_code("A"), "A"), (store.tenant_code("B"), "B")):
+            check_against_oracle(frg, store, Q, Gn, 5, 0.4, tags=alltags, tenant=tenant, company=company,
+                                 variant=variant)
+        r = frg.Matcher(store).match(Q, 1, 0.4, variant=variant)
+        ref_names, _, _ = o.match(Q, 1, 0.4)
+        assert [x[0] for x in r.ids] == [x[0] for x in ref_names]
+
+    both_upsert(list(range(200)), list(range(200)))
+    compare()
+    both_upsert([10, 57, 150, 205, 206], [300, 301, 302, 303, 304])     # 3 in place, 2 appended
+    compare()
+    both_remove([3, 57, 199, 0])
+    compare()
+    both_upsert([57, 3], [57, 3])                                        # come back at the END
+    compare()
+    assert store.row_of("p057") == 202 and store.row_of("p003") == 203
+    st = store.stats()
+    assert st.rows == 204 and st.live == 202
+    store.compact()
+    st = store.stats()
+    assert st.rows == 202 and st.live == 202
+    compare()
+    assert frg.Matcher(store).match(vec[:1], 1, 0.4, company_id="nobody").rows[0, 0] == -1
+    store.close()
+
+
+def test_embedding_manager_replays_reference_scenario(frg, golden):
+    """tests/golden/managers.npz: ids order and loaded matrices of BOTH reference managers."""
+    from datetime import datetime, timedelta
+    g = golden("managers.npz")
+    st = g["stored"]
+    A, B = "a" * 24, "b" * 24
+    t0 = datetime(2026, 1, 1)
+
+    def emp(i):
+        return {"_id": "%024x" % i, "embedding": st[i], "companyId": A if i < 8 or i >= 12 else B, "status": "active",
+                "blacklisted": False, "lastUpdated": t0, "employeeName": "e%d" % i}
+
+    def vis(i):
+        return {"_id": "%024x" % (100 + i), "embedding": st[20 + i], "companyId": A if i < 3 else B,
+                "lastUpdated": t0, "visitorName": "v%d" % i}
+
+    def scenario():
+        E = [emp(i) for i in range(12)]
+        E[3]["status"] = "inactive"; E[5]["blacklisted"] = True; E[6]["embedding_status"] = "pending"
+        V = [vis(i) for i in range(6)]
+        V[4]["embedding_status"] = "pending"
+        return E, V
+
+    def same(mgr, prefix):
+        ids, G, _ = mgr.store.snapshot_arrays()
+        assert ids == list(g[prefix + "_ids"])
+        ref = g[prefix + "_G"]
+        assert (np.isnan(G) == np.isnan(ref)).all()
+        assert np.nanmax(np.abs(G - ref)) <= 2e-7
+
+    E, V = scenario()
+    src = frg.ListSource(E, V)
+    m = frg.EmbeddingManager(src, mode="live")
+    same(m, "ref_live_load")
+    s = m.get_stats()
+    assert [s["total_embeddings"], s["employees"], s["visitors"]] == list(g["ref_live_load_stats"])
+    assert s["initial_load_complete"] and s["last_sync"]
+    later = datetime.utcnow() + timedelta(seconds=5)
+    E[1]["embedding"] = st[30]; E[1]["lastUpdated"] = later
+    E[0]["status"] = "inactive"
+    E.append(dict(emp(12), lastUpdated=later))
+    V[1]["embedding"] = st[31]; V[1]["lastUpdated"] = later
+    E[3]["status"] = "active"; E[3]["lastUpdated"] = later
+    m.force_sync()
+    same(m, "ref_live_sync1")
+    E[0]["status"] = "active"; E[0]["lastUpdated"] = datetime.utcnow() + timedelta(seconds=10)
+    m.force_sync()
+    same(m, "ref_live_sync2")
+    ids, _, tags = m.store.snapshot_arrays()
+    for comp, key in ((A, "ref_live_tenant_a"), (B, "ref_live_tenant_b")):
+        code = m.store.tenant_code(comp)
+        assert sorted(i for i, t in zip(ids, tags) if t == code) == list(g[key])
+        view = m.get_embeddings_for_company(comp)
+        out = frg.FaceRecognitionProcessor(view.store).recognize(g["mgr_queries"], view.company_id)
+        tag = "a" if comp == A else "b"
+        assert [x["person_id"] is not None for x in out] == list(g["ref_live_match_%s_known" % tag])
+        assert np.abs(np.array([x["recognition_score"] for x in out], np.float32)
+                      - g["ref_live_match_%s_score" % tag]).max() <= TOL
+    m.store.close()
+
+    E, V = scenario()
+    mb = frg.EmbeddingManager(frg.ListSource(E, V), mode="campus")
+    same(mb, "ref_campus_load")
+    E[1]["embedding"] = st[30]
+    E[0]["status"] = "inactive"
+    E.append(emp(12))
+    mb.force_sync()
+    same(mb, "ref_campus_sync1")
+    assert mb.get_all().company_id is None
+    mb.store.close()
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_euclidean_128d(frg, k):
+    """BASELINE config 3 (ours; parity unpinned by the reference): d = ||g - q||_2, smallest wins."""
+    rng = np.random.default_rng(3)
+    n, d = 30000, 128
+    G = (rng.standard_normal((n, d)) * 0.1).astype(np.float32)
+    Q = (G[[5, 999, 12345]] + 0.02 * rng.standard_normal((3, d))).astype(np.float32)
+    Q = np.concatenate([Q, (rng.standard_normal((2, d)) * 0.1).astype(np.float32)])
+    store = frg.GalleryStore(dim=d, capacity=n, raw=True)
+    store.append_rows(G)
+    Gd, _ = store.read_rows()
+    assert np.array_equal(Gd, G)
+    r = check_against_oracle(frg, store, Q, G, k, 0.6, metric="euclidean", variant="scan_f32")
+    assert list(r.rows[:3, 0]) == [5, 999, 12345]
+    assert r.accept[:3].all() and not r.accept[3:].any()
+    store.close()
+
+
+def test_device_pointer_entry_point_and_streams(frg):
+    """frg_match with device buffers on a non-default stream, interleaved with updates (config 5:
+    online enrol/update between batches): each match sees the store as of its call."""
+    import torch
+    n, d = 20000, 512
+    store = frg.GalleryStore(dim=d, capacity=n + 64)
+    store.fill_synthetic(n, 0, 1234)
+    G = synth.gallery(n, d)
+    Q, _ = synth.queries(32, n, d)
+    new = synth.unit_rows(np.arange(3), d, 555, synth.STREAM_IMPOSTOR)
+    Q[1], Q[3], Q[5] = new[0], new[1], new[2]
+    m = frg.Matcher(store)
+    s = torch.cuda.Stream()
+    Qd = torch.from_numpy(Q).cuda()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        before = m.match_device(Qd, 1, 0.45)
+    store.upsert(["new0", "new1", "new2"], new)                      # host entry point, default stream
+    with torch.cuda.stream(s):
+        after = m.match_device(Qd, 1, 0.45)
+    store.remove(["new1"])
+    with torch.cuda.stream(s):
+        final = m.match_device(Qd, 1, 0.45)
+    torch.cuda.synchronize()
+    b, a, f = (x[2].cpu().numpy().astype(bool) for x in (before, after, final))
+    assert not b[[1, 3, 5]].any() and a[[1, 3, 5]].all() and list(f[[1, 3, 5]]) == [True, False, True]
+    assert list(after[0].cpu().numpy()[[1, 3, 5], 0]) == [n, n + 1, n + 2]
+    ref_rows, ref_scores, ref_acc = mo.match_topk(Q, G, 1, 0.45)
+    assert (before[0].cpu().numpy()[:, 0] == ref_rows[:, 0]).all()
+    store.close()
+
+
+def test_merge_topk_equals_unsharded(frg):
+    """Row-sharded match (each shard its own store + row_offset) folded by frg_merge_topk equals the
+    single-store result - the single-GPU emulation of SURVEY.md section 8e."""
+    import ctypes as C
+    import torch
+    N_ = frg._native
+    n, d, f, k, parts = 30000, 512, 40, 10, 4
+    G = synth.gallery(n, d)
+    G[20000] = G[100]                                             # a tie that straddles two shards
+    Q, _ = synth.queries(f, n, d)
+    Q[0] = G[100]
+    whole = frg.GalleryStore(dim=d, capacity=n)
+    whole.append_rows(G, prenormalised=True)
+    ref = frg.Matcher(whole).match(Q, k, 0.4)
+    bounds = [0, 7000, 7001, 19999, n]
+    scores = torch.empty((parts, f, k), dtype=torch.float32, device="cuda")
+    rows = torch.empty((parts, f, k), dtype=torch.int64, device="cuda")
+    stores = []
+    for p in range(parts):
+        st = frg.GalleryStore(dim=d, capacity=n)
+        st.append_rows(G[bounds[p]:bounds[p + 1]], prenormalised=True)
+        r = frg.Matcher(st).match(Q, k, 0.4, row_offset=bounds[p])
+        rows[p] = torch.from_numpy(r.rows).cuda()
+        scores[p] = torch.from_numpy(r.scores).cuda()
+        stores.append(st)
+    out_r = torch.empty((f, k), dtype=torch.int64, device="cuda")
+    out_s = torch.empty((f, k), dtype=torch.float32, device="cuda")
+    out_a = torch.empty((f,), dtype=torch.uint8, device="cuda")
+    N_.check(N_.lib.frg_merge_topk(0, C.c_void_p(scores.data_ptr()), C.c_void_p(rows.data_ptr()), parts, f, k,
+                                   N_.METRIC_COSINE, np.float32(0.4), C.c_void_p(out_r.data_ptr()),
+                                   C.c_void_p(out_s.data_ptr()), C.c_void_p(out_a.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert (out_r.cpu().numpy() == ref.rows).all()
+    assert (out_s.cpu().numpy() == ref.scores).all()
+    assert (out_a.cpu().numpy().astype(bool) == ref.accept).all()
+    assert list(ref.rows[0, :2]) == [100, 20000]
+    for st in stores + [whole]:
+        st.close()
+
+
+def test_full_size_1m_gallery(frg):
+    """BASELINE config 2 at full size (1 M x 512): rows/scores against a numpy sgemm oracle on the
+    device-generated gallery copied back, plus size-independent properties."""
+    n, d, k = 1_000_000, 512, 5
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.fill_synthetic(n, 0, synth.GALLERY_SEED)
+    # spot-check the generator at full size
+    probe = np.array([0, 1, 31, 65535, 65536, 499_999, 999_999])
+    for r0 in probe:
+        v, _ = store.read_rows(int(r0), 1)
+        assert np.array_equal(v[0], synth.unit_rows([r0], d)[0])
+    Q, target = synth.queries(64, n, d)
+    G, _ = store.read_rows()
+    for variant in VARIANTS:
+        r = check_against_oracle(frg, store, Q, G, k, 0.45, variant=variant)
+        hit = target >= 0
+        assert (r.rows[hit, 0] == target[hit]).all() and r.accept[hit].all() and not r.accept[~hit].any()
+        # property: a gallery row queried against the gallery finds itself with score 1 (+- 1e-6)
+        self_q = G[[0, 123_456, 999_999]]
+        rs = frg.Matcher(store).match(self_q, 1, 0.45, variant=variant)
+        assert list(rs.rows[:, 0]) == [0, 123_456, 999_999] and np.abs(rs.scores[:, 0] - 1).max() < 2e-6
+        # property: top-k scores are non-increasing and rows distinct
+        assert (np.diff(r.scores, axis=1) <= 0).all()
+        assert all(len(set(x)) == k for x in r.rows)
+    store.close()
