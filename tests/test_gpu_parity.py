@@ -206,9 +206,7 @@ def test_store_semantics_follow_the_dict(frg, variant):
         assert np.nanmax(np.abs(sG - G), initial=0) <= 2e-7
         assert (stags == tags).all()
         Q = (vec[[3, 10, 150, 299, 57]] + 0.05 * rng.standard_normal((5, d))).astype(np.float32)
-        rows_all, _, stags_all = None, None, None
-        allG, alltags = store.read_rows()
-        Gn = allG.copy()
+        Gn, alltags = store.read_rows()
         for tenant, company in ((None, None), (store.tenant_code("A"), "A"), (store.tenant_code("B"), "B")):
             check_against_oracle(frg, store, Q, Gn, 5, 0.4, tags=alltags, tenant=tenant, company=company,
                                  variant=variant)
@@ -226,10 +224,10 @@ def test_store_semantics_follow_the_dict(frg, variant):
     compare()
     assert store.row_of("p057") == 202 and store.row_of("p003") == 203
     st = store.stats()
-    assert st.rows == 204 and st.live == 202
+    assert st.rows == 204 and st.live == 200          # 202 rows ever appended + 2 re-enrolled, 4 tombstones
     store.compact()
     st = store.stats()
-    assert st.rows == 202 and st.live == 202
+    assert st.rows == 200 and st.live == 200
     compare()
     assert frg.Matcher(store).match(vec[:1], 1, 0.4, company_id="nobody").rows[0, 0] == -1
     store.close()
