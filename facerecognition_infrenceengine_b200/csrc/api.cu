@@ -416,9 +416,68 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
 
 // --------------------------------------------------------------------------------------------- match
 static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq) {
-  (void)s; (void)nq;
+  const char* why = "";
+  const bool tc_ok = s->plane != nullptr && tc_supported(s->dim, p->metric, &why);
   if (p->variant != FRG_VARIANT_AUTO) return p->variant;
-  return FRG_VARIANT_SCAN_F32;
+  // dispatch table: the tensor-core filter reads 2 B/element instead of 4 and wins from
+  // the smallest batches on; the exact scan remains for galleries without a scan plane, for the
+  // Euclidean metric and for dims the tile shapes do not cover.
+  (void)nq;
+  return tc_ok ? FRG_VARIANT_TC_EXACT : FRG_VARIANT_SCAN_F32;
+}
+
+static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, int sm_count,
+                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+  ScanArgs a;
+  a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
+  a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = sm_count;
+  size_t part_bytes = 0;
+  FRG_CHECK(scan_f32_workspace_bytes(a, &part_bytes));
+  const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
+  unsigned char* ws = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + part_bytes, st));
+  float* qn = reinterpret_cast<float*>(ws);
+  a.qn = qn;
+  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE, qn, nullptr, st);
+  if (rc == FRG_OK)
+    rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
+  g_variant = "scan_f32";
+  cudaError_t e = cudaFreeAsync(ws, st);
+  if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
+  return rc;
+}
+
+static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, bool rescore,
+                    int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+  const char* why = "";
+  if (!s->plane) { set_error("match: the store was created without FRG_STORE_BF16_PLANE"); return FRG_ERR_UNSUPPORTED; }
+  if (!tc_supported(s->dim, p->metric, &why)) { set_error("match: %s", why); return FRG_ERR_UNSUPPORTED; }
+  if (s->rows > 0x7fffffff) { set_error("match: more than 2^31-1 rows in one shard"); return FRG_ERR_UNSUPPORTED; }
+  if (s->rows == 0) return match_scan(s, q, nq, k, p, sm_count, out_rows, out_scores, out_accept, st);
+  const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
+  const size_t qb_bytes = (size_t(nq) * s->dim * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
+  const size_t tc_bytes = tc_workspace_bytes(s->rows, s->dim, nq, k, sm_count);
+  unsigned char* ws = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + tc_bytes, st));
+  float* qn = reinterpret_cast<float*>(ws);
+  __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes);
+  int* flagged = nullptr; int* n_flagged = nullptr;
+  int rc = launch_normalise_queries(q, nq, s->dim, true, qn, qb, st);
+  if (rc == FRG_OK)
+    rc = launch_tc_match(s, qn, qb, nq, k, p->tenant, rescore, p->threshold, p->row_offset, ws + qn_bytes + qb_bytes,
+                         sm_count, out_rows, out_scores, out_accept, &flagged, &n_flagged, st);
+  if (rc == FRG_OK) {
+    // queries whose candidate lists overflowed are redone exactly, inside the same enqueue
+    ScanArgs a;
+    a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
+    a.qn = qn; a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = sm_count;
+    rc = launch_scan_f32_flagged(a, flagged, n_flagged, p->row_offset, p->threshold, out_rows, out_scores,
+                                 out_accept, st);
+  }
+  g_variant = rescore ? "tc_exact" : "tc_bf16";
+  cudaError_t e = cudaFreeAsync(ws, st);
+  if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
+  return rc;
 }
 
 int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
@@ -437,30 +496,17 @@ int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_mat
   std::lock_guard<std::mutex> lk(s->mu);   // enqueue under the lock: the snapshot a match sees is the
                                            // store as of this call (peopleCount.py:816-819 semantics)
   FRG_CHECK(store_begin_read(s, st));
-  const int variant = pick_variant(s, p, nq);
-  if (variant != FRG_VARIANT_SCAN_F32) {
-    set_error("match: variant %d not built in this library", variant);
-    return FRG_ERR_UNSUPPORTED;
+  switch (pick_variant(s, p, nq)) {
+    case FRG_VARIANT_SCAN_F32:
+      return match_scan(s, q, nq, k, p, di.sm_count, out_rows, out_scores, out_accept, st);
+    case FRG_VARIANT_TC_EXACT:
+      return match_tc(s, q, nq, k, p, true, di.sm_count, out_rows, out_scores, out_accept, st);
+    case FRG_VARIANT_TC_BF16:
+      return match_tc(s, q, nq, k, p, false, di.sm_count, out_rows, out_scores, out_accept, st);
+    default:
+      set_error("match: unknown variant %d", p->variant);
+      return FRG_ERR_INVALID;
   }
-
-  ScanArgs a;
-  a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
-  a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = di.sm_count;
-  size_t part_bytes = 0;
-  FRG_CHECK(scan_f32_workspace_bytes(a, &part_bytes));
-  const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
-  unsigned char* ws = nullptr;
-  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + part_bytes, st));
-  float* qn = reinterpret_cast<float*>(ws);
-  a.qn = qn;
-  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE, qn, nullptr, st);
-  if (rc == FRG_OK)
-    rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
-  note_launch("scan_f32");
-  --g_launches;  // note_launch above only records the variant name
-  cudaError_t e = cudaFreeAsync(ws, st);
-  if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
-  return rc;
 }
 
 int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,

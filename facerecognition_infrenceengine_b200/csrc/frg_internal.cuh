@@ -104,6 +104,11 @@ int scan_f32_workspace_bytes(const ScanArgs& a, size_t* bytes);
 int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, float threshold,
                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
+// scan_f32.cu: exact re-do of the queries listed on the device (tensor-core candidate overflow)
+int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, const int* n_flagged, int64_t row_offset,
+                            float threshold, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
+                            cudaStream_t st);
+
 // merge.cu: generic k-way merge of sorted partial lists
 int launch_merge_i64(const float* scores, const int64_t* rows, int parts, int nq, int k_in, int k_out,
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
@@ -111,6 +116,18 @@ int launch_merge_i64(const float* scores, const int64_t* rows, int parts, int nq
 int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq, int k_in, int k_out,
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
+
+int launch_merge_flagged(const float* scores, const int32_t* rows, int parts, int nq, int k, float threshold,
+                         int64_t row_offset, const int* q_index, const int* n_active, int64_t* out_rows,
+                         float* out_scores, uint8_t* out_accept, cudaStream_t st);
+
+// tc_match.cu: tcgen05 filter + exact rescoring (cosine, dim multiple of 64 and <= 512)
+int tc_supported(int dim, int metric, const char** why);
+size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count);
+int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
+                    bool rescore, float threshold, int64_t row_offset, unsigned char* ws, int sm_count,
+                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,
+                    int** n_flagged_out, cudaStream_t st);
 
 // store_kernels.cu
 int launch_ingest(const float* vecs, const int64_t* rows, const int32_t* tags, int64_t n, int64_t append_at,

@@ -24,11 +24,15 @@ template <typename RowT, int KMAX>
 __global__ void __launch_bounds__(128)
 merge_kernel(const float* __restrict__ scores, const RowT* __restrict__ rows, int parts, int nq,
              int k_in, int k_out, int metric, float threshold, int64_t row_offset, int internal_euclid,
+             const int* __restrict__ q_index, const int* __restrict__ n_active,
              int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
              uint8_t* __restrict__ out_accept) {
   const int lane = threadIdx.x & 31;
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= nq) return;
+  // `slot` addresses the partial lists; with an index list (flagged queries) it differs from the
+  // query the result belongs to
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= nq || (n_active && slot >= *n_active)) return;
+  const int q = q_index ? q_index[slot] : slot;
   const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
   const float sentinel = euclid ? -INFINITY : kNoScore;
 
@@ -40,7 +44,7 @@ merge_kernel(const float* __restrict__ scores, const RowT* __restrict__ rows, in
   const int total = parts * k_in;
   for (int c = lane; c < total; c += 32) {
     const int part = c / k_in, j = c - part * k_in;
-    const size_t off = (size_t(part) * nq + q) * k_in + j;
+    const size_t off = (size_t(part) * nq + slot) * k_in + j;
     const RowT r = rows[off];
     if (r < 0 || r == RowLimits<RowT>::none()) continue;
     float s = scores[off];
@@ -95,13 +99,13 @@ merge_kernel(const float* __restrict__ scores, const RowT* __restrict__ rows, in
 template <typename RowT>
 static int launch_merge(const float* scores, const RowT* rows, int parts, int nq, int k_in, int k_out,
                         int metric, float threshold, int64_t row_offset, bool internal_euclid,
-                        int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+                        const int* q_index, const int* n_active, int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
   if (nq <= 0) return FRG_OK;
   if (k_out < 1 || k_out > FRG_MAX_K || k_in < 1) { set_error("merge: k out of range"); return FRG_ERR_INVALID; }
   const int grid = (nq + 3) / 4;
   const int ie = internal_euclid ? 1 : 0;
 #define FRG_MERGE(K) merge_kernel<RowT, K><<<grid, 128, 0, st>>>(scores, rows, parts, nq, k_in, k_out, metric, \
-      threshold, row_offset, ie, out_rows, out_scores, out_accept)
+      threshold, row_offset, ie, q_index, n_active, out_rows, out_scores, out_accept)
   if (k_out == 1) FRG_MERGE(1);
   else if (k_out <= 4) FRG_MERGE(4);
   else if (k_out <= 8) FRG_MERGE(8);
@@ -116,14 +120,21 @@ int launch_merge_i64(const float* scores, const int64_t* rows, int parts, int nq
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
   return launch_merge<int64_t>(scores, rows, parts, nq, k_in, k_out, metric, threshold, row_offset,
-                               finalize_euclid, out_rows, out_scores, out_accept, st);
+                               finalize_euclid, nullptr, nullptr, out_rows, out_scores, out_accept, st);
 }
 
 int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq, int k_in, int k_out,
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
   return launch_merge<int32_t>(scores, rows, parts, nq, k_in, k_out, metric, threshold, row_offset,
-                               finalize_euclid, out_rows, out_scores, out_accept, st);
+                               finalize_euclid, nullptr, nullptr, out_rows, out_scores, out_accept, st);
+}
+
+int launch_merge_flagged(const float* scores, const int32_t* rows, int parts, int nq, int k, float threshold,
+                         int64_t row_offset, const int* q_index, const int* n_active, int64_t* out_rows,
+                         float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+  return launch_merge<int32_t>(scores, rows, parts, nq, k, k, FRG_METRIC_COSINE, threshold, row_offset, false,
+                               q_index, n_active, out_rows, out_scores, out_accept, st);
 }
 
 }  // namespace frg

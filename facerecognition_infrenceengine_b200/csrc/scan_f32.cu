@@ -96,17 +96,14 @@ __device__ __forceinline__ void list_insert(float* sc, int32_t* ix, int K, float
   sc[t] = s; ix[t] = row;
 }
 
+// One pass over the gallery for the queries q_of[0..nq_pass): fills part_[sc|ix][(block*part_stride + part_q0 + b)*K ..].
 template <int NJ, int QB, int METRIC>
-__global__ void __launch_bounds__(kScanWarps * 32, 2)
-scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
-                const float* __restrict__ qn, int nq_total, int q0, int nq_pass, int K, int32_t tenant,
-                float* __restrict__ part_sc, int32_t* __restrict__ part_ix) {
+__device__ __forceinline__ void scan_pass(const float* __restrict__ master, const int32_t* __restrict__ tags,
+                                          int64_t rows, const float* __restrict__ qn, const int (&q_of)[QB],
+                                          int nq_pass, int part_stride, int part_q0, int K, int32_t tenant,
+                                          float* __restrict__ part_sc, int32_t* __restrict__ part_ix,
+                                          float* l_sc, int32_t* l_ix) {
   constexpr int DIM = NJ * 128;
-  extern __shared__ unsigned char smem_raw[];
-  // [warp][query][K]
-  float* l_sc = reinterpret_cast<float*>(smem_raw);
-  int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float sentinel = METRIC == FRG_METRIC_COSINE ? kNoScore : -INFINITY;
@@ -119,7 +116,7 @@ scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ ta
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       q[b][j] = (b < nq_pass)
-                    ? __ldg(reinterpret_cast<const float4*>(qn + size_t(q0 + b) * DIM) + j * 32 + lane)
+                    ? __ldg(reinterpret_cast<const float4*>(qn + size_t(q_of[b]) * DIM) + j * 32 + lane)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -177,8 +174,8 @@ scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ ta
     int head[kScanWarps];
 #pragma unroll
     for (int w = 0; w < kScanWarps; ++w) head[w] = 0;
-    float* o_sc = part_sc + (size_t(blockIdx.x) * nq_total + q0 + b) * K;
-    int32_t* o_ix = part_ix + (size_t(blockIdx.x) * nq_total + q0 + b) * K;
+    float* o_sc = part_sc + (size_t(blockIdx.x) * part_stride + part_q0 + b) * K;
+    int32_t* o_ix = part_ix + (size_t(blockIdx.x) * part_stride + part_q0 + b) * K;
     for (int j = 0; j < K; ++j) {
       float bs = sentinel; int32_t br = 0x7fffffff; int bw = -1;
 #pragma unroll
@@ -194,6 +191,45 @@ scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ ta
       o_sc[j] = bs;
       o_ix[j] = (br == 0x7fffffff) ? -1 : br;
     }
+  }
+}
+
+template <int NJ, int QB, int METRIC>
+__global__ void __launch_bounds__(kScanWarps * 32, 2)
+scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
+                const float* __restrict__ qn, int nq_total, int q0, int nq_pass, int K, int32_t tenant,
+                float* __restrict__ part_sc, int32_t* __restrict__ part_ix) {
+  extern __shared__ unsigned char smem_raw[];
+  float* l_sc = reinterpret_cast<float*>(smem_raw);                          // [warp][query][K]
+  int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
+  int q_of[QB];
+#pragma unroll
+  for (int b = 0; b < QB; ++b) q_of[b] = q0 + b;
+  scan_pass<NJ, QB, METRIC>(master, tags, rows, qn, q_of, nq_pass, nq_total, q0, K, tenant, part_sc, part_ix,
+                            l_sc, l_ix);
+}
+
+// Exact re-do of the queries a tensor-core pass could not settle (candidate overflow).  The list
+// and its length live on the device; the kernel loops over it, so nothing waits for the host and an
+// empty list costs one idle launch.
+template <int NJ, int QB, int METRIC>
+__global__ void __launch_bounds__(kScanWarps * 32, 2)
+scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
+                        const float* __restrict__ qn, int nq_total, const int* __restrict__ flagged,
+                        const int* __restrict__ n_flagged, int K, int32_t tenant,
+                        float* __restrict__ part_sc, int32_t* __restrict__ part_ix) {
+  extern __shared__ unsigned char smem_raw[];
+  float* l_sc = reinterpret_cast<float*>(smem_raw);
+  int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
+  const int nf = *n_flagged;
+  for (int q0 = 0; q0 < nf; q0 += QB) {
+    const int nq_pass = nf - q0 < QB ? nf - q0 : QB;
+    int q_of[QB];
+#pragma unroll
+    for (int b = 0; b < QB; ++b) q_of[b] = b < nq_pass ? flagged[q0 + b] : 0;
+    scan_pass<NJ, QB, METRIC>(master, tags, rows, qn, q_of, nq_pass, nq_total, q0, K, tenant, part_sc, part_ix,
+                              l_sc, l_ix);
+    __syncthreads();
   }
 }
 
@@ -278,6 +314,42 @@ int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, floa
   return launch_merge_i32(part_sc, part_ix, grid, a.nq, a.k, a.k, a.metric, threshold, row_offset,
                           /*finalize_euclid=*/a.metric == FRG_METRIC_EUCLIDEAN, out_rows, out_scores,
                           out_accept, st);
+}
+
+template <int NJ, int QB>
+static int launch_flagged_t(const ScanArgs& a, int grid, const int* flagged, const int* n_flagged, float* ps,
+                            int32_t* pi, cudaStream_t st) {
+  const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
+  scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE><<<grid, kScanWarps * 32, smem, st>>>(
+      a.master, a.tags, a.rows, a.qn, a.nq, flagged, n_flagged, a.k, a.tenant, ps, pi);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, const int* n_flagged, int64_t row_offset,
+                            float threshold, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
+                            cudaStream_t st) {
+  if (a.rows <= 0 || a.nq <= 0) return FRG_OK;
+  const int grid = a.sm_count;       // partial lists are sized for the worst case (every query flagged)
+  const size_t n_part = size_t(grid) * a.nq * a.k;
+  unsigned char* ws = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), n_part * 8, st));
+  float* ps = reinterpret_cast<float*>(ws);
+  int32_t* pi = reinterpret_cast<int32_t*>(ps + n_part);
+  int rc;
+  switch (a.dim) {
+    case 128: rc = launch_flagged_t<1, 4>(a, grid, flagged, n_flagged, ps, pi, st); break;
+    case 256: rc = launch_flagged_t<2, 4>(a, grid, flagged, n_flagged, ps, pi, st); break;
+    case 512: rc = launch_flagged_t<4, 4>(a, grid, flagged, n_flagged, ps, pi, st); break;
+    default: set_error("flagged scan: dim %d not built", a.dim); rc = FRG_ERR_UNSUPPORTED; break;
+  }
+  if (rc == FRG_OK)
+    rc = launch_merge_flagged(ps, pi, grid, a.nq, a.k, threshold, row_offset, flagged, n_flagged, out_rows,
+                              out_scores, out_accept, st);
+  cudaError_t e = cudaFreeAsync(ws, st);
+  if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
+  return rc;
 }
 
 }  // namespace frg

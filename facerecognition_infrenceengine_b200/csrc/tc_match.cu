@@ -1,0 +1,656 @@
+// Tensor-core variants (FRG_VARIANT_TC_EXACT / FRG_VARIANT_TC_BF16): the query x gallery contraction
+// on tcgen05 with the threshold / top-k in the epilogue, so no score matrix reaches HBM.
+//
+//   S[q, r] = sum_k Qb[q, k] * Gb[r, k]        Qb, Gb = bf16 images of the unit fp32 vectors
+//
+// The bf16 product is only a FILTER.  |S - s| <= eps = 4e-3 rigorously for unit vectors (each side
+// rounds to bf16: 2^-9 relative per vector, plus fp32 accumulation), so every row of the true
+// top-k has S >= tau - 2*eps, tau = k-th best coarse score.  Pipeline per batch:
+//
+//   1. pre-pass  (tc_scan_kernel<TOPK>)   over a 1/stride strided view of the scan plane: per-query
+//      running top-k of coarse scores -> L[q] = its k-th best, a lower bound of tau.
+//   2. filter    (tc_scan_kernel<FILTER>) over the whole plane: append every (row, S) with
+//      S >= L[q] - 2*eps to the query's candidate list (a few hundred rows out of 10^6).
+//   3. select + rescore (select_rescore_kernel): tau from the candidates, keep S >= tau - 2*eps,
+//      recompute those few scores EXACTLY in fp32 from the master rows (same arithmetic as the
+//      streaming scan), order by (score desc, row asc), apply the threshold.
+//   4. queries whose lists overflowed (adversarial duplicates, sparse tenants) are re-done by the
+//      exact streaming scan inside the same enqueue (fallback_* kernels) - never by the host.
+//
+// Kernel anatomy (one CTA per SM, 192 threads):
+//   warp 0   TMA producer: gallery tiles [128 rows x 64 k] bf16, 128B-swizzled, 6-stage mbarrier ring
+//   warp 1   MMA issuer: one elected lane, tcgen05.mma cta_group::1 kind::f16, M=128 (queries) x N=128
+//            (gallery rows) x K=16, A = the query tile resident in smem (128 x 512 bf16 = 128 KB),
+//            B = the staged gallery tile; accumulators in TMEM, double buffered (2 x 128 columns)
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns; thread = one query, columns = gallery rows:
+//            a running max against the query's threshold (1 FMNMX per score), rare slow path.
+// The gallery is read once per 128-query tile: algorithmic bytes = rows * dim * 2 per launch and
+// query tile; flops = 2 * 128 * rows * dim.
+#include <cuda.h>
+
+#include "frg_internal.cuh"
+
+namespace frg {
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// A broken pipeline must abort the kernel, not hang the GPU: bounded spin, then trap.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+// Field layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | swizzle [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+
+// ------------------------------------------------------------------------------------------ shapes
+constexpr int kTileQ = 128;          // UMMA M: queries per CTA tile (TMEM lanes)
+constexpr int kTileR = 128;          // UMMA N: gallery rows per accumulator (TMEM columns)
+constexpr int kBlockK = 64;          // one 128-byte swizzle row of bf16
+constexpr int kStages = 6;
+constexpr int kStageBytes = kTileR * kBlockK * 2;          // 16 KB
+constexpr int kTcThreads = 192;
+constexpr int kTmemCols = 2 * kTileR;                      // double-buffered accumulator
+constexpr float kCoarseEps = 4e-3f;                        // |bf16 filter score - fp32 score| bound
+// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTileR >> 3) << 17) |
+                            (uint32_t(kTileQ >> 4) << 24);
+
+enum TcMode { kModeTopK = 0, kModeFilter = 1 };
+
+struct TcScanParams {
+  int dim;                 // 512 etc. (multiple of 64)
+  int n_view_rows;         // rows of the (possibly strided) view
+  int row_scale;           // real row = view row * row_scale
+  int nq;                  // real queries
+  int k;                   // list length (TOPK) / unused (FILTER)
+  int32_t tenant;
+  const int32_t* tags;     // per REAL row
+  // TOPK outputs: [chunk][nq][k]
+  float* part_sc;
+  int32_t* part_ix;
+  // FILTER inputs / outputs
+  const float* floor_sc;   // [nq][k_floor] pre-pass lists; L = entry k_floor-1
+  int k_floor;
+  int cap;                 // candidate slots per query
+  int* cand_count;         // [nq]
+  int2* cand;              // [nq][cap] (row, score bits)
+};
+
+template <int K>
+__device__ __forceinline__ void reg_insert(float (&sc)[K], int32_t (&ix)[K], float s, int32_t row) {
+  sc[K - 1] = s; ix[K - 1] = row;
+#pragma unroll
+  for (int t = K - 1; t > 0; --t) {
+    if (sc[t] > sc[t - 1]) {       // strict: among equal scores the earlier (lower) row stays ahead
+      float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
+      int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
+    }
+  }
+}
+
+template <int MODE, int K>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map,
+               const TcScanParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 128B swizzle wants 1024-byte aligned tiles
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* sm = smem_raw + (base - raw);
+  const int kblocks = p.dim / kBlockK;
+  const uint32_t q_bytes = uint32_t(kTileQ) * p.dim * 2;            // resident query tile
+  const uint32_t q_smem = base;
+  const uint32_t stage_smem = base + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + q_bytes + kStages * kStageBytes);
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
+  auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+  const uint32_t bar_q = bar0 + 8u * (2 * kStages + 4);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x;
+  const int chunk = blockIdx.y, chunks = gridDim.y;
+  const int tiles_total = (p.n_view_rows + kTileR - 1) / kTileR;
+  const int tile_begin = int((int64_t(tiles_total) * chunk) / chunks);
+  const int tile_end = int((int64_t(tiles_total) * (chunk + 1)) / chunks);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 4); }
+    mbar_init(bar_q, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&q_map);
+      tma_prefetch_desc(&g_map);
+      mbar_expect_tx(bar_q, q_bytes);
+      for (int kb = 0; kb < kblocks; ++kb)
+        tma_load_2d(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_empty(stage), phase ^ 1);
+          mbar_expect_tx(bar_full(stage), kStageBytes);
+          tma_load_2d(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK, t * kTileR,
+                      gridDim.x > 1 ? kEvictLast : kEvictFirst);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      int buf = 0; uint32_t tphase = 0;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        mbar_wait(bar_tempty(buf), tphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * kTileR);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_full(stage), phase);
+          tc_fence_after();
+          const uint64_t a0 = umma_desc_sw128(q_smem + kb * (kTileQ * kBlockK * 2));
+          const uint64_t b0 = umma_desc_sw128(stage_smem + stage * kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty(stage));                 // smem slot reusable once these MMAs retire
+          if (kb == kblocks - 1) umma_commit(bar_tfull(buf));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: thread = query (TMEM lane), columns = gallery rows =====
+    const int quarter = warp & 3;                        // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+    const int q_local = quarter * 32 + lane;
+    const int q = qtile * kTileQ + q_local;
+    const bool q_real = q < p.nq;
+
+    float sc[K];
+    int32_t ix[K];
+    float thr;
+    if (MODE == kModeTopK) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
+      thr = q_real ? kNoScore : INFINITY;
+    } else {
+      float floor_v = q_real ? p.floor_sc[size_t(q) * p.k_floor + (p.k_floor - 1)] : INFINITY;
+      // fewer than k valid rows in the pre-pass view: no usable bound, every valid row is a candidate
+      thr = (floor_v <= kNoScore) ? -INFINITY : floor_v - 2.0f * kCoarseEps;
+    }
+
+    int buf = 0; uint32_t tphase = 0;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      mbar_wait(bar_tfull(buf), tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kTileR);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTileR; c0 += 32) {
+        float v[32];
+        __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after the slow path
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+        const bool hit = (MODE == kModeTopK) ? (m > thr) : (m >= thr);
+        if (hit) {
+          const int view_row0 = t * kTileR + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool pass = (MODE == kModeTopK) ? (v[j] > thr) : (v[j] >= thr);
+            if (pass && view_row0 + j < p.n_view_rows) {
+              const int row = (view_row0 + j) * p.row_scale;
+              const int32_t tag = __ldg(p.tags + row);
+              if (tag >= 0 && (p.tenant < 0 || tag == p.tenant)) {
+                if (MODE == kModeTopK) {
+                  reg_insert<K>(sc, ix, v[j], row);
+                  thr = sc[K - 1];
+                } else {
+                  const int slot = atomicAdd(p.cand_count + q, 1);
+                  if (slot < p.cap) p.cand[size_t(q) * p.cap + slot] = make_int2(row, __float_as_int(v[j]));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(buf));
+      if (++buf == 2) { buf = 0; tphase ^= 1; }
+    }
+    if (MODE == kModeTopK && q_real) {
+      float* o_sc = p.part_sc + (size_t(chunk) * p.nq + q) * K;
+      int32_t* o_ix = p.part_ix + (size_t(chunk) * p.nq + q) * K;
+#pragma unroll
+      for (int j = 0; j < K; ++j) { o_sc[j] = sc[j]; o_ix[j] = ix[j] == 0x7fffffff ? -1 : ix[j]; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ stage 3
+// One warp per query: tau from the candidate list, keep S >= tau - 2*eps, rescore in fp32, top-k.
+constexpr int kMaxKeep = 128;      // rescored rows per query before the query is handed to the fallback
+
+template <int K>
+__global__ void __launch_bounds__(128)
+select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ cand_count, int cap, int nq,
+                      int k, int dim, const float* __restrict__ qn, const float* __restrict__ master,
+                      int rescore, float threshold, int64_t row_offset, int64_t* __restrict__ out_rows,
+                      float* __restrict__ out_scores, uint8_t* __restrict__ out_accept,
+                      int* __restrict__ flagged, int* __restrict__ n_flagged) {
+  __shared__ int keep_row[4][kMaxKeep];
+  __shared__ float keep_sc[4][kMaxKeep];
+  const int lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= nq) return;
+  const int count = cand_count[q];
+  const int n = count < cap ? count : cap;
+  bool overflow = count > cap;
+  const int2* mine = cand + size_t(q) * cap;
+
+  // (a) tau = k-th best coarse score: lane-local top-K, then k rounds of warp arg-max
+  float sc[K];
+  int32_t ix[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { sc[j] = -INFINITY; ix[j] = 0x7fffffff; }
+  for (int c = lane; c < n; c += 32) {
+    const int2 e = mine[c];
+    const float s = __int_as_float(e.y);
+    if (s > sc[K - 1] || (s == sc[K - 1] && e.x < ix[K - 1])) {
+      sc[K - 1] = s; ix[K - 1] = e.x;
+#pragma unroll
+      for (int t = K - 1; t > 0; --t) {
+        if (sc[t] > sc[t - 1] || (sc[t] == sc[t - 1] && ix[t] < ix[t - 1])) {
+          float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
+          int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
+        }
+      }
+    }
+  }
+  float tau = -INFINITY;
+  float top_sc = 0.f; int32_t top_ix = -1;     // lane j keeps the j-th coarse winner (TC_BF16 output)
+  for (int j = 0; j < k; ++j) {
+    float bs = sc[0]; int32_t br = ix[0]; int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int32_t orow = __shfl_xor_sync(0xffffffffu, br, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (os > bs || (os == bs && (orow < br || (orow == br && ol < bl)))) { bs = os; br = orow; bl = ol; }
+    }
+    if (lane == bl) {
+#pragma unroll
+      for (int t = 0; t < K - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }
+      sc[K - 1] = -INFINITY; ix[K - 1] = 0x7fffffff;
+    }
+    if (lane == j) { top_sc = bs; top_ix = br == 0x7fffffff ? -1 : br; }
+    tau = bs;                                   // -inf when fewer than k candidates exist: keep all
+  }
+
+  if (!rescore) {
+    // bf16 gallery mode: report the coarse scores themselves (own tolerance)
+    if (lane < k) {
+      const bool filled = top_ix >= 0 && top_sc > kNoScore;
+      out_rows[size_t(q) * k + lane] = filled ? int64_t(top_ix) + row_offset : int64_t(kNoRow);
+      out_scores[size_t(q) * k + lane] = filled ? top_sc : kNoScore;
+      if (lane == 0 && out_accept) out_accept[q] = (filled && top_sc >= threshold) ? 1 : 0;
+    }
+    if (overflow && lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
+    return;
+  }
+
+  // (b) compact the rows that can still be in the true top-k
+  const float keep_thr = tau - 2.0f * kCoarseEps;
+  int m = 0;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int c = c0 + lane;
+    int2 e = make_int2(-1, 0);
+    bool kp = false;
+    if (c < n) { e = mine[c]; kp = __int_as_float(e.y) >= keep_thr; }
+    const unsigned bal = __ballot_sync(0xffffffffu, kp);
+    const int pos = m + __popc(bal & ((1u << lane) - 1));
+    if (kp && pos < kMaxKeep) keep_row[w][pos] = e.x;
+    m += __popc(bal);
+  }
+  if (m > kMaxKeep) { overflow = true; m = kMaxKeep; }
+  __syncwarp();
+
+  // (c) exact fp32 rescoring: one row per lane-group pass, whole warp per row (coalesced 16-byte loads)
+  const int nvec = dim >> 2;
+  for (int i = 0; i < m; ++i) {
+    const float4* g = reinterpret_cast<const float4*>(master + size_t(keep_row[w][i]) * dim);
+    const float4* qq = reinterpret_cast<const float4*>(qn + size_t(q) * dim);
+    float a = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const float4 x = __ldg(g + v), y = __ldg(qq + v);
+      a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) keep_sc[w][i] = a;
+  }
+  __syncwarp();
+
+  // (d) final order (score desc, row asc) over the m exact scores; lane-local lists + warp merge
+#pragma unroll
+  for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
+  for (int c = lane; c < m; c += 32) {
+    const float s = keep_sc[w][c];
+    const int32_t r = keep_row[w][c];
+    if (!(s > kNoScore)) continue;              // scores <= -1 and NaN never match
+    if (s > sc[K - 1] || (s == sc[K - 1] && r < ix[K - 1])) {
+      sc[K - 1] = s; ix[K - 1] = r;
+#pragma unroll
+      for (int t = K - 1; t > 0; --t) {
+        if (sc[t] > sc[t - 1] || (sc[t] == sc[t - 1] && ix[t] < ix[t - 1])) {
+          float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
+          int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
+        }
+      }
+    }
+  }
+  for (int j = 0; j < k; ++j) {
+    float bs = sc[0]; int32_t br = ix[0]; int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int32_t orow = __shfl_xor_sync(0xffffffffu, br, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (os > bs || (os == bs && (orow < br || (orow == br && ol < bl)))) { bs = os; br = orow; bl = ol; }
+    }
+    if (lane == bl) {
+#pragma unroll
+      for (int t = 0; t < K - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }
+      sc[K - 1] = kNoScore; ix[K - 1] = 0x7fffffff;
+    }
+    if (lane == 0) {
+      const bool filled = br != 0x7fffffff;
+      out_rows[size_t(q) * k + j] = filled ? int64_t(br) + row_offset : int64_t(kNoRow);
+      out_scores[size_t(q) * k + j] = filled ? bs : kNoScore;
+      if (j == 0 && out_accept) out_accept[q] = (filled && bs >= threshold) ? 1 : 0;
+    }
+  }
+  if (overflow && lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FRG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return FRG_ERR_CUDA; }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return FRG_OK;
+}
+
+// 2-D bf16 row-major [rows][dim] view with a row pitch (bytes), box = 64 k x box_rows, 128B swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int dim, int64_t rows, size_t pitch_bytes, int box_rows) {
+  EncodeTiledFn enc;
+  FRG_CHECK(get_encode(&enc));
+  cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(pitch_bytes)};
+  cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld pitch=%zu", int(r), (long long)rows, pitch_bytes); return FRG_ERR_CUDA; }
+  return FRG_OK;
+}
+
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+static size_t tc_smem_bytes(int dim) {
+  return size_t(kTileQ) * dim * 2 + size_t(kStages) * kStageBytes + 256 + 1024;
+}
+
+int tc_supported(int dim, int metric, const char** why) {
+  if (metric != FRG_METRIC_COSINE) { *why = "tensor-core variants implement the cosine metric only"; return 0; }
+  if (dim % kBlockK != 0 || dim < kBlockK || dim > 512) { *why = "tensor-core variants need dim in {64..512} and a multiple of 64"; return 0; }
+  return 1;
+}
+
+struct TcPlan {
+  int qtiles, stride, n_view, chunks_pre, chunks_main, kreg, cap;
+  size_t off_qb, off_pre_sc, off_pre_ix, off_floor_sc, off_floor_rows, off_cnt, off_cand, off_flag, total;
+};
+
+static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
+
+static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
+  pl->qtiles = (nq + kTileQ - 1) / kTileQ;
+  // pre-pass view: about 16 K rows (>= one tile per SM), stride a power of two <= 64
+  int stride = 1;
+  while (stride < 64 && rows / (stride * 2) >= 16384) stride *= 2;
+  pl->stride = stride;
+  pl->n_view = int((rows + stride - 1) / stride);
+  auto chunks_for = [&](int64_t nrows) {
+    const int tiles = int((nrows + kTileR - 1) / kTileR);
+    int c = sm_count / gcd_int(sm_count, pl->qtiles);
+    if (c > tiles) c = tiles;
+    return c < 1 ? 1 : c;
+  };
+  pl->chunks_pre = chunks_for(pl->n_view);
+  pl->chunks_main = chunks_for(rows);
+  pl->kreg = reg_k(k);
+  int cap = 4 * k * stride;
+  if (cap < 256) cap = 256;
+  pl->cap = cap;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  pl->off_qb = take(size_t(nq) * dim * 2);
+  pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
+  pl->off_pre_ix = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
+  pl->off_floor_sc = take(size_t(nq) * k * 4);
+  pl->off_floor_rows = take(size_t(nq) * k * 8);
+  pl->off_cnt = take(size_t(nq) * 4 + 4);
+  pl->off_cand = take(size_t(nq) * cap * 8);
+  pl->off_flag = take(size_t(nq) * 4);
+  pl->total = off;
+}
+
+template <int MODE, int K>
+static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p, int qtiles, int chunks,
+                          cudaStream_t st) {
+  const size_t smem = tc_smem_bytes(p.dim);
+  FRG_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes(512))));
+  tc_scan_kernel<MODE, K><<<dim3(qtiles, chunks), kTcThreads, smem, st>>>(qm, gm, p);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
+  TcPlan pl;
+  tc_plan(rows, dim, nq, k, sm_count, &pl);
+  return pl.total;
+}
+
+// qn: normalised fp32 queries [nq][dim] (already computed); ws: tc_workspace_bytes() of scratch.
+// Leaves the overflowed queries in (flagged, n_flagged) for the caller's fallback pass.
+int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
+                    bool rescore, float threshold, int64_t row_offset, unsigned char* ws, int sm_count,
+                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,
+                    int** n_flagged_out, cudaStream_t st) {
+  TcPlan pl;
+  tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
+  float* pre_sc = reinterpret_cast<float*>(ws + pl.off_pre_sc);
+  int32_t* pre_ix = reinterpret_cast<int32_t*>(ws + pl.off_pre_ix);
+  float* floor_sc = reinterpret_cast<float*>(ws + pl.off_floor_sc);
+  int64_t* floor_rows = reinterpret_cast<int64_t*>(ws + pl.off_floor_rows);
+  int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
+  int* n_flagged = cnt + nq;
+  int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
+  int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
+  *flagged_out = flagged;
+  *n_flagged_out = n_flagged;
+
+  CUtensorMap qm, gm_view, gm_full;
+  FRG_CHECK(make_map(&qm, qb, s->dim, nq, size_t(s->dim) * 2, kTileQ));
+  FRG_CHECK(make_map(&gm_view, s->plane, s->dim, pl.n_view, size_t(s->dim) * 2 * pl.stride, kTileR));
+  FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));
+  FRG_CUDA(cudaMemsetAsync(cnt, 0, size_t(nq) * 4 + 4, st));
+
+  TcScanParams p{};
+  p.dim = s->dim; p.nq = nq; p.k = pl.kreg; p.tenant = tenant; p.tags = s->tags;
+  // 1. pre-pass over the strided view
+  p.n_view_rows = pl.n_view; p.row_scale = pl.stride; p.part_sc = pre_sc; p.part_ix = pre_ix;
+  int rc;
+  switch (pl.kreg) {
+    case 1: rc = launch_tc_scan<kModeTopK, 1>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 4: rc = launch_tc_scan<kModeTopK, 4>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 8: rc = launch_tc_scan<kModeTopK, 8>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    default: rc = launch_tc_scan<kModeTopK, 16>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+  }
+  FRG_CHECK(rc);
+  FRG_CHECK(launch_merge_i32(pre_sc, pre_ix, pl.chunks_pre, nq, pl.kreg, k, FRG_METRIC_COSINE, 0.f, 0, false,
+                             floor_rows, floor_sc, nullptr, st));
+  // 2. filter over the whole plane
+  p.n_view_rows = int(s->rows); p.row_scale = 1; p.floor_sc = floor_sc; p.k_floor = k; p.cap = pl.cap;
+  p.cand_count = cnt; p.cand = cand;
+  profile_begin(st);
+  FRG_CHECK((launch_tc_scan<kModeFilter, 1>(qm, gm_full, p, pl.qtiles, pl.chunks_main, st)));
+  profile_end(st, 1);
+  // 3. select + exact rescoring
+  const int grid = (nq + 3) / 4;
+  const int rs = rescore ? 1 : 0;
+#define FRG_SELECT(KK) select_rescore_kernel<KK><<<grid, 128, 0, st>>>(cand, cnt, pl.cap, nq, k, s->dim, qn, s->master, \
+      rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
+  switch (pl.kreg) {
+    case 1: FRG_SELECT(1); break;
+    case 4: FRG_SELECT(4); break;
+    case 8: FRG_SELECT(8); break;
+    default: FRG_SELECT(16); break;
+  }
+#undef FRG_SELECT
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
+}
+
+}  // namespace frg

@@ -13,7 +13,8 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
 KIND = {"recognized": 0, "unknown": 1, "ignored": 2}
-VARIANTS = ["scan_f32", "auto"]
+VARIANTS = ["scan_f32", "tc_exact", "auto"]
+COARSE_EPS = 4e-3            # |bf16 filter score - fp32 score| bound; bf16 gallery mode tolerance
 
 
 @pytest.fixture(scope="module")
@@ -31,6 +32,10 @@ def hex_ids(n, base=0):
 
 def check_against_oracle(frg, store, Q, G, k, threshold, tags=None, tenant=None, company=None, variant="auto",
                          metric="cosine"):
+    if variant == "tc_exact" and store.dim > 512:
+        with pytest.raises(frg.NativeError):
+            frg.Matcher(store).match(Q, k, threshold, variant=variant)
+        pytest.skip("tensor-core variants cover dim <= 512; auto uses the exact scan there")
     m = frg.Matcher(store, metric=metric)
     r = m.match(Q, k, threshold, company_id=company, variant=variant)
     assert r.launches > 0
@@ -303,6 +308,48 @@ def test_embedding_manager_replays_reference_scenario(frg, golden):
     same(mb, "ref_campus_sync1")
     assert mb.get_all().company_id is None
     mb.store.close()
+
+
+@pytest.mark.parametrize("n,f,k", [(20000, 40, 5), (300000, 130, 10)])
+def test_bf16_gallery_mode(frg, n, f, k):
+    """FRG_VARIANT_TC_BF16: the coarse bf16 scores are returned as they are.  Stated bound:
+    |delta score| <= 4e-3 (rigorous for unit vectors: 2 x 2^-9 + accumulation); ids exact wherever the
+    oracle gap exceeds 2 x 4e-3; decisions identical outside that band around the threshold."""
+    d = 512
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.fill_synthetic(n, 0, 77)
+    G = synth.gallery(n, d, 77)
+    Q, target = synth.queries(f, n, d, seed=5, gallery_seed=77)
+    r = frg.Matcher(store).match(Q, k, 0.45, variant="tc_bf16")
+    assert r.variant == "tc_bf16"
+    ref_rows, ref_scores, ref_acc = mo.match_topk(Q, G, k + 1, 0.45)
+    assert np.abs(r.scores - ref_scores[:, :k]).max() <= COARSE_EPS
+    assert mo.ids_match_with_gap(ref_rows, ref_scores, r.rows, 2 * COARSE_EPS).all()
+    near = np.abs(ref_scores[:, 0] - 0.45) <= COARSE_EPS
+    assert (r.accept[~near] == ref_acc[~near]).all()
+    hit = target >= 0
+    assert (r.rows[hit, 0] == target[hit]).all()
+    store.close()
+
+
+def test_candidate_overflow_falls_back_to_exact_scan(frg):
+    """Adversarial gallery for the tensor-core filter: thousands of rows within the bf16 error band of
+    the k-th best (here: exact duplicates).  The candidate list overflows, the query is flagged on the
+    device and redone by the exact scan inside the same call - same answer as the oracle."""
+    d, n = 512, 60000
+    G = synth.gallery(n, d, 31)
+    dup = np.arange(1000, 9000, 2)                      # 4000 copies of row 7
+    G[dup] = G[7]
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.append_rows(G, prenormalised=True)
+    Q, _ = synth.queries(6, n, d, seed=8, gallery_seed=31)
+    Q[2] = G[7] + 0.001
+    Q[4] = G[7]
+    for k in (1, 5, 16):
+        r = check_against_oracle(frg, store, Q, G, k, 0.4, variant="tc_exact")
+        want = sorted([7] + list(dup))[:k]
+        assert list(r.rows[4]) == want and list(r.rows[2]) == want       # ties -> lowest rows, in order
+    store.close()
 
 
 @pytest.mark.parametrize("k", [1, 3])
