@@ -183,6 +183,19 @@ def workload_config(args, batch):
                 args.rows * args.dim * 4 / 1e9, args.rows * args.dim * 2 / 1e9)}
 
 
+def roofline_for(variant, n, dim, F, dom_launch_ms, peaks):
+    """Roofline of the dominant kernel: t_roof = max(bytes / BW_hbm, flops / P_tensor).
+    scan_f32 reads the fp32 master once per pass of <= 4 queries; the tcgen05 filter reads the bf16
+    scan plane once per batch and does 2*F*n*dim flops."""
+    if variant == "scan_f32":
+        bytes_ = n * dim * 4
+        ach = bytes_ / (dom_launch_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "scan_f32_kernel", "achieved": ach, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "algorithmic_bytes_per_launch": bytes_, "launch_ms": dom_launch_ms, "peak_source": peaks["source"]}
+    return tc_roofline(variant, n, dim, F, dom_launch_ms, peaks)
+
+
 def ours_arm(args, rank, world):
     import torch
     import facerecognition_infrenceengine_b200 as frg
@@ -197,57 +210,70 @@ def ours_arm(args, rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    n, dim, F, k = args.rows, args.dim, args.batch, args.k
+    n, dim, k = args.rows, args.dim, args.k
 
     store = frg.GalleryStore(dim=dim, capacity=n, device=local)
     store.fill_synthetic(n, 0, args.seed)
     torch.cuda.synchronize()
     matcher = frg.Matcher(store)
-
-    # a ring of distinct query batches (50 % genuine / 50 % impostor)
-    nb = 4
-    Qh = [synth.queries(F, n, dim, q0=i * F)[0] for i in range(nb)]
-    Qd = [torch.from_numpy(q).to(dev) for q in Qh]
-    outs = [(torch.empty((F, k), dtype=torch.int64, device=dev), torch.empty((F, k), dtype=torch.float32, device=dev),
-             torch.empty((F,), dtype=torch.uint8, device=dev)) for _ in range(nb)]
     stream = torch.cuda.current_stream(dev)
+    nb = 4
 
-    def step(i):
-        matcher.match_device(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
+    def make_batches(F):
+        # a ring of distinct query batches (50 % genuine / 50 % impostor);
+        # every rank takes its own slice of the query stream
+        Qh = [synth.queries(F, n, dim, q0=(rank * nb + i) * F)[0] for i in range(nb)]
+        Qd = [torch.from_numpy(q).to(dev) for q in Qh]
+        outs = [(torch.empty((F, k), dtype=torch.int64, device=dev),
+                 torch.empty((F, k), dtype=torch.float32, device=dev),
+                 torch.empty((F,), dtype=torch.uint8, device=dev)) for _ in range(nb)]
+        return Qh, Qd, outs
 
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-    launches_per_step = N.last_launch_count()
-    variant = N.last_variant()
+    def time_device(F, steps, warmup, Qd, outs, clocks=False):
+        def step(i):
+            matcher.match_device(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        launches_per_step, variant = N.last_launch_count(), N.last_variant()
+        sampler = None
+        if clocks:
+            sampler = ClockSampler(local)
+            sampler.start()
+            time.sleep(0.3)
+        N.profile_enable(True)
+        N.profile_collect()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(steps):
+            step(i)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        total_ms = ev0.elapsed_time(ev1)
+        dom_ms, dom_launches = N.profile_collect()
+        N.profile_enable(False)
+        ck = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            total_ms = float(t.item())
+        ms = total_ms / steps
+        return {"batch": F, "value": F * world / (ms * 1e-3), "ms_per_step": ms, "variant": variant,
+                "launches_per_step": launches_per_step, "dom_ms": dom_ms, "dom_launches": dom_launches,
+                "total_ms": total_ms, "clocks": ck}
 
-    # ---- device-timed region
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.25)
-    N.profile_enable(True)
-    N.profile_collect()
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    total_ms = ev0.elapsed_time(ev1)
-    dom_ms, dom_launches = N.profile_collect()
-    N.profile_enable(False)
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = F * world / (ms_per_step * 1e-3)      # queries are sharded across ranks, galleries replicated
+    # ---- headline batch: device-timed region
+    F = args.batch
+    Qh, Qd, outs = make_batches(F)
+    main = time_device(F, args.steps, args.warmup, Qd, outs, clocks=True)
+    variant = main["variant"]
+    clocks = main["clocks"]
+    ms_per_step, value = main["ms_per_step"], main["value"]
 
     # ---- parity spot-check of what was just timed (never inside the timed region)
     parity = None
@@ -255,55 +281,59 @@ def ours_arm(args, rank, world):
         nchk = min(F, 32)
         G, _ = store.read_rows()
         ref_rows, ref_scores, ref_acc = mo.match_topk(Qh[0][:nchk], G, k + 1, 0.45)
-        got_r, got_s, got_a = (x.cpu().numpy() for x in outs[(args.steps - 1) % nb]) if (args.steps - 1) % nb == 0 else (None,) * 3
-        step(0)
+        matcher.match_device(Qd[0], k, 0.45, variant=args.variant, out=outs[0])
         torch.cuda.synchronize()
         got_r, got_s, got_a = (x.cpu().numpy() for x in outs[0])
-        ids_ok = bool(mo.ids_match_with_gap(ref_rows, ref_scores, got_r[:nchk], 1e-4).all())
-        parity = {"checked_queries": nchk, "ids_ok": ids_ok,
+        parity = {"checked_queries": nchk,
+                  "ids_ok": bool(mo.ids_match_with_gap(ref_rows, ref_scores, got_r[:nchk], 1e-4).all()),
                   "max_abs_dscore": float(np.abs(got_s[:nchk] - ref_scores[:, :k]).max()),
                   "accept_ok": bool((got_a[:nchk].astype(bool) == ref_acc).all())}
         del G
 
-    # ---- end to end through the host-buffer ABI call
+    # ---- end to end through the host-buffer ABI call (pinned host in, pinned host out)
     Qp = [torch.from_numpy(q).pin_memory() for q in Qh]
-    res = frg.MatchResult(np.empty((F, k), np.int64), np.empty((F, k), np.float32), np.zeros(F, np.uint8))
     rows_p = torch.empty((F, k), dtype=torch.int64).pin_memory()
     sc_p = torch.empty((F, k), dtype=torch.float32).pin_memory()
     ac_p = torch.empty((F,), dtype=torch.uint8).pin_memory()
     res = frg.MatchResult(rows_p.numpy(), sc_p.numpy(), ac_p.numpy())
     for i in range(max(3, args.warmup)):
         matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
-    e2e_steps = args.steps
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
+    for i in range(args.steps):
         matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": F * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
-           "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / e2e_steps * 1e3,
+    e2e = {"value": F * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
+           "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / args.steps * 1e3,
            "api": "frg_match_host via Matcher.match (pinned host buffers)"}
+
+    # ---- other batch sizes of configs[1] ("batch 1-1024"): device-timed, same method
+    sweep = []
+    if args.sweep and world == 1:
+        for Fs in [int(x) for x in args.sweep.split(",") if x]:
+            if Fs == F:
+                r = main
+            else:
+                _, Qd_s, outs_s = make_batches(Fs)
+                r = time_device(Fs, args.steps, args.warmup, Qd_s, outs_s)
+                del Qd_s, outs_s
+            rf = roofline_for(r["variant"], n, dim, Fs, r["dom_ms"] / max(r["dom_launches"], 1), peaks)
+            sweep.append({"batch": Fs, "value": r["value"], "ms_per_step": r["ms_per_step"], "variant": r["variant"],
+                          "bound": rf["bound"], "kernel_frac": rf["frac"], "kernel_ms": rf["launch_ms"],
+                          "step_frac_of_roofline": step_roofline_ms(n, dim, Fs, peaks) / r["ms_per_step"]})
 
     if rank != 0:
         return
 
-    # ---- roofline of the dominant kernel
-    dom_launch_ms = dom_ms / max(dom_launches, 1)
-    if variant in ("scan_f32",):
-        bytes_per_launch = n * dim * 4
-        achieved = bytes_per_launch / (dom_launch_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "scan_f32_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": dom_launch_ms,
-                "launches_per_step": dom_launches / args.steps, "peak_source": peaks["source"]}
-    else:
-        roof = tc_roofline(args, variant, n, dim, F, dom_launch_ms, dom_launches, peaks)
-    roof["kernel_share_of_step"] = dom_ms / total_ms
+    roof = roofline_for(variant, n, dim, F, main["dom_ms"] / max(main["dom_launches"], 1), peaks)
+    roof["launches_per_step"] = main["dom_launches"] / args.steps
+    roof["kernel_share_of_step"] = main["dom_ms"] / main["total_ms"]
+    roof["step_frac_of_roofline"] = step_roofline_ms(n, dim, F, peaks) / ms_per_step
 
     # ---- CPU baseline (bounded sample of the same workload, on this box's host cores)
     cpu = None
@@ -311,10 +341,12 @@ def ours_arm(args, rank, world):
         procs = args.cpu_procs or (os.cpu_count() or 1)
         G, _ = store.read_rows()                        # bit-identical to the CPU generator (tested)
         q_cpu = args.cpu_queries or procs
-        qps, per_step, results = run_cpu_loop(G, Qh[0][:q_cpu], 0.45, procs, 1, 0)
+        Qc, _ = synth.queries(q_cpu, n, dim)
+        qps, per_step, results = run_cpu_loop(G, Qc, 0.45, procs, 1, 0)
         # the same queries through the GPU: identical ids and decisions
-        r = matcher.match(Qh[0][:q_cpu], 1, 0.45, variant=args.variant)
-        same = all((res_[0] == gid[0]) and (res_[2] == bool(a)) for res_, gid, a in zip(results, r.ids, r.accept))
+        r = matcher.match(Qc, 1, 0.45, variant=args.variant)
+        same = all((res_[0] == gid[0] or (res_[0] is None and gid[0] is None)) and (res_[2] == bool(a))
+                   for res_, gid, a in zip(results, r.ids, r.accept))
         cpu = {"value": qps, "unit": UNIT, "cores": procs, "kind": "port",
                "sample": "%d queries (1 per worker process) x %d rows, top-1 + threshold 0.45, "
                          "per-face Python loop of peopleCount.py:860-887" % (q_cpu, n),
@@ -325,12 +357,19 @@ def ours_arm(args, rank, world):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
             "data": "synthetic", "config": workload_config(args, F), "variant": variant,
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "parity": parity, "peaks": peaks}
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": main["launches_per_step"] * args.steps,
+            "clocks": clocks, "parity": parity, "sweep": sweep, "peaks": peaks}
     print(json.dumps(line), flush=True)
 
 
-def tc_roofline(args, variant, n, dim, F, launch_ms, launches, peaks):
+def step_roofline_ms(n, dim, F, peaks, bytes_per_elem=2):
+    """Whole-step roofline: the slower of the scan-plane bytes at HBM speed and 2*F*n*dim flops at the
+    tensor peak."""
+    return max(n * dim * bytes_per_elem / (peaks["hbm_gbs"] * 1e9), 2.0 * F * n * dim / (peaks["bf16_tflops"] * 1e12)) * 1e3
+
+
+def tc_roofline(variant, n, dim, F, launch_ms, peaks):
     flops = 2.0 * F * n * dim
     bytes_ = n * dim * 2
     t_hbm = bytes_ / (peaks["hbm_gbs"] * 1e9)
@@ -358,6 +397,7 @@ def main():
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--variant", default="auto")
+    ap.add_argument("--sweep", default="1,8,64,128,256,512,1024")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)

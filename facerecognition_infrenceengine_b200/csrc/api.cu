@@ -259,8 +259,8 @@ int frg_store_stats(frg_store* s, frg_store_stats_t* out) {
   return FRG_OK;
 }
 
-int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
-                     int64_t n, uint32_t flags, void* stream) {
+static int upsert_impl(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
+                       int64_t n, uint32_t flags, void* stream, bool tags_may_be_negative) {
   if (!s || (n > 0 && !vecs) || n < 0) { set_error("upsert: bad argument"); return FRG_ERR_INVALID; }
   if (n == 0) return FRG_OK;
   DeviceGuard g(s->device);
@@ -272,7 +272,14 @@ int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const
   FRG_CHECK(launch_ingest(vecs, rows, tags, n, s->rows, s->dim, normalise, s->master, s->plane, s->tags, st));
   if (!rows) s->rows += n;
   s->live = -1;
+  if (tags && tags_may_be_negative) s->maybe_dead = true;
   return store_end_write(s, st);
+}
+
+int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
+                     int64_t n, uint32_t flags, void* stream) {
+  // device-resident tags cannot be inspected here: assume they may carry -1 (tombstones)
+  return upsert_impl(s, rows, vecs, tags, n, flags, stream, true);
 }
 
 
@@ -306,7 +313,9 @@ int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, 
     if (e == cudaSuccess) e = cudaMemcpy(dt, tags, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upsert_host staging", __FILE__, __LINE__); }
-  rc = frg_store_upsert(s, dr, dv, dt, n, flags, st);
+  bool negative = false;
+  if (tags) for (int64_t i = 0; i < n; ++i) negative |= tags[i] < 0;
+  rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative);
   if (rc == FRG_OK) {
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
@@ -324,6 +333,7 @@ int frg_store_remove(frg_store* s, const int64_t* rows, int64_t n, void* stream)
   FRG_CHECK(store_begin_write(s, st));
   FRG_CHECK(launch_tombstone(rows, n, s->rows, s->tags, st));
   s->live = -1;
+  s->maybe_dead = true;
   return store_end_write(s, st);
 }
 
@@ -362,7 +372,7 @@ int frg_store_compact(frg_store* s, int64_t* old_to_new) {
     }
   }
   const int64_t m = int64_t(src.size());
-  if (m == n) { s->live = n; return FRG_OK; }
+  if (m == n) { s->live = n; s->maybe_dead = false; return FRG_OK; }
   float* nm; __nv_bfloat16* np; int32_t* nt;
   FRG_CHECK(alloc_arrays(s, s->capacity, &nm, &np, &nt));
   int64_t* dsrc = nullptr;
@@ -382,6 +392,7 @@ int frg_store_compact(frg_store* s, int64_t* old_to_new) {
   cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
   s->master = nm; s->plane = np; s->tags = nt;
   s->rows = m; s->live = m; s->version++;
+  s->maybe_dead = false;
   s->readers.clear(); s->has_write = false;
   return FRG_OK;
 }
@@ -411,6 +422,7 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
   FRG_CHECK(launch_synth(n, s->rows, global_row0, seed, tag, s->dim, s->master, s->plane, s->tags, st));
   s->rows += n;
   if (s->live >= 0 && tag >= 0) s->live += n;
+  if (tag < 0) s->maybe_dead = true;
   return store_end_write(s, st);
 }
 

@@ -68,6 +68,7 @@ struct frg_store {
   int64_t rows = 0;       // next append position
   int64_t live = 0;       // maintained on the host from upsert/remove arguments when possible (-1 = unknown)
   int64_t version = 0;
+  bool maybe_dead = false;            // a row was tombstoned since the last compaction (or tag -1 was upserted)
   float* master = nullptr;            // [capacity][dim] fp32, unit rows
   __nv_bfloat16* plane = nullptr;     // [capacity][dim] bf16 image (scan plane) or null
   int32_t* tags = nullptr;            // [capacity]

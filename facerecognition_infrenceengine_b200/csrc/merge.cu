@@ -41,22 +41,37 @@ merge_kernel(const float* __restrict__ scores, const RowT* __restrict__ rows, in
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) { sc[j] = sentinel; ix[j] = RowLimits<RowT>::none(); }
 
+  // candidates are read four at a time so that the global loads of one round are independent
   const int total = parts * k_in;
-  for (int c = lane; c < total; c += 32) {
-    const int part = c / k_in, j = c - part * k_in;
-    const size_t off = (size_t(part) * nq + slot) * k_in + j;
-    const RowT r = rows[off];
-    if (r < 0 || r == RowLimits<RowT>::none()) continue;
-    float s = scores[off];
-    if (euclid && !internal_euclid) s = -s;          // external lists carry distances
-    if (!(s > sentinel)) continue;                   // also drops NaN
-    if (better<RowT>(s, r, sc[KMAX - 1], ix[KMAX - 1])) {
-      sc[KMAX - 1] = s; ix[KMAX - 1] = r;
+  for (int c0 = lane; c0 < total; c0 += 32 * 4) {
+    RowT r[4];
+    float s[4];
 #pragma unroll
-      for (int t = KMAX - 1; t > 0; --t) {
-        if (better<RowT>(sc[t], ix[t], sc[t - 1], ix[t - 1])) {
-          float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
-          RowT tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      r[u] = RowLimits<RowT>::none();
+      s[u] = sentinel;
+      if (c < total) {
+        const int part = c / k_in, j = c - part * k_in;
+        const size_t off = (size_t(part) * nq + slot) * k_in + j;
+        r[u] = rows[off];
+        s[u] = scores[off];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r[u] < 0 || r[u] == RowLimits<RowT>::none()) continue;
+      float v = s[u];
+      if (euclid && !internal_euclid) v = -v;        // external lists carry distances
+      if (!(v > sentinel)) continue;                 // also drops NaN
+      if (better<RowT>(v, r[u], sc[KMAX - 1], ix[KMAX - 1])) {
+        sc[KMAX - 1] = v; ix[KMAX - 1] = r[u];
+#pragma unroll
+        for (int t = KMAX - 1; t > 0; --t) {
+          if (better<RowT>(sc[t], ix[t], sc[t - 1], ix[t - 1])) {
+            float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
+            RowT tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
+          }
         }
       }
     }

@@ -28,6 +28,8 @@
 // query tile; flops = 2 * 128 * rows * dim.
 #include <cuda.h>
 
+#include <cmath>
+
 #include "frg_internal.cuh"
 
 namespace frg {
@@ -151,18 +153,17 @@ struct TcScanParams {
   int n_view_rows;         // rows of the (possibly strided) view
   int row_scale;           // real row = view row * row_scale
   int nq;                  // real queries
-  int k;                   // list length (TOPK) / unused (FILTER)
   int32_t tenant;
   const int32_t* tags;     // per REAL row
-  // TOPK outputs: [chunk][nq][k]
+  // TOPK outputs: [chunk][nq][K]
   float* part_sc;
   int32_t* part_ix;
   // FILTER inputs / outputs
   const float* floor_sc;   // [nq][k_floor] pre-pass lists; L = entry k_floor-1
   int k_floor;
-  int cap;                 // candidate slots per query
-  int* cand_count;         // [nq]
-  int2* cand;              // [nq][cap] (row, score bits)
+  int seg;                 // candidate slots per (query, chunk) segment
+  int* seg_count;          // [nq][chunks]
+  int2* cand;              // [nq][chunks][seg] (row, score bits)
 };
 
 template <int K>
@@ -177,7 +178,10 @@ __device__ __forceinline__ void reg_insert(float (&sc)[K], int32_t (&ix)[K], flo
   }
 }
 
-template <int MODE, int K>
+// MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
+// once per 32-row block, one row per lane, and turned into a warp-uniform bit mask with a ballot -
+// no per-candidate global load sits on the epilogue's dependent path.
+template <int MODE, int K, bool MASKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map,
                const TcScanParams p) {
@@ -276,6 +280,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     float sc[K];
     int32_t ix[K];
     float thr;
+    int emitted = 0;
+    int2* my_seg = nullptr;
     if (MODE == kModeTopK) {
 #pragma unroll
       for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
@@ -284,39 +290,54 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       float floor_v = q_real ? p.floor_sc[size_t(q) * p.k_floor + (p.k_floor - 1)] : INFINITY;
       // fewer than k valid rows in the pre-pass view: no usable bound, every valid row is a candidate
       thr = (floor_v <= kNoScore) ? -INFINITY : floor_v - 2.0f * kCoarseEps;
+      if (q_real) my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
     }
 
     int buf = 0; uint32_t tphase = 0;
     for (int t = tile_begin; t < tile_end; ++t) {
+      // validity of this tile's 4 x 32 rows, fetched while the MMAs of the tile are still running
+      uint32_t vmask[kTileR / 32];
+#pragma unroll
+      for (int b = 0; b < kTileR / 32; ++b) {
+        const int view_row = t * kTileR + b * 32 + lane;
+        bool ok = view_row < p.n_view_rows;
+        if (MASKED && ok) {
+          const int32_t tag = __ldg(p.tags + size_t(view_row) * p.row_scale);
+          ok = tag >= 0 && (p.tenant < 0 || tag == p.tenant);
+        }
+        vmask[b] = __ballot_sync(0xffffffffu, ok);
+      }
       mbar_wait(bar_tfull(buf), tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kTileR);
-#pragma unroll 1
-      for (int c0 = 0; c0 < kTileR; c0 += 32) {
+#pragma unroll
+      for (int b = 0; b < kTileR / 32; ++b) {
         float v[32];
         __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after the slow path
-        tmem_ld32(taddr + c0, v);
+        tmem_ld32(taddr + b * 32, v);
         tmem_ld_wait();
+        const uint32_t vm = vmask[b];
+        if (vm != 0xffffffffu) {           // warp-uniform: tombstones / other tenants / rows past the end
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (vm >> j) & 1u ? v[j] : -INFINITY;
+        }
         float m = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
         const bool hit = (MODE == kModeTopK) ? (m > thr) : (m >= thr);
         if (hit) {
-          const int view_row0 = t * kTileR + c0;
+          const int row0 = (t * kTileR + b * 32) * p.row_scale;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const bool pass = (MODE == kModeTopK) ? (v[j] > thr) : (v[j] >= thr);
-            if (pass && view_row0 + j < p.n_view_rows) {
-              const int row = (view_row0 + j) * p.row_scale;
-              const int32_t tag = __ldg(p.tags + row);
-              if (tag >= 0 && (p.tenant < 0 || tag == p.tenant)) {
-                if (MODE == kModeTopK) {
-                  reg_insert<K>(sc, ix, v[j], row);
-                  thr = sc[K - 1];
-                } else {
-                  const int slot = atomicAdd(p.cand_count + q, 1);
-                  if (slot < p.cap) p.cand[size_t(q) * p.cap + slot] = make_int2(row, __float_as_int(v[j]));
-                }
+            if (MODE == kModeTopK) {
+              if (v[j] > thr) {
+                reg_insert<K>(sc, ix, v[j], row0 + j * p.row_scale);
+                thr = sc[K - 1];
+              }
+            } else {
+              if (v[j] >= thr) {
+                if (emitted < p.seg) my_seg[emitted] = make_int2(row0 + j, __float_as_int(v[j]));
+                ++emitted;
               }
             }
           }
@@ -327,11 +348,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       if (lane == 0) mbar_arrive(bar_tempty(buf));
       if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
-    if (MODE == kModeTopK && q_real) {
-      float* o_sc = p.part_sc + (size_t(chunk) * p.nq + q) * K;
-      int32_t* o_ix = p.part_ix + (size_t(chunk) * p.nq + q) * K;
+    if (q_real) {
+      if (MODE == kModeTopK) {
+        float* o_sc = p.part_sc + (size_t(chunk) * p.nq + q) * K;
+        int32_t* o_ix = p.part_ix + (size_t(chunk) * p.nq + q) * K;
 #pragma unroll
-      for (int j = 0; j < K; ++j) { o_sc[j] = sc[j]; o_ix[j] = ix[j] == 0x7fffffff ? -1 : ix[j]; }
+        for (int j = 0; j < K; ++j) { o_sc[j] = sc[j]; o_ix[j] = ix[j] == 0x7fffffff ? -1 : ix[j]; }
+      } else {
+        p.seg_count[size_t(q) * chunks + chunk] = emitted;      // > seg means the segment overflowed
+      }
     }
   }
 
@@ -344,26 +369,87 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------ stage 3
-// One warp per query: tau from the candidate list, keep S >= tau - 2*eps, rescore in fp32, top-k.
+// One warp per query: tau from the candidate segments, keep S >= tau - 2*eps, rescore in fp32, top-k.
 constexpr int kMaxKeep = 128;      // rescored rows per query before the query is handed to the fallback
 
 template <int K>
-__global__ void __launch_bounds__(128)
-select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ cand_count, int cap, int nq,
-                      int k, int dim, const float* __restrict__ qn, const float* __restrict__ master,
-                      int rescore, float threshold, int64_t row_offset, int64_t* __restrict__ out_rows,
-                      float* __restrict__ out_scores, uint8_t* __restrict__ out_accept,
-                      int* __restrict__ flagged, int* __restrict__ n_flagged) {
-  __shared__ int keep_row[4][kMaxKeep];
-  __shared__ float keep_sc[4][kMaxKeep];
+__device__ __forceinline__ void lane_insert(float (&sc)[K], int32_t (&ix)[K], float s, int32_t r) {
+  if (s > sc[K - 1] || (s == sc[K - 1] && r < ix[K - 1])) {
+    sc[K - 1] = s; ix[K - 1] = r;
+#pragma unroll
+    for (int t = K - 1; t > 0; --t) {
+      if (sc[t] > sc[t - 1] || (sc[t] == sc[t - 1] && ix[t] < ix[t - 1])) {
+        float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
+        int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
+      }
+    }
+  }
+}
+
+// pops the warp-wide best (score desc, row asc) of the lane-local sorted lists
+template <int K>
+__device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], int lane, float sentinel,
+                                              float* best_s, int32_t* best_r) {
+  float bs = sc[0]; int32_t br = ix[0]; int bl = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int32_t orow = __shfl_xor_sync(0xffffffffu, br, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (os > bs || (os == bs && (orow < br || (orow == br && ol < bl)))) { bs = os; br = orow; bl = ol; }
+  }
+  if (lane == bl) {
+#pragma unroll
+    for (int t = 0; t < K - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }
+    sc[K - 1] = sentinel; ix[K - 1] = 0x7fffffff;
+  }
+  *best_s = bs; *best_r = br;
+}
+
+constexpr int kSelectWarps = 2;
+
+template <int K>
+__global__ void __launch_bounds__(kSelectWarps * 32)
+select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg_count, int chunks, int seg,
+                      int kStage, int nq, int k, int dim, const float* __restrict__ qn,
+                      const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
+                      int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
+                      uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged) {
+  extern __shared__ int2 stage_all[];                // [warp][kStage] candidates staged per warp
+  __shared__ int keep_row[kSelectWarps][kMaxKeep];
+  __shared__ float keep_sc[kSelectWarps][kMaxKeep];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  const int q = blockIdx.x * 4 + w;
+  const int q = blockIdx.x * kSelectWarps + w;
   if (q >= nq) return;
-  const int count = cand_count[q];
-  const int n = count < cap ? count : cap;
-  bool overflow = count > cap;
-  const int2* mine = cand + size_t(q) * cap;
+  int2* stage = stage_all + size_t(w) * kStage;
+
+  // gather this query's segments into shared memory (coalesced, all loads independent)
+  const int* cnt = seg_count + size_t(q) * chunks;
+  const int2* mine = cand + size_t(q) * chunks * seg;
+  bool overflow = false;
+  int n = 0;
+  for (int c0 = 0; c0 < chunks; c0 += 32) {
+    const int c = c0 + lane;
+    int have = c < chunks ? cnt[c] : 0;
+    if (have > seg) { overflow = true; have = seg; }
+    // exclusive prefix of `have` across the warp
+    int incl = have;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int start = n + incl - have;
+    for (int i = 0; i < have; ++i) {
+      const int pos = start + i;
+      if (pos < kStage) stage[pos] = mine[size_t(c) * seg + i];
+    }
+    n += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  overflow = __any_sync(0xffffffffu, overflow);
+  if (n > kStage) { overflow = true; n = kStage; }
+  __syncwarp();
 
   // (a) tau = k-th best coarse score: lane-local top-K, then k rounds of warp arg-max
   float sc[K];
@@ -371,35 +457,14 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ can
 #pragma unroll
   for (int j = 0; j < K; ++j) { sc[j] = -INFINITY; ix[j] = 0x7fffffff; }
   for (int c = lane; c < n; c += 32) {
-    const int2 e = mine[c];
-    const float s = __int_as_float(e.y);
-    if (s > sc[K - 1] || (s == sc[K - 1] && e.x < ix[K - 1])) {
-      sc[K - 1] = s; ix[K - 1] = e.x;
-#pragma unroll
-      for (int t = K - 1; t > 0; --t) {
-        if (sc[t] > sc[t - 1] || (sc[t] == sc[t - 1] && ix[t] < ix[t - 1])) {
-          float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
-          int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
-        }
-      }
-    }
+    const int2 e = stage[c];
+    lane_insert<K>(sc, ix, __int_as_float(e.y), e.x);
   }
   float tau = -INFINITY;
   float top_sc = 0.f; int32_t top_ix = -1;     // lane j keeps the j-th coarse winner (TC_BF16 output)
   for (int j = 0; j < k; ++j) {
-    float bs = sc[0]; int32_t br = ix[0]; int bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int32_t orow = __shfl_xor_sync(0xffffffffu, br, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (os > bs || (os == bs && (orow < br || (orow == br && ol < bl)))) { bs = os; br = orow; bl = ol; }
-    }
-    if (lane == bl) {
-#pragma unroll
-      for (int t = 0; t < K - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }
-      sc[K - 1] = -INFINITY; ix[K - 1] = 0x7fffffff;
-    }
+    float bs; int32_t br;
+    warp_pop_best<K>(sc, ix, lane, -INFINITY, &bs, &br);
     if (lane == j) { top_sc = bs; top_ix = br == 0x7fffffff ? -1 : br; }
     tau = bs;                                   // -inf when fewer than k candidates exist: keep all
   }
@@ -423,7 +488,7 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ can
     const int c = c0 + lane;
     int2 e = make_int2(-1, 0);
     bool kp = false;
-    if (c < n) { e = mine[c]; kp = __int_as_float(e.y) >= keep_thr; }
+    if (c < n) { e = stage[c]; kp = __int_as_float(e.y) >= keep_thr; }
     const unsigned bal = __ballot_sync(0xffffffffu, kp);
     const int pos = m + __popc(bal & ((1u << lane) - 1));
     if (kp && pos < kMaxKeep) keep_row[w][pos] = e.x;
@@ -432,19 +497,35 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ can
   if (m > kMaxKeep) { overflow = true; m = kMaxKeep; }
   __syncwarp();
 
-  // (c) exact fp32 rescoring: one row per lane-group pass, whole warp per row (coalesced 16-byte loads)
+  // (c) exact fp32 rescoring, 4 rows in flight per warp (coalesced 16-byte loads, same element ->
+  //     lane mapping and summation order as the streaming scan)
   const int nvec = dim >> 2;
-  for (int i = 0; i < m; ++i) {
-    const float4* g = reinterpret_cast<const float4*>(master + size_t(keep_row[w][i]) * dim);
-    const float4* qq = reinterpret_cast<const float4*>(qn + size_t(q) * dim);
-    float a = 0.f;
+  const float4* qq = reinterpret_cast<const float4*>(qn + size_t(q) * dim);
+  for (int i0 = 0; i0 < m; i0 += 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u < m ? i0 + u : i0;
+      g[u] = reinterpret_cast<const float4*>(master + size_t(keep_row[w][i]) * dim);
+    }
     for (int v = lane; v < nvec; v += 32) {
-      const float4 x = __ldg(g + v), y = __ldg(qq + v);
-      a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+      const float4 y = __ldg(qq + v);
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = __ldg(g[u] + v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = fmaf(x[u].x, y.x, a[u]); a[u] = fmaf(x[u].y, y.y, a[u]);
+        a[u] = fmaf(x[u].z, y.z, a[u]); a[u] = fmaf(x[u].w, y.w, a[u]);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) keep_sc[w][i] = a;
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
+      if (lane == 0 && i0 + u < m) keep_sc[w][i0 + u] = a[u];
+    }
   }
   __syncwarp();
 
@@ -453,33 +534,11 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ can
   for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
   for (int c = lane; c < m; c += 32) {
     const float s = keep_sc[w][c];
-    const int32_t r = keep_row[w][c];
-    if (!(s > kNoScore)) continue;              // scores <= -1 and NaN never match
-    if (s > sc[K - 1] || (s == sc[K - 1] && r < ix[K - 1])) {
-      sc[K - 1] = s; ix[K - 1] = r;
-#pragma unroll
-      for (int t = K - 1; t > 0; --t) {
-        if (sc[t] > sc[t - 1] || (sc[t] == sc[t - 1] && ix[t] < ix[t - 1])) {
-          float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
-          int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
-        }
-      }
-    }
+    if (s > kNoScore) lane_insert<K>(sc, ix, s, keep_row[w][c]);   // scores <= -1 and NaN never match
   }
   for (int j = 0; j < k; ++j) {
-    float bs = sc[0]; int32_t br = ix[0]; int bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int32_t orow = __shfl_xor_sync(0xffffffffu, br, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (os > bs || (os == bs && (orow < br || (orow == br && ol < bl)))) { bs = os; br = orow; bl = ol; }
-    }
-    if (lane == bl) {
-#pragma unroll
-      for (int t = 0; t < K - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }
-      sc[K - 1] = kNoScore; ix[K - 1] = 0x7fffffff;
-    }
+    float bs; int32_t br;
+    warp_pop_best<K>(sc, ix, lane, kNoScore, &bs, &br);
     if (lane == 0) {
       const bool filled = br != 0x7fffffff;
       out_rows[size_t(q) * k + j] = filled ? int64_t(br) + row_offset : int64_t(kNoRow);
@@ -536,15 +595,16 @@ int tc_supported(int dim, int metric, const char** why) {
 }
 
 struct TcPlan {
-  int qtiles, stride, n_view, chunks_pre, chunks_main, kreg, cap;
-  size_t off_qb, off_pre_sc, off_pre_ix, off_floor_sc, off_floor_rows, off_cnt, off_cand, off_flag, total;
+  int qtiles, stride, n_view, chunks_pre, chunks_main, kreg, seg, stage_entries;
+  size_t off_pre_sc, off_pre_ix, off_floor_sc, off_floor_rows, off_cnt, off_cand, off_flag, total;
 };
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
 
 static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
+  (void)dim;
   pl->qtiles = (nq + kTileQ - 1) / kTileQ;
-  // pre-pass view: about 16 K rows (>= one tile per SM), stride a power of two <= 64
+  // pre-pass view: the largest power-of-two stride <= 64 that still leaves >= 16 K sampled rows
   int stride = 1;
   while (stride < 64 && rows / (stride * 2) >= 16384) stride *= 2;
   pl->stride = stride;
@@ -558,31 +618,45 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   pl->chunks_pre = chunks_for(pl->n_view);
   pl->chunks_main = chunks_for(rows);
   pl->kreg = reg_k(k);
-  int cap = 4 * k * stride;
-  if (cap < 256) cap = 256;
-  pl->cap = cap;
+  // Expected candidates per query ~ 2 * stride * Gamma(k): the k-th best of a 1/stride sample sits
+  // at tail mass Gamma(k)/n_view, and the 2*eps widening about doubles the count at dim 512.  Room for
+  // mean + ~10 sigma keeps the overflow probability negligible; the exact fallback covers the rest.
+  int stage_entries = int(2.0 * stride * (k + 10.0 * sqrt(double(k)) + 10.0));
+  if (stage_entries < 256) stage_entries = 256;
+  if (stage_entries > 8192) stage_entries = 8192;
+  pl->stage_entries = stage_entries;
+  int seg = (2 * stage_entries + pl->chunks_main - 1) / pl->chunks_main;   // x2: imbalance across chunks
+  if (seg < 16) seg = 16;
+  pl->seg = seg;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-  pl->off_qb = take(size_t(nq) * dim * 2);
   pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
   pl->off_pre_ix = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
   pl->off_floor_sc = take(size_t(nq) * k * 4);
   pl->off_floor_rows = take(size_t(nq) * k * 8);
-  pl->off_cnt = take(size_t(nq) * 4 + 4);
-  pl->off_cand = take(size_t(nq) * cap * 8);
-  pl->off_flag = take(size_t(nq) * 4);
+  pl->off_cnt = take(size_t(nq) * pl->chunks_main * 4);
+  pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
+  pl->off_flag = take(size_t(nq) * 4 + 4);
   pl->total = off;
 }
 
-template <int MODE, int K>
+template <int MODE, int K, bool MASKED>
 static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p, int qtiles, int chunks,
                           cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p.dim);
-  FRG_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes(512))));
-  tc_scan_kernel<MODE, K><<<dim3(qtiles, chunks), kTcThreads, smem, st>>>(qm, gm, p);
+  FRG_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE, K, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                int(tc_smem_bytes(512))));
+  tc_scan_kernel<MODE, K, MASKED><<<dim3(qtiles, chunks), kTcThreads, smem, st>>>(qm, gm, p);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;
+}
+
+template <int MODE, int K>
+static int launch_tc_scan_m(bool masked, const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p,
+                            int qtiles, int chunks, cudaStream_t st) {
+  return masked ? launch_tc_scan<MODE, K, true>(qm, gm, p, qtiles, chunks, st)
+                : launch_tc_scan<MODE, K, false>(qm, gm, p, qtiles, chunks, st);
 }
 
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
@@ -591,8 +665,8 @@ size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
   return pl.total;
 }
 
-// qn: normalised fp32 queries [nq][dim] (already computed); ws: tc_workspace_bytes() of scratch.
-// Leaves the overflowed queries in (flagged, n_flagged) for the caller's fallback pass.
+// qn / qb: normalised fp32 queries and their bf16 image [nq][dim]; ws: tc_workspace_bytes() of scratch.
+// Leaves the overflowed queries in (flagged, n_flagged) for the caller's exact fallback pass.
 int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
                     bool rescore, float threshold, int64_t row_offset, unsigned char* ws, int sm_count,
                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,
@@ -604,43 +678,49 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   float* floor_sc = reinterpret_cast<float*>(ws + pl.off_floor_sc);
   int64_t* floor_rows = reinterpret_cast<int64_t*>(ws + pl.off_floor_rows);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
-  int* n_flagged = cnt + nq;
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
+  int* n_flagged = flagged + nq;
   *flagged_out = flagged;
   *n_flagged_out = n_flagged;
+  const bool masked = tenant >= 0 || s->maybe_dead;
 
   CUtensorMap qm, gm_view, gm_full;
   FRG_CHECK(make_map(&qm, qb, s->dim, nq, size_t(s->dim) * 2, kTileQ));
   FRG_CHECK(make_map(&gm_view, s->plane, s->dim, pl.n_view, size_t(s->dim) * 2 * pl.stride, kTileR));
   FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));
-  FRG_CUDA(cudaMemsetAsync(cnt, 0, size_t(nq) * 4 + 4, st));
+  FRG_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(int), st));
 
   TcScanParams p{};
-  p.dim = s->dim; p.nq = nq; p.k = pl.kreg; p.tenant = tenant; p.tags = s->tags;
+  p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   // 1. pre-pass over the strided view
   p.n_view_rows = pl.n_view; p.row_scale = pl.stride; p.part_sc = pre_sc; p.part_ix = pre_ix;
   int rc;
   switch (pl.kreg) {
-    case 1: rc = launch_tc_scan<kModeTopK, 1>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
-    case 4: rc = launch_tc_scan<kModeTopK, 4>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
-    case 8: rc = launch_tc_scan<kModeTopK, 8>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
-    default: rc = launch_tc_scan<kModeTopK, 16>(qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 1: rc = launch_tc_scan_m<kModeTopK, 1>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 4: rc = launch_tc_scan_m<kModeTopK, 4>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 8: rc = launch_tc_scan_m<kModeTopK, 8>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    default: rc = launch_tc_scan_m<kModeTopK, 16>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
   }
   FRG_CHECK(rc);
   FRG_CHECK(launch_merge_i32(pre_sc, pre_ix, pl.chunks_pre, nq, pl.kreg, k, FRG_METRIC_COSINE, 0.f, 0, false,
                              floor_rows, floor_sc, nullptr, st));
   // 2. filter over the whole plane
-  p.n_view_rows = int(s->rows); p.row_scale = 1; p.floor_sc = floor_sc; p.k_floor = k; p.cap = pl.cap;
-  p.cand_count = cnt; p.cand = cand;
+  p.n_view_rows = int(s->rows); p.row_scale = 1; p.floor_sc = floor_sc; p.k_floor = k; p.seg = pl.seg;
+  p.seg_count = cnt; p.cand = cand;
   profile_begin(st);
-  FRG_CHECK((launch_tc_scan<kModeFilter, 1>(qm, gm_full, p, pl.qtiles, pl.chunks_main, st)));
+  FRG_CHECK((launch_tc_scan_m<kModeFilter, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st)));
   profile_end(st, 1);
   // 3. select + exact rescoring
-  const int grid = (nq + 3) / 4;
+  const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
   const int rs = rescore ? 1 : 0;
-#define FRG_SELECT(KK) select_rescore_kernel<KK><<<grid, 128, 0, st>>>(cand, cnt, pl.cap, nq, k, s->dim, qn, s->master, \
-      rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
+  const size_t sel_smem = size_t(kSelectWarps) * pl.stage_entries * sizeof(int2);
+#define FRG_SELECT(KK)                                                                                          \
+  FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                int(kSelectWarps * 8192 * sizeof(int2))));                                      \
+  select_rescore_kernel<KK><<<grid, kSelectWarps * 32, sel_smem, st>>>(cand, cnt, pl.chunks_main, pl.seg,       \
+      pl.stage_entries, nq, k, s->dim, qn, s->master, rs, threshold, row_offset, out_rows, out_scores,          \
+      out_accept, flagged, n_flagged)
   switch (pl.kreg) {
     case 1: FRG_SELECT(1); break;
     case 4: FRG_SELECT(4); break;

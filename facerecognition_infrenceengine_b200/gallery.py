@@ -70,7 +70,7 @@ class GalleryStore:
         with self._lock:
             if key not in self._tenants:
                 if not create:
-                    return -2          # matches no row
+                    return 0x7FFFFFFF  # a tag no row carries: matches nothing (negative would mean "all")
                 self._tenants[key] = len(self._tenants) + 1
             return self._tenants[key]
 
