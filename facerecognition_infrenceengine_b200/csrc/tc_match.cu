@@ -289,7 +289,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     } else {
       float floor_v = q_real ? p.floor_sc[size_t(q) * p.k_floor + (p.k_floor - 1)] : INFINITY;
       // fewer than k valid rows in the pre-pass view: no usable bound, every valid row is a candidate
-      thr = (floor_v <= kNoScore) ? -INFINITY : floor_v - 2.0f * kCoarseEps;
+      // (finite, so that masked columns, which are set to -inf, still fail the comparison)
+      thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
       if (q_real) my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
     }
 

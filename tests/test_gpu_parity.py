@@ -322,9 +322,17 @@ def test_bf16_gallery_mode(frg, n, f, k):
     Q, target = synth.queries(f, n, d, seed=5, gallery_seed=77)
     r = frg.Matcher(store).match(Q, k, 0.45, variant="tc_bf16")
     assert r.variant == "tc_bf16"
-    ref_rows, ref_scores, ref_acc = mo.match_topk(Q, G, k + 1, 0.45)
-    assert np.abs(r.scores - ref_scores[:, :k]).max() <= COARSE_EPS
-    assert mo.ids_match_with_gap(ref_rows, ref_scores, r.rows, 2 * COARSE_EPS).all()
+    S = mo.cosine_scores(Q, G)
+    ref_rows, ref_scores = mo.topk_from_scores(S, k)
+    ref_acc = mo.accept_fp32(ref_scores[:, 0], ref_rows[:, 0], 0.45)
+    assert np.abs(r.scores - ref_scores).max() <= COARSE_EPS
+    for f_ in range(f):
+        true_of_returned = S[f_, r.rows[f_]]
+        assert np.abs(true_of_returned - r.scores[f_]).max() <= COARSE_EPS          # reported vs true score
+        assert (true_of_returned >= ref_scores[f_, k - 1] - 2 * COARSE_EPS).all()     # nothing far below the k-th
+        must = ref_rows[f_][ref_scores[f_] > ref_scores[f_, k - 1] + 2 * COARSE_EPS]   # clearly-in rows are in
+        assert set(must) <= set(r.rows[f_])
+        assert (np.diff(true_of_returned) <= 2 * COARSE_EPS).all()                    # order right up to the band
     near = np.abs(ref_scores[:, 0] - 0.45) <= COARSE_EPS
     assert (r.accept[~near] == ref_acc[~near]).all()
     hit = target >= 0
