@@ -150,8 +150,8 @@ enum TcMode { kModeTopK = 0, kModeFilter = 1 };
 
 struct TcScanParams {
   int dim;                 // 512 etc. (multiple of 64)
-  int n_view_rows;         // rows of the (possibly strided) view
-  int row_scale;           // real row = view row * row_scale
+  int n_rows;              // gallery rows
+  int tile_scale;          // pre-pass: only every tile_scale-th 128-row tile is visited (1 = all)
   int nq;                  // real queries
   int32_t tenant;
   const int32_t* tags;     // per REAL row
@@ -159,7 +159,8 @@ struct TcScanParams {
   float* part_sc;
   int32_t* part_ix;
   // FILTER inputs / outputs
-  const float* floor_sc;   // [nq][k_floor] pre-pass lists; L = entry k_floor-1
+  const float* floor_sc;   // pre-pass partial lists [floor_parts][nq][K]; L[q] = k_floor-th best over all
+  int floor_parts;
   int k_floor;
   int seg;                 // candidate slots per (query, chunk) segment
   int* seg_count;          // [nq][chunks]
@@ -207,7 +208,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int qtile = blockIdx.x;
   const int chunk = blockIdx.y, chunks = gridDim.y;
-  const int tiles_total = (p.n_view_rows + kTileR - 1) / kTileR;
+  // view tile v stands for gallery tile v * tile_scale (the pre-pass samples whole 128-row tiles:
+  // contiguous 128 KB reads, spread evenly over the gallery)
+  const int tiles_all = (p.n_rows + kTileR - 1) / kTileR;
+  const int tiles_total = (tiles_all + p.tile_scale - 1) / p.tile_scale;
   const int tile_begin = int((int64_t(tiles_total) * chunk) / chunks);
   const int tile_end = int((int64_t(tiles_total) * (chunk + 1)) / chunks);
 
@@ -236,8 +240,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty(stage), phase ^ 1);
           mbar_expect_tx(bar_full(stage), kStageBytes);
-          tma_load_2d(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK, t * kTileR,
-                      gridDim.x > 1 ? kEvictLast : kEvictFirst);
+          tma_load_2d(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK,
+                      t * p.tile_scale * kTileR, gridDim.x > 1 ? kEvictLast : kEvictFirst);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -287,11 +291,51 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
       thr = q_real ? kNoScore : INFINITY;
     } else {
-      float floor_v = q_real ? p.floor_sc[size_t(q) * p.k_floor + (p.k_floor - 1)] : INFINITY;
-      // fewer than k valid rows in the pre-pass view: no usable bound, every valid row is a candidate
-      // (finite, so that masked columns, which are set to -inf, still fail the comparison)
-      thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
-      if (q_real) my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
+      // L[q] = k-th best coarse score the pre-pass saw, folded here from its per-CTA lists (K sorted
+      // scores each) while the first gallery tiles are still in flight: a lower bound of tau.
+      thr = INFINITY;
+      if (q_real) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) sc[j] = kNoScore;
+        for (int c0 = 0; c0 < p.floor_parts; c0 += 4) {
+          float part[4][K];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u < p.floor_parts ? c0 + u : c0;
+            const float* src = p.floor_sc + (size_t(c) * p.nq + q) * K;
+            if (K >= 4) {
+#pragma unroll
+              for (int j = 0; j < K; j += 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(src + j));
+                part[u][j] = x.x; part[u][j + 1] = x.y; part[u][j + 2] = x.z; part[u][j + 3] = x.w;
+              }
+            } else {
+              part[u][0] = __ldg(src);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + u >= p.floor_parts) break;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+              const float s = part[u][j];
+              if (s > sc[K - 1]) {
+                sc[K - 1] = s;
+#pragma unroll
+                for (int t = K - 1; t > 0; --t)
+                  if (sc[t] > sc[t - 1]) { const float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts; }
+              }
+            }
+          }
+        }
+        float floor_v = kNoScore;
+#pragma unroll
+        for (int j = 0; j < K; ++j) if (j == p.k_floor - 1) floor_v = sc[j];
+        // fewer than k valid rows in the pre-pass sample: no usable bound, every valid row is a candidate
+        // (finite, so that masked columns, which are set to -inf, still fail the comparison)
+        thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
+        my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
+      }
     }
 
     int buf = 0; uint32_t tphase = 0;
@@ -300,10 +344,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       uint32_t vmask[kTileR / 32];
 #pragma unroll
       for (int b = 0; b < kTileR / 32; ++b) {
-        const int view_row = t * kTileR + b * 32 + lane;
-        bool ok = view_row < p.n_view_rows;
+        const int row = t * p.tile_scale * kTileR + b * 32 + lane;
+        bool ok = row < p.n_rows;
         if (MASKED && ok) {
-          const int32_t tag = __ldg(p.tags + size_t(view_row) * p.row_scale);
+          const int32_t tag = __ldg(p.tags + row);
           ok = tag >= 0 && (p.tenant < 0 || tag == p.tenant);
         }
         vmask[b] = __ballot_sync(0xffffffffu, ok);
@@ -327,12 +371,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
         const bool hit = (MODE == kModeTopK) ? (m > thr) : (m >= thr);
         if (hit) {
-          const int row0 = (t * kTileR + b * 32) * p.row_scale;
+          const int row0 = t * p.tile_scale * kTileR + b * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (MODE == kModeTopK) {
               if (v[j] > thr) {
-                reg_insert<K>(sc, ix, v[j], row0 + j * p.row_scale);
+                reg_insert<K>(sc, ix, v[j], row0 + j);
                 thr = sc[K - 1];
               }
             } else {
@@ -408,6 +452,7 @@ __device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], 
 }
 
 constexpr int kSelectWarps = 2;
+constexpr int kMaxChunks = 160;       // >= SM count of the part: candidate segments per query
 
 template <int K>
 __global__ void __launch_bounds__(kSelectWarps * 32)
@@ -425,7 +470,9 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg
   if (q >= nq) return;
   int2* stage = stage_all + size_t(w) * kStage;
 
-  // gather this query's segments into shared memory (coalesced, all loads independent)
+  // gather this query's segments into shared memory: exclusive prefix of the segment counts, then
+  // every staged slot finds its (segment, offset) by binary search - all candidate loads independent
+  __shared__ int seg_prefix[kSelectWarps][kMaxChunks + 1];
   const int* cnt = seg_count + size_t(q) * chunks;
   const int2* mine = cand + size_t(q) * chunks * seg;
   bool overflow = false;
@@ -434,22 +481,27 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg
     const int c = c0 + lane;
     int have = c < chunks ? cnt[c] : 0;
     if (have > seg) { overflow = true; have = seg; }
-    // exclusive prefix of `have` across the warp
     int incl = have;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int up = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += up;
     }
-    const int start = n + incl - have;
-    for (int i = 0; i < have; ++i) {
-      const int pos = start + i;
-      if (pos < kStage) stage[pos] = mine[size_t(c) * seg + i];
-    }
+    if (c < chunks) seg_prefix[w][c] = n + incl - have;
     n += __shfl_sync(0xffffffffu, incl, 31);
   }
+  if (lane == 0) seg_prefix[w][chunks] = n;
   overflow = __any_sync(0xffffffffu, overflow);
   if (n > kStage) { overflow = true; n = kStage; }
+  __syncwarp();
+  for (int pos = lane; pos < n; pos += 32) {
+    int lo = 0, hi = chunks;                 // largest c with seg_prefix[c] <= pos
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_prefix[w][mid] <= pos) lo = mid; else hi = mid;
+    }
+    stage[pos] = mine[size_t(lo) * seg + (pos - seg_prefix[w][lo])];
+  }
   __syncwarp();
 
   // (a) tau = k-th best coarse score: lane-local top-K, then k rounds of warp arg-max
@@ -596,8 +648,8 @@ int tc_supported(int dim, int metric, const char** why) {
 }
 
 struct TcPlan {
-  int qtiles, stride, n_view, chunks_pre, chunks_main, kreg, seg, stage_entries;
-  size_t off_pre_sc, off_pre_ix, off_floor_sc, off_floor_rows, off_cnt, off_cand, off_flag, total;
+  int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
+  size_t off_pre_sc, off_pre_ix, off_cnt, off_cand, off_flag, total;
 };
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
@@ -605,19 +657,20 @@ static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); 
 static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
   (void)dim;
   pl->qtiles = (nq + kTileQ - 1) / kTileQ;
-  // pre-pass view: the largest power-of-two stride <= 64 that still leaves >= 16 K sampled rows
+  // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
+  // leaves >= 16 K sampled rows
   int stride = 1;
   while (stride < 64 && rows / (stride * 2) >= 16384) stride *= 2;
   pl->stride = stride;
-  pl->n_view = int((rows + stride - 1) / stride);
-  auto chunks_for = [&](int64_t nrows) {
-    const int tiles = int((nrows + kTileR - 1) / kTileR);
+  const int tiles_all = int((rows + kTileR - 1) / kTileR);
+  auto chunks_for = [&](int tiles) {
     int c = sm_count / gcd_int(sm_count, pl->qtiles);
+    if (c > kMaxChunks) c = kMaxChunks;
     if (c > tiles) c = tiles;
     return c < 1 ? 1 : c;
   };
-  pl->chunks_pre = chunks_for(pl->n_view);
-  pl->chunks_main = chunks_for(rows);
+  pl->chunks_pre = chunks_for((tiles_all + stride - 1) / stride);
+  pl->chunks_main = chunks_for(tiles_all);
   pl->kreg = reg_k(k);
   // Expected candidates per query ~ 2 * stride * Gamma(k): the k-th best of a 1/stride sample sits
   // at tail mass Gamma(k)/n_view, and the 2*eps widening about doubles the count at dim 512.  Room for
@@ -633,8 +686,6 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
   pl->off_pre_ix = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
-  pl->off_floor_sc = take(size_t(nq) * k * 4);
-  pl->off_floor_rows = take(size_t(nq) * k * 8);
   pl->off_cnt = take(size_t(nq) * pl->chunks_main * 4);
   pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
   pl->off_flag = take(size_t(nq) * 4 + 4);
@@ -676,8 +727,6 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
   float* pre_sc = reinterpret_cast<float*>(ws + pl.off_pre_sc);
   int32_t* pre_ix = reinterpret_cast<int32_t*>(ws + pl.off_pre_ix);
-  float* floor_sc = reinterpret_cast<float*>(ws + pl.off_floor_sc);
-  int64_t* floor_rows = reinterpret_cast<int64_t*>(ws + pl.off_floor_rows);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
@@ -686,31 +735,34 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   *n_flagged_out = n_flagged;
   const bool masked = tenant >= 0 || s->maybe_dead;
 
-  CUtensorMap qm, gm_view, gm_full;
+  CUtensorMap qm, gm_full;
   FRG_CHECK(make_map(&qm, qb, s->dim, nq, size_t(s->dim) * 2, kTileQ));
-  FRG_CHECK(make_map(&gm_view, s->plane, s->dim, pl.n_view, size_t(s->dim) * 2 * pl.stride, kTileR));
   FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));
   FRG_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(int), st));
 
   TcScanParams p{};
   p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
-  // 1. pre-pass over the strided view
-  p.n_view_rows = pl.n_view; p.row_scale = pl.stride; p.part_sc = pre_sc; p.part_ix = pre_ix;
+  // 1. pre-pass over the sampled tiles
+  p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.part_sc = pre_sc; p.part_ix = pre_ix;
   int rc;
   switch (pl.kreg) {
-    case 1: rc = launch_tc_scan_m<kModeTopK, 1>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
-    case 4: rc = launch_tc_scan_m<kModeTopK, 4>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
-    case 8: rc = launch_tc_scan_m<kModeTopK, 8>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
-    default: rc = launch_tc_scan_m<kModeTopK, 16>(masked, qm, gm_view, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 1: rc = launch_tc_scan_m<kModeTopK, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 4: rc = launch_tc_scan_m<kModeTopK, 4>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
+    case 8: rc = launch_tc_scan_m<kModeTopK, 8>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
+    default: rc = launch_tc_scan_m<kModeTopK, 16>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
   }
   FRG_CHECK(rc);
-  FRG_CHECK(launch_merge_i32(pre_sc, pre_ix, pl.chunks_pre, nq, pl.kreg, k, FRG_METRIC_COSINE, 0.f, 0, false,
-                             floor_rows, floor_sc, nullptr, st));
-  // 2. filter over the whole plane
-  p.n_view_rows = int(s->rows); p.row_scale = 1; p.floor_sc = floor_sc; p.k_floor = k; p.seg = pl.seg;
+  // 2. filter over the whole plane (folds the pre-pass lists into L[q] in its prologue)
+  p.tile_scale = 1; p.floor_sc = pre_sc; p.floor_parts = pl.chunks_pre; p.k_floor = k; p.seg = pl.seg;
   p.seg_count = cnt; p.cand = cand;
   profile_begin(st);
-  FRG_CHECK((launch_tc_scan_m<kModeFilter, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st)));
+  switch (pl.kreg) {
+    case 1: rc = launch_tc_scan_m<kModeFilter, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
+    case 4: rc = launch_tc_scan_m<kModeFilter, 4>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
+    case 8: rc = launch_tc_scan_m<kModeFilter, 8>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
+    default: rc = launch_tc_scan_m<kModeFilter, 16>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
+  }
+  FRG_CHECK(rc);
   profile_end(st, 1);
   // 3. select + exact rescoring
   const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
