@@ -256,6 +256,7 @@ def ours_arm(args, rank, world):
             torch.distributed.barrier()
         total_ms = ev0.elapsed_time(ev1)
         dom_ms, dom_launches = N.profile_collect()
+        stages = {k_: v / steps for k_, v in N.profile_stages().items()}
         N.profile_enable(False)
         ck = sampler.stop() if sampler else None
         if world > 1:
@@ -265,7 +266,7 @@ def ours_arm(args, rank, world):
         ms = total_ms / steps
         return {"batch": F, "value": F * world / (ms * 1e-3), "ms_per_step": ms, "variant": variant,
                 "launches_per_step": launches_per_step, "dom_ms": dom_ms, "dom_launches": dom_launches,
-                "total_ms": total_ms, "clocks": ck}
+                "total_ms": total_ms, "clocks": ck, "stage_ms": stages}
 
     # ---- headline batch: device-timed region
     F = args.batch
@@ -325,6 +326,7 @@ def ours_arm(args, rank, world):
             rf = roofline_for(r["variant"], n, dim, Fs, r["dom_ms"] / max(r["dom_launches"], 1), peaks)
             sweep.append({"batch": Fs, "value": r["value"], "ms_per_step": r["ms_per_step"], "variant": r["variant"],
                           "bound": rf["bound"], "kernel_frac": rf["frac"], "kernel_ms": rf["launch_ms"],
+                          "stage_ms": {k_: round(v, 4) for k_, v in r["stage_ms"].items()},
                           "step_frac_of_roofline": step_roofline_ms(n, dim, Fs, peaks) / r["ms_per_step"]})
 
     if rank != 0:

@@ -67,6 +67,7 @@ SIGNATURES = {
     "frg_last_variant": (C.c_char_p, []),
     "frg_profile_enable": (C.c_int, [C.c_int32]),
     "frg_profile_collect": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "frg_profile_stage_ms": (C.c_int, [C.c_int32, C.POINTER(C.c_float)]),
 }
 
 
@@ -124,3 +125,16 @@ def profile_collect():
     ms, n = C.c_float(0), C.c_int32(0)
     check(lib.frg_profile_collect(C.byref(ms), C.byref(n)))
     return float(ms.value), int(n.value)
+
+
+STAGE_NAMES = ["prep", "prepass", "floor", "dominant", "select", "fallback"]
+
+
+def profile_stages():
+    """Per-stage device ms accumulated by the last profile_collect()."""
+    out = {}
+    for i, name in enumerate(STAGE_NAMES):
+        ms = C.c_float(0)
+        check(lib.frg_profile_stage_ms(i, C.byref(ms)))
+        out[name] = float(ms.value)
+    return out

@@ -30,20 +30,23 @@ void note_launch(const char* variant) {
 }
 void reset_launches() { g_launches = 0; g_variant = "none"; }
 
-struct ProfileSpan { cudaEvent_t a, b; int launches; };
+struct ProfileSpan { cudaEvent_t a, b; int launches; int stage; };
 static thread_local bool g_profile = false;
 static thread_local std::vector<ProfileSpan> g_spans;
 static thread_local cudaEvent_t g_open = nullptr;
+static thread_local int g_open_stage = 0;
+static thread_local float g_stage_ms[FRG_PROFILE_STAGES] = {0};
 
-void profile_begin(cudaStream_t st) {
+void profile_begin(cudaStream_t st, int stage) {
   if (!g_profile) return;
   if (cudaEventCreate(&g_open) != cudaSuccess) { g_open = nullptr; return; }
+  g_open_stage = stage;
   cudaEventRecord(g_open, st);
 }
 
 void profile_end(cudaStream_t st, int launches) {
   if (!g_profile || !g_open) return;
-  ProfileSpan sp{g_open, nullptr, launches};
+  ProfileSpan sp{g_open, nullptr, launches, g_open_stage};
   g_open = nullptr;
   if (cudaEventCreate(&sp.b) != cudaSuccess) { cudaEventDestroy(sp.a); return; }
   cudaEventRecord(sp.b, st);
@@ -175,13 +178,14 @@ int frg_profile_collect(float* dominant_ms, int32_t* dominant_launches) {
   float total = 0.f;
   int launches = 0;
   int rc = FRG_OK;
+  for (float& v : g_stage_ms) v = 0.f;
   for (auto& sp : g_spans) {
     float ms = 0.f;
     cudaError_t e = cudaEventSynchronize(sp.b);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
     if (e != cudaSuccess && rc == FRG_OK) rc = cuda_fail(e, "profile events", __FILE__, __LINE__);
-    total += ms;
-    launches += sp.launches;
+    if (sp.stage >= 0 && sp.stage < FRG_PROFILE_STAGES) g_stage_ms[sp.stage] += ms;
+    if (sp.stage == kStageDominant) { total += ms; launches += sp.launches; }
     cudaEventDestroy(sp.a);
     cudaEventDestroy(sp.b);
   }
@@ -189,6 +193,12 @@ int frg_profile_collect(float* dominant_ms, int32_t* dominant_launches) {
   if (dominant_ms) *dominant_ms = total;
   if (dominant_launches) *dominant_launches = launches;
   return rc;
+}
+
+int frg_profile_stage_ms(int32_t stage, float* ms) {
+  if (stage < 0 || stage >= FRG_PROFILE_STAGES || !ms) { set_error("bad profile stage"); return FRG_ERR_INVALID; }
+  *ms = g_stage_ms[stage];
+  return FRG_OK;
 }
 
 int frg_device_count(int32_t* count) {
@@ -474,7 +484,9 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   float* qn = reinterpret_cast<float*>(ws);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes);
   int* flagged = nullptr; int* n_flagged = nullptr;
+  profile_begin(st, kStagePrep);
   int rc = launch_normalise_queries(q, nq, s->dim, true, qn, qb, st);
+  profile_end(st, 1);
   if (rc == FRG_OK)
     rc = launch_tc_match(s, qn, qb, nq, k, p->tenant, rescore, p->threshold, p->row_offset, ws + qn_bytes + qb_bytes,
                          sm_count, out_rows, out_scores, out_accept, &flagged, &n_flagged, st);
@@ -483,8 +495,10 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
     ScanArgs a;
     a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
     a.qn = qn; a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = sm_count;
+    profile_begin(st, kStageFallback);
     rc = launch_scan_f32_flagged(a, flagged, n_flagged, p->row_offset, p->threshold, out_rows, out_scores,
                                  out_accept, st);
+    profile_end(st, 2);
   }
   g_variant = rescore ? "tc_exact" : "tc_bf16";
   cudaError_t e = cudaFreeAsync(ws, st);

@@ -36,7 +36,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void note_launch(const char* variant_or_null);   // launch accounting for frg_last_launch_count()
 void reset_launches();
 // bench-only timing of the dominant kernel(s): bracket them with profile_begin/profile_end
-void profile_begin(cudaStream_t st);
+enum ProfileStage { kStagePrep = 0, kStagePrepass = 1, kStageFloor = 2, kStageDominant = 3, kStageSelect = 4,
+                    kStageFallback = 5 };
+void profile_begin(cudaStream_t st, int stage = kStageDominant);
 void profile_end(cudaStream_t st, int launches);
 
 struct DeviceInfo {

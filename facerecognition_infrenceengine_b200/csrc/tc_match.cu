@@ -29,6 +29,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "frg_internal.cuh"
 
@@ -159,9 +160,7 @@ struct TcScanParams {
   float* part_sc;
   int32_t* part_ix;
   // FILTER inputs / outputs
-  const float* floor_sc;   // pre-pass partial lists [floor_parts][nq][K]; L[q] = k_floor-th best over all
-  int floor_parts;
-  int k_floor;
+  const float* floor_sc;   // [nq] L[q]: k-th best coarse score of the pre-pass sample (-1: fewer than k)
   int seg;                 // candidate slots per (query, chunk) segment
   int* seg_count;          // [nq][chunks]
   int2* cand;              // [nq][chunks][seg] (row, score bits)
@@ -291,51 +290,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
       thr = q_real ? kNoScore : INFINITY;
     } else {
-      // L[q] = k-th best coarse score the pre-pass saw, folded here from its per-CTA lists (K sorted
-      // scores each) while the first gallery tiles are still in flight: a lower bound of tau.
-      thr = INFINITY;
-      if (q_real) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) sc[j] = kNoScore;
-        for (int c0 = 0; c0 < p.floor_parts; c0 += 4) {
-          float part[4][K];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u < p.floor_parts ? c0 + u : c0;
-            const float* src = p.floor_sc + (size_t(c) * p.nq + q) * K;
-            if (K >= 4) {
-#pragma unroll
-              for (int j = 0; j < K; j += 4) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(src + j));
-                part[u][j] = x.x; part[u][j + 1] = x.y; part[u][j + 2] = x.z; part[u][j + 3] = x.w;
-              }
-            } else {
-              part[u][0] = __ldg(src);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (c0 + u >= p.floor_parts) break;
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-              const float s = part[u][j];
-              if (s > sc[K - 1]) {
-                sc[K - 1] = s;
-#pragma unroll
-                for (int t = K - 1; t > 0; --t)
-                  if (sc[t] > sc[t - 1]) { const float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts; }
-              }
-            }
-          }
-        }
-        float floor_v = kNoScore;
-#pragma unroll
-        for (int j = 0; j < K; ++j) if (j == p.k_floor - 1) floor_v = sc[j];
-        // fewer than k valid rows in the pre-pass sample: no usable bound, every valid row is a candidate
-        // (finite, so that masked columns, which are set to -inf, still fail the comparison)
-        thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
-        my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
-      }
+      // L[q]: k-th best coarse score the pre-pass saw (floor_kernel), a lower bound of tau
+      const float floor_v = q_real ? __ldg(p.floor_sc + q) : INFINITY;
+      // fewer than k valid rows in the pre-pass sample: no usable bound, every valid row is a candidate
+      // (finite, so that masked columns, which are set to -inf, still fail the comparison)
+      thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
+      if (q_real) my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
     }
 
     int buf = 0; uint32_t tphase = 0;
@@ -411,6 +371,71 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// ------------------------------------------------------------------------------------------ stage 1b
+// L[q] = k-th best score over the pre-pass partial lists [parts][nq][K] (each sorted, best first).
+// One warp per query, lane-local sorted lists of scores only, then k rounds of warp max + pop.
+template <int K>
+__global__ void __launch_bounds__(128)
+floor_kernel(const float* __restrict__ part_sc, int parts, int nq, int k, float* __restrict__ floor_out) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  float sc[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) sc[j] = kNoScore;
+  for (int c0 = lane; c0 < parts; c0 += 64) {
+    float v[2][K];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = c0 + 32 * u;
+#pragma unroll
+      for (int j = 0; j < K; ++j) v[u][j] = kNoScore;
+      if (c < parts) {
+        const float* src = part_sc + (size_t(c) * nq + q) * K;
+        if (K >= 4) {
+#pragma unroll
+          for (int j = 0; j < K; j += 4) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(src + j));
+            v[u][j] = x.x; v[u][j + 1] = x.y; v[u][j + 2] = x.z; v[u][j + 3] = x.w;
+          }
+        } else {
+          v[u][0] = __ldg(src);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float s = v[u][j];
+        if (s > sc[K - 1]) {
+          sc[K - 1] = s;
+#pragma unroll
+          for (int t = K - 1; t > 0; --t)
+            if (sc[t] > sc[t - 1]) { const float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts; }
+        }
+      }
+    }
+  }
+  float kth = kNoScore;
+  for (int j = 0; j < k; ++j) {
+    float bs = sc[0]; int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (os > bs || (os == bs && ol < bl)) { bs = os; bl = ol; }
+    }
+    if (lane == bl) {
+#pragma unroll
+      for (int t = 0; t < K - 1; ++t) sc[t] = sc[t + 1];
+      sc[K - 1] = kNoScore;
+    }
+    kth = bs;
+  }
+  if (lane == 0) floor_out[q] = kth;      // -1 when the sample held fewer than k valid rows
 }
 
 // ------------------------------------------------------------------------------------------ stage 3
@@ -649,7 +674,7 @@ int tc_supported(int dim, int metric, const char** why) {
 
 struct TcPlan {
   int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
-  size_t off_pre_sc, off_pre_ix, off_cnt, off_cand, off_flag, total;
+  size_t off_pre_sc, off_pre_ix, off_floor, off_cnt, off_cand, off_flag, total;
 };
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
@@ -670,6 +695,9 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
     return c < 1 ? 1 : c;
   };
   pl->chunks_pre = chunks_for((tiles_all + stride - 1) / stride);
+  // fewer, longer pre-pass CTAs: the floor fold costs O(parts) per query
+  static const int pre_cap = []() { const char* e = getenv("FRG_TC_PRE_CHUNKS"); return e ? atoi(e) : 74; }();
+  if (pre_cap > 0 && pl->chunks_pre > pre_cap) pl->chunks_pre = pre_cap;
   pl->chunks_main = chunks_for(tiles_all);
   pl->kreg = reg_k(k);
   // Expected candidates per query ~ 2 * stride * Gamma(k): the k-th best of a 1/stride sample sits
@@ -686,6 +714,7 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
   pl->off_pre_ix = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
+  pl->off_floor = take(size_t(nq) * 4);
   pl->off_cnt = take(size_t(nq) * pl->chunks_main * 4);
   pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
   pl->off_flag = take(size_t(nq) * 4 + 4);
@@ -727,6 +756,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
   float* pre_sc = reinterpret_cast<float*>(ws + pl.off_pre_sc);
   int32_t* pre_ix = reinterpret_cast<int32_t*>(ws + pl.off_pre_ix);
+  float* floor_sc = reinterpret_cast<float*>(ws + pl.off_floor);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
@@ -745,6 +775,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   // 1. pre-pass over the sampled tiles
   p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.part_sc = pre_sc; p.part_ix = pre_ix;
   int rc;
+  profile_begin(st, kStagePrepass);
   switch (pl.kreg) {
     case 1: rc = launch_tc_scan_m<kModeTopK, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
     case 4: rc = launch_tc_scan_m<kModeTopK, 4>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
@@ -752,19 +783,29 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
     default: rc = launch_tc_scan_m<kModeTopK, 16>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
   }
   FRG_CHECK(rc);
-  // 2. filter over the whole plane (folds the pre-pass lists into L[q] in its prologue)
-  p.tile_scale = 1; p.floor_sc = pre_sc; p.floor_parts = pl.chunks_pre; p.k_floor = k; p.seg = pl.seg;
-  p.seg_count = cnt; p.cand = cand;
-  profile_begin(st);
-  switch (pl.kreg) {
-    case 1: rc = launch_tc_scan_m<kModeFilter, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
-    case 4: rc = launch_tc_scan_m<kModeFilter, 4>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
-    case 8: rc = launch_tc_scan_m<kModeFilter, 8>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
-    default: rc = launch_tc_scan_m<kModeFilter, 16>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st); break;
+  profile_end(st, 1);
+  profile_begin(st, kStageFloor);
+  {
+    const int fgrid = (nq + 3) / 4;
+    switch (pl.kreg) {
+      case 1: floor_kernel<1><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
+      case 4: floor_kernel<4><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
+      case 8: floor_kernel<8><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
+      default: floor_kernel<16><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
+    }
+    note_launch(nullptr);
+    FRG_CUDA(cudaGetLastError());
   }
+  profile_end(st, 1);
+  // 2. filter over the whole plane
+  p.tile_scale = 1; p.floor_sc = floor_sc; p.seg = pl.seg;
+  p.seg_count = cnt; p.cand = cand;
+  profile_begin(st, kStageDominant);
+  rc = launch_tc_scan_m<kModeFilter, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
   FRG_CHECK(rc);
   profile_end(st, 1);
   // 3. select + exact rescoring
+  profile_begin(st, kStageSelect);
   const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
   const int rs = rescore ? 1 : 0;
   const size_t sel_smem = size_t(kSelectWarps) * pl.stage_entries * sizeof(int2);
@@ -783,6 +824,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
 #undef FRG_SELECT
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
+  profile_end(st, 1);
   return FRG_OK;
 }
 

@@ -156,6 +156,10 @@ FRG_API const char* frg_last_variant(void);
  * device time and launch count since the last collect, and clears them.  Thread-local. */
 FRG_API int frg_profile_enable(int32_t on);
 FRG_API int frg_profile_collect(float* dominant_ms, int32_t* dominant_launches);
+/* Per-stage device time of the matches since the last frg_profile_collect (filled by that call):
+ * stage 0 query prep, 1 pre-pass, 2 floor merge, 3 dominant scan/filter, 4 select+rescore, 5 fallback. */
+#define FRG_PROFILE_STAGES 6
+FRG_API int frg_profile_stage_ms(int32_t stage, float* ms);
 
 #ifdef __cplusplus
 }
