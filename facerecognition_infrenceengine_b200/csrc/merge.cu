@@ -119,7 +119,9 @@ static int launch_merge(const float* scores, const RowT* rows, int parts, int nq
   if (k_out < 1 || k_out > FRG_MAX_K || k_in < 1) { set_error("merge: k out of range"); return FRG_ERR_INVALID; }
   const int grid = (nq + 3) / 4;
   const int ie = internal_euclid ? 1 : 0;
-#define FRG_MERGE(K) merge_kernel<RowT, K><<<grid, 128, 0, st>>>(scores, rows, parts, nq, k_in, k_out, metric, \
+#define FRG_MERGE(K)                                                                                            \
+  cudaFuncSetAttribute(merge_kernel<RowT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);             \
+  merge_kernel<RowT, K><<<grid, 128, 0, st>>>(scores, rows, parts, nq, k_in, k_out, metric, \
       threshold, row_offset, ie, q_index, n_active, out_rows, out_scores, out_accept)
   if (k_out == 1) FRG_MERGE(1);
   else if (k_out <= 4) FRG_MERGE(4);

@@ -47,6 +47,8 @@ int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, fl
                              __nv_bfloat16* qn_bf16, cudaStream_t st) {
   if (nq <= 0) return FRG_OK;
   const int warps_per_block = 4;
+  // same smem/L1 split as the tensor-core kernels that follow: no carve-out switch between launches
+  FRG_CUDA(cudaFuncSetAttribute(normalise_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   normalise_queries_kernel<<<(nq + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(
       q, nq, dim, normalise ? 1 : 0, qn, qn_bf16);
   note_launch(nullptr);

@@ -320,6 +320,8 @@ template <int NJ, int QB>
 static int launch_flagged_t(const ScanArgs& a, int grid, const int* flagged, const int* n_flagged, float* ps,
                             int32_t* pi, cudaStream_t st) {
   const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
+  FRG_CUDA(cudaFuncSetAttribute(scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE>,
+                                cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE><<<grid, kScanWarps * 32, smem, st>>>(
       a.master, a.tags, a.rows, a.qn, a.nq, flagged, n_flagged, a.k, a.tenant, ps, pi);
   note_launch(nullptr);

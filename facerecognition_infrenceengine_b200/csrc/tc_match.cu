@@ -7,8 +7,9 @@
 // rounds to bf16: 2^-9 relative per vector, plus fp32 accumulation), so every row of the true
 // top-k has S >= tau - 2*eps, tau = k-th best coarse score.  Pipeline per batch:
 //
-//   1. pre-pass  (tc_scan_kernel<TOPK>)   over a 1/stride strided view of the scan plane: per-query
-//      running top-k of coarse scores -> L[q] = its k-th best, a lower bound of tau.
+//   1. pre-pass  (tc_scan_kernel<GROUPMAX>) over every stride-th 128-row tile of the scan plane:
+//      per query, the running maximum of each of 32 disjoint row groups (row mod 32).  The k-th
+//      largest of those 32 maxima (floor_kernel) is attained by k distinct rows, hence L[q] <= tau.
 //   2. filter    (tc_scan_kernel<FILTER>) over the whole plane: append every (row, S) with
 //      S >= L[q] - 2*eps to the query's candidate list (a few hundred rows out of 10^6).
 //   3. select + rescore (select_rescore_kernel): tau from the candidates, keep S >= tau - 2*eps,
@@ -147,7 +148,8 @@ constexpr float kCoarseEps = 4e-3f;                        // |bf16 filter score
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTileR >> 3) << 17) |
                             (uint32_t(kTileQ >> 4) << 24);
 
-enum TcMode { kModeTopK = 0, kModeFilter = 1 };
+enum TcMode { kModeGroupMax = 0, kModeFilter = 1 };
+constexpr int kGroups = 32;
 
 struct TcScanParams {
   int dim;                 // 512 etc. (multiple of 64)
@@ -156,9 +158,8 @@ struct TcScanParams {
   int nq;                  // real queries
   int32_t tenant;
   const int32_t* tags;     // per REAL row
-  // TOPK outputs: [chunk][nq][K]
+  // GROUPMAX output: [chunk][nq][32] running maxima of the row groups (row mod 32)
   float* part_sc;
-  int32_t* part_ix;
   // FILTER inputs / outputs
   const float* floor_sc;   // [nq] L[q]: k-th best coarse score of the pre-pass sample (-1: fewer than k)
   int seg;                 // candidate slots per (query, chunk) segment
@@ -166,22 +167,10 @@ struct TcScanParams {
   int2* cand;              // [nq][chunks][seg] (row, score bits)
 };
 
-template <int K>
-__device__ __forceinline__ void reg_insert(float (&sc)[K], int32_t (&ix)[K], float s, int32_t row) {
-  sc[K - 1] = s; ix[K - 1] = row;
-#pragma unroll
-  for (int t = K - 1; t > 0; --t) {
-    if (sc[t] > sc[t - 1]) {       // strict: among equal scores the earlier (lower) row stays ahead
-      float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts;
-      int32_t tr = ix[t]; ix[t] = ix[t - 1]; ix[t - 1] = tr;
-    }
-  }
-}
-
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
 // once per 32-row block, one row per lane, and turned into a warp-uniform bit mask with a ballot -
 // no per-candidate global load sits on the epilogue's dependent path.
-template <int MODE, int K, bool MASKED>
+template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map,
                const TcScanParams p) {
@@ -280,15 +269,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     const int q = qtile * kTileQ + q_local;
     const bool q_real = q < p.nq;
 
-    float sc[K];
-    int32_t ix[K];
-    float thr;
+    float gmax[kGroups];                                 // GROUPMAX: running maximum per row group
+    float thr = INFINITY;
     int emitted = 0;
     int2* my_seg = nullptr;
-    if (MODE == kModeTopK) {
+    if (MODE == kModeGroupMax) {
 #pragma unroll
-      for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
-      thr = q_real ? kNoScore : INFINITY;
+      for (int j = 0; j < kGroups; ++j) gmax[j] = kNoScore;
     } else {
       // L[q]: k-th best coarse score the pre-pass saw (floor_kernel), a lower bound of tau
       const float floor_v = q_real ? __ldg(p.floor_sc + q) : INFINITY;
@@ -326,20 +313,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (vm >> j) & 1u ? v[j] : -INFINITY;
         }
-        float m = v[0];
+        if (MODE == kModeGroupMax) {
+          // column j of every 32-row block belongs to group j (tiles start at multiples of 128)
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
-        const bool hit = (MODE == kModeTopK) ? (m > thr) : (m >= thr);
-        if (hit) {
-          const int row0 = t * p.tile_scale * kTileR + b * 32;
+          for (int j = 0; j < 32; ++j) gmax[j] = fmaxf(gmax[j], v[j]);
+        } else {
+          float m = v[0];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (MODE == kModeTopK) {
-              if (v[j] > thr) {
-                reg_insert<K>(sc, ix, v[j], row0 + j);
-                thr = sc[K - 1];
-              }
-            } else {
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+          if (m >= thr) {
+            const int row0 = t * p.tile_scale * kTileR + b * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
               if (v[j] >= thr) {
                 if (emitted < p.seg) my_seg[emitted] = make_int2(row0 + j, __float_as_int(v[j]));
                 ++emitted;
@@ -354,11 +339,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
     if (q_real) {
-      if (MODE == kModeTopK) {
-        float* o_sc = p.part_sc + (size_t(chunk) * p.nq + q) * K;
-        int32_t* o_ix = p.part_ix + (size_t(chunk) * p.nq + q) * K;
+      if (MODE == kModeGroupMax) {
+        float4* o = reinterpret_cast<float4*>(p.part_sc + (size_t(chunk) * p.nq + q) * kGroups);
 #pragma unroll
-        for (int j = 0; j < K; ++j) { o_sc[j] = sc[j]; o_ix[j] = ix[j] == 0x7fffffff ? -1 : ix[j]; }
+        for (int j = 0; j < kGroups; j += 4) o[j / 4] = make_float4(gmax[j], gmax[j + 1], gmax[j + 2], gmax[j + 3]);
       } else {
         p.seg_count[size_t(q) * chunks + chunk] = emitted;      // > seg means the segment overflowed
       }
@@ -374,68 +358,37 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------ stage 1b
-// L[q] = k-th best score over the pre-pass partial lists [parts][nq][K] (each sorted, best first).
-// One warp per query, lane-local sorted lists of scores only, then k rounds of warp max + pop.
-template <int K>
+// L[q]: lane g folds group g's maximum over the pre-pass CTAs (coalesced: 32 consecutive floats per
+// CTA and query), then the k-th largest of the 32 group maxima is taken with k warp-max rounds.
+// The groups are disjoint row sets, so that value is reached by k distinct rows: L[q] <= tau.
 __global__ void __launch_bounds__(128)
 floor_kernel(const float* __restrict__ part_sc, int parts, int nq, int k, float* __restrict__ floor_out) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
-  float sc[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) sc[j] = kNoScore;
-  for (int c0 = lane; c0 < parts; c0 += 64) {
-    float v[2][K];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = c0 + 32 * u;
-#pragma unroll
-      for (int j = 0; j < K; ++j) v[u][j] = kNoScore;
-      if (c < parts) {
-        const float* src = part_sc + (size_t(c) * nq + q) * K;
-        if (K >= 4) {
-#pragma unroll
-          for (int j = 0; j < K; j += 4) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(src + j));
-            v[u][j] = x.x; v[u][j + 1] = x.y; v[u][j + 2] = x.z; v[u][j + 3] = x.w;
-          }
-        } else {
-          v[u][0] = __ldg(src);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const float s = v[u][j];
-        if (s > sc[K - 1]) {
-          sc[K - 1] = s;
-#pragma unroll
-          for (int t = K - 1; t > 0; --t)
-            if (sc[t] > sc[t - 1]) { const float ts = sc[t]; sc[t] = sc[t - 1]; sc[t - 1] = ts; }
-        }
-      }
-    }
+  float g = kNoScore;
+  int c = 0;
+  for (; c + 4 <= parts; c += 4) {
+    const float a0 = __ldg(part_sc + (size_t(c) * nq + q) * kGroups + lane);
+    const float a1 = __ldg(part_sc + (size_t(c + 1) * nq + q) * kGroups + lane);
+    const float a2 = __ldg(part_sc + (size_t(c + 2) * nq + q) * kGroups + lane);
+    const float a3 = __ldg(part_sc + (size_t(c + 3) * nq + q) * kGroups + lane);
+    g = fmaxf(fmaxf(g, a0), fmaxf(fmaxf(a1, a2), a3));
   }
+  for (; c < parts; ++c) g = fmaxf(g, __ldg(part_sc + (size_t(c) * nq + q) * kGroups + lane));
   float kth = kNoScore;
   for (int j = 0; j < k; ++j) {
-    float bs = sc[0]; int bl = lane;
+    float bs = g; int bl = lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float os = __shfl_xor_sync(0xffffffffu, bs, o);
       const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
       if (os > bs || (os == bs && ol < bl)) { bs = os; bl = ol; }
     }
-    if (lane == bl) {
-#pragma unroll
-      for (int t = 0; t < K - 1; ++t) sc[t] = sc[t + 1];
-      sc[K - 1] = kNoScore;
-    }
+    if (lane == bl) g = kNoScore;          // pop
     kth = bs;
   }
-  if (lane == 0) floor_out[q] = kth;      // -1 when the sample held fewer than k valid rows
+  if (lane == 0) floor_out[q] = kth;      // -1 when the sample held fewer than k usable groups
 }
 
 // ------------------------------------------------------------------------------------------ stage 3
@@ -674,7 +627,7 @@ int tc_supported(int dim, int metric, const char** why) {
 
 struct TcPlan {
   int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
-  size_t off_pre_sc, off_pre_ix, off_floor, off_cnt, off_cand, off_flag, total;
+  size_t off_pre_sc, off_floor, off_cnt, off_cand, off_flag, total;
 };
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
@@ -696,14 +649,15 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   };
   pl->chunks_pre = chunks_for((tiles_all + stride - 1) / stride);
   // fewer, longer pre-pass CTAs: the floor fold costs O(parts) per query
-  static const int pre_cap = []() { const char* e = getenv("FRG_TC_PRE_CHUNKS"); return e ? atoi(e) : 74; }();
+  static const int pre_cap = []() { const char* e = getenv("FRG_TC_PRE_CHUNKS"); return e ? atoi(e) : 148; }();
   if (pre_cap > 0 && pl->chunks_pre > pre_cap) pl->chunks_pre = pre_cap;
   pl->chunks_main = chunks_for(tiles_all);
   pl->kreg = reg_k(k);
   // Expected candidates per query ~ 2 * stride * Gamma(k): the k-th best of a 1/stride sample sits
   // at tail mass Gamma(k)/n_view, and the 2*eps widening about doubles the count at dim 512.  Room for
   // mean + ~10 sigma keeps the overflow probability negligible; the exact fallback covers the rest.
-  int stage_entries = int(2.0 * stride * (k + 10.0 * sqrt(double(k)) + 10.0));
+  // (x1.5: the group-max floor is a little looser than an exact k-th best of the sample)
+  int stage_entries = int(3.0 * stride * (k + 10.0 * sqrt(double(k)) + 10.0));
   if (stage_entries < 256) stage_entries = 256;
   if (stage_entries > 8192) stage_entries = 8192;
   pl->stage_entries = stage_entries;
@@ -712,8 +666,7 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   pl->seg = seg;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-  pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
-  pl->off_pre_ix = take(size_t(pl->chunks_pre) * nq * pl->kreg * 4);
+  pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * kGroups * 4);
   pl->off_floor = take(size_t(nq) * 4);
   pl->off_cnt = take(size_t(nq) * pl->chunks_main * 4);
   pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
@@ -721,23 +674,23 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   pl->total = off;
 }
 
-template <int MODE, int K, bool MASKED>
+template <int MODE, bool MASKED>
 static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p, int qtiles, int chunks,
                           cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p.dim);
-  FRG_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE, K, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  FRG_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 int(tc_smem_bytes(512))));
-  tc_scan_kernel<MODE, K, MASKED><<<dim3(qtiles, chunks), kTcThreads, smem, st>>>(qm, gm, p);
+  tc_scan_kernel<MODE, MASKED><<<dim3(qtiles, chunks), kTcThreads, smem, st>>>(qm, gm, p);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;
 }
 
-template <int MODE, int K>
+template <int MODE>
 static int launch_tc_scan_m(bool masked, const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p,
                             int qtiles, int chunks, cudaStream_t st) {
-  return masked ? launch_tc_scan<MODE, K, true>(qm, gm, p, qtiles, chunks, st)
-                : launch_tc_scan<MODE, K, false>(qm, gm, p, qtiles, chunks, st);
+  return masked ? launch_tc_scan<MODE, true>(qm, gm, p, qtiles, chunks, st)
+                : launch_tc_scan<MODE, false>(qm, gm, p, qtiles, chunks, st);
 }
 
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
@@ -755,7 +708,6 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   TcPlan pl;
   tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
   float* pre_sc = reinterpret_cast<float*>(ws + pl.off_pre_sc);
-  int32_t* pre_ix = reinterpret_cast<int32_t*>(ws + pl.off_pre_ix);
   float* floor_sc = reinterpret_cast<float*>(ws + pl.off_floor);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
@@ -773,35 +725,21 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   TcScanParams p{};
   p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   // 1. pre-pass over the sampled tiles
-  p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.part_sc = pre_sc; p.part_ix = pre_ix;
-  int rc;
+  p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.part_sc = pre_sc;
   profile_begin(st, kStagePrepass);
-  switch (pl.kreg) {
-    case 1: rc = launch_tc_scan_m<kModeTopK, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
-    case 4: rc = launch_tc_scan_m<kModeTopK, 4>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
-    case 8: rc = launch_tc_scan_m<kModeTopK, 8>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
-    default: rc = launch_tc_scan_m<kModeTopK, 16>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st); break;
-  }
-  FRG_CHECK(rc);
+  FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
   profile_end(st, 1);
   profile_begin(st, kStageFloor);
-  {
-    const int fgrid = (nq + 3) / 4;
-    switch (pl.kreg) {
-      case 1: floor_kernel<1><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
-      case 4: floor_kernel<4><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
-      case 8: floor_kernel<8><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
-      default: floor_kernel<16><<<fgrid, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc); break;
-    }
-    note_launch(nullptr);
-    FRG_CUDA(cudaGetLastError());
-  }
+  FRG_CUDA(cudaFuncSetAttribute(floor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  floor_kernel<<<(nq + 3) / 4, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
   profile_end(st, 1);
   // 2. filter over the whole plane
   p.tile_scale = 1; p.floor_sc = floor_sc; p.seg = pl.seg;
   p.seg_count = cnt; p.cand = cand;
   profile_begin(st, kStageDominant);
-  rc = launch_tc_scan_m<kModeFilter, 1>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
+  int rc = launch_tc_scan_m<kModeFilter>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
   FRG_CHECK(rc);
   profile_end(st, 1);
   // 3. select + exact rescoring
@@ -812,6 +750,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
 #define FRG_SELECT(KK)                                                                                          \
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                 int(kSelectWarps * 8192 * sizeof(int2))));                                      \
+  FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
   select_rescore_kernel<KK><<<grid, kSelectWarps * 32, sel_smem, st>>>(cand, cnt, pl.chunks_main, pl.seg,       \
       pl.stage_entries, nq, k, s->dim, qn, s->master, rs, threshold, row_offset, out_rows, out_scores,          \
       out_accept, flagged, n_flagged)
