@@ -120,9 +120,12 @@ static int launch_merge(const float* scores, const RowT* rows, int parts, int nq
   const int grid = (nq + 3) / 4;
   const int ie = internal_euclid ? 1 : 0;
 #define FRG_MERGE(K)                                                                                            \
-  cudaFuncSetAttribute(merge_kernel<RowT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);             \
-  merge_kernel<RowT, K><<<grid, 128, 0, st>>>(scores, rows, parts, nq, k_in, k_out, metric, \
-      threshold, row_offset, ie, q_index, n_active, out_rows, out_scores, out_accept)
+  do {                                                                                                          \
+    cudaFuncSetAttribute(merge_kernel<RowT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);           \
+    merge_kernel<RowT, K><<<grid, 128, 0, st>>>(scores, rows, parts, nq, k_in, k_out, metric, threshold,        \
+                                                row_offset, ie, q_index, n_active, out_rows, out_scores,       \
+                                                out_accept);                                                    \
+  } while (0)
   if (k_out == 1) FRG_MERGE(1);
   else if (k_out <= 4) FRG_MERGE(4);
   else if (k_out <= 8) FRG_MERGE(8);
