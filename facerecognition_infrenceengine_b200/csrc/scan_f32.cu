@@ -11,7 +11,7 @@
 // matrix ever reaches HBM.
 //
 // Algorithmic bytes per launch = rows * dim * 4; grid = 2 CTAs x SM count.
-#include "frg_internal.cuh"
+#include "merge_device.cuh"
 
 namespace frg {
 
@@ -210,18 +210,22 @@ scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ ta
 }
 
 // Exact re-do of the queries a tensor-core pass could not settle (candidate overflow).  The list
-// and its length live on the device; the kernel loops over it, so nothing waits for the host and an
-// empty list costs one idle launch.
-template <int NJ, int QB, int METRIC>
+// and its length live on the device; the kernel loops over it, so nothing waits for the host, and
+// the CTA that finishes last folds the per-CTA lists into the final results (ticket counter), so an
+// empty list costs ONE idle launch.  ctl[0] = number of flagged queries, ctl[1] = ticket (starts 0).
+template <int NJ, int QB, int METRIC, int KMAX>
 __global__ void __launch_bounds__(kScanWarps * 32, 2)
 scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
                         const float* __restrict__ qn, int nq_total, const int* __restrict__ flagged,
-                        const int* __restrict__ n_flagged, int K, int32_t tenant,
-                        float* __restrict__ part_sc, int32_t* __restrict__ part_ix) {
+                        int* __restrict__ ctl, int K, int32_t tenant, float threshold, int64_t row_offset,
+                        float* __restrict__ part_sc, int32_t* __restrict__ part_ix,
+                        int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
+                        uint8_t* __restrict__ out_accept) {
   extern __shared__ unsigned char smem_raw[];
   float* l_sc = reinterpret_cast<float*>(smem_raw);
   int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
-  const int nf = *n_flagged;
+  __shared__ int is_last;
+  const int nf = ctl[0];
   for (int q0 = 0; q0 < nf; q0 += QB) {
     const int nq_pass = nf - q0 < QB ? nf - q0 : QB;
     int q_of[QB];
@@ -231,6 +235,16 @@ scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restr
                               l_sc, l_ix);
     __syncthreads();
   }
+  if (nf == 0) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ctl + 1, 1) == int(gridDim.x) - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int slot = threadIdx.x >> 5; slot < nf; slot += kScanWarps)
+    merge_one<int32_t, KMAX>(part_sc, part_ix, int(gridDim.x), nq_total, K, K, METRIC, threshold, row_offset, 0,
+                             slot, flagged[slot], out_rows, out_scores, out_accept);
 }
 
 static int scan_grid(const ScanArgs& a) {
@@ -316,20 +330,32 @@ int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, floa
                           out_accept, st);
 }
 
-template <int NJ, int QB>
-static int launch_flagged_t(const ScanArgs& a, int grid, const int* flagged, const int* n_flagged, float* ps,
-                            int32_t* pi, cudaStream_t st) {
+template <int NJ, int QB, int KMAX>
+static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int* ctl, float threshold,
+                            int64_t row_offset, float* ps, int32_t* pi, int64_t* out_rows, float* out_scores,
+                            uint8_t* out_accept, cudaStream_t st) {
   const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
-  FRG_CUDA(cudaFuncSetAttribute(scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE>,
-                                cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE><<<grid, kScanWarps * 32, smem, st>>>(
-      a.master, a.tags, a.rows, a.qn, a.nq, flagged, n_flagged, a.k, a.tenant, ps, pi);
+  auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX>;
+  FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
+                                            threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;
 }
 
-int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, const int* n_flagged, int64_t row_offset,
+template <int NJ, int QB>
+static int launch_flagged_t(const ScanArgs& a, int grid, const int* flagged, int* ctl, float threshold,
+                            int64_t row_offset, float* ps, int32_t* pi, int64_t* out_rows, float* out_scores,
+                            uint8_t* out_accept, cudaStream_t st) {
+  if (a.k == 1) return launch_flagged_k<NJ, QB, 1>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
+  if (a.k <= 4) return launch_flagged_k<NJ, QB, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
+  if (a.k <= 8) return launch_flagged_k<NJ, QB, 8>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
+  return launch_flagged_k<NJ, QB, 16>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
+}
+
+// ctl: device int[2] = {number of flagged queries, ticket counter (0)}
+int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, int* ctl, int64_t row_offset,
                             float threshold, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
                             cudaStream_t st) {
   if (a.rows <= 0 || a.nq <= 0) return FRG_OK;
@@ -341,14 +367,11 @@ int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, const int* n_
   int32_t* pi = reinterpret_cast<int32_t*>(ps + n_part);
   int rc;
   switch (a.dim) {
-    case 128: rc = launch_flagged_t<1, 4>(a, grid, flagged, n_flagged, ps, pi, st); break;
-    case 256: rc = launch_flagged_t<2, 4>(a, grid, flagged, n_flagged, ps, pi, st); break;
-    case 512: rc = launch_flagged_t<4, 4>(a, grid, flagged, n_flagged, ps, pi, st); break;
+    case 128: rc = launch_flagged_t<1, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st); break;
+    case 256: rc = launch_flagged_t<2, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st); break;
+    case 512: rc = launch_flagged_t<4, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st); break;
     default: set_error("flagged scan: dim %d not built", a.dim); rc = FRG_ERR_UNSUPPORTED; break;
   }
-  if (rc == FRG_OK)
-    rc = launch_merge_flagged(ps, pi, grid, a.nq, a.k, threshold, row_offset, flagged, n_flagged, out_rows,
-                              out_scores, out_accept, st);
   cudaError_t e = cudaFreeAsync(ws, st);
   if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
   return rc;

@@ -151,6 +151,17 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTile
 enum TcMode { kModeGroupMax = 0, kModeFilter = 1 };
 constexpr int kGroups = 32;
 
+// order-preserving float <-> uint32 key, so that the group maxima of all pre-pass CTAs can be folded
+// with one atomicMax per (query, group)
+__device__ __forceinline__ uint32_t float_key(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+constexpr uint32_t kNoScoreKey = 0x407FFFFFu;     // float_key(-1.0f)
+
 struct TcScanParams {
   int dim;                 // 512 etc. (multiple of 64)
   int n_rows;              // gallery rows
@@ -158,10 +169,10 @@ struct TcScanParams {
   int nq;                  // real queries
   int32_t tenant;
   const int32_t* tags;     // per REAL row
-  // GROUPMAX output: [chunk][nq][32] running maxima of the row groups (row mod 32)
-  float* part_sc;
+  // GROUPMAX output: [nq][32] maxima of the row groups (row mod 32) as ordered keys, atomicMax-folded
+  uint32_t* group_key;
   // FILTER inputs / outputs
-  const float* floor_sc;   // [nq] L[q]: k-th best coarse score of the pre-pass sample (-1: fewer than k)
+  int k;                   // L[q] = k-th largest of the 32 group maxima (computed in the prologue)
   int seg;                 // candidate slots per (query, chunk) segment
   int* seg_count;          // [nq][chunks]
   int2* cand;              // [nq][chunks][seg] (row, score bits)
@@ -277,12 +288,35 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < kGroups; ++j) gmax[j] = kNoScore;
     } else {
-      // L[q]: k-th best coarse score the pre-pass saw (floor_kernel), a lower bound of tau
-      const float floor_v = q_real ? __ldg(p.floor_sc + q) : INFINITY;
-      // fewer than k valid rows in the pre-pass sample: no usable bound, every valid row is a candidate
-      // (finite, so that masked columns, which are set to -inf, still fail the comparison)
-      thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
-      if (q_real) my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
+      // L[q] = k-th largest of the 32 group maxima the pre-pass left behind.  The groups are
+      // disjoint row sets, so that value is reached by k distinct valid rows: L[q] <= tau.
+      if (q_real) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.group_key + size_t(q) * kGroups);
+#pragma unroll
+        for (int j = 0; j < kGroups; j += 4) {
+          const uint4 x = __ldg(src + j / 4);
+          gmax[j] = key_float(x.x); gmax[j + 1] = key_float(x.y);
+          gmax[j + 2] = key_float(x.z); gmax[j + 3] = key_float(x.w);
+        }
+        float floor_v = kNoScore;
+        for (int r = 0; r < p.k; ++r) {
+          float m = gmax[0];
+#pragma unroll
+          for (int j = 1; j < kGroups; ++j) m = fmaxf(m, gmax[j]);
+          floor_v = m;
+          bool popped = false;                 // remove ONE instance of the maximum
+#pragma unroll
+          for (int j = 0; j < kGroups; ++j) {
+            const bool hit = !popped && gmax[j] == m;
+            gmax[j] = hit ? -INFINITY : gmax[j];
+            popped |= hit;
+          }
+        }
+        // fewer than k usable groups in the sample: no bound, every valid row is a candidate
+        // (finite, so that masked columns, which are set to -inf, still fail the comparison)
+        thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
+        my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
+      }
     }
 
     int buf = 0; uint32_t tphase = 0;
@@ -340,9 +374,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     }
     if (q_real) {
       if (MODE == kModeGroupMax) {
-        float4* o = reinterpret_cast<float4*>(p.part_sc + (size_t(chunk) * p.nq + q) * kGroups);
+        uint32_t* o = p.group_key + size_t(q) * kGroups;
 #pragma unroll
-        for (int j = 0; j < kGroups; j += 4) o[j / 4] = make_float4(gmax[j], gmax[j + 1], gmax[j + 2], gmax[j + 3]);
+        for (int j = 0; j < kGroups; ++j)
+          if (gmax[j] > kNoScore) atomicMax(o + j, float_key(gmax[j]));
       } else {
         p.seg_count[size_t(q) * chunks + chunk] = emitted;      // > seg means the segment overflowed
       }
@@ -355,40 +390,6 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     __syncwarp();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-}
-
-// ------------------------------------------------------------------------------------------ stage 1b
-// L[q]: lane g folds group g's maximum over the pre-pass CTAs (coalesced: 32 consecutive floats per
-// CTA and query), then the k-th largest of the 32 group maxima is taken with k warp-max rounds.
-// The groups are disjoint row sets, so that value is reached by k distinct rows: L[q] <= tau.
-__global__ void __launch_bounds__(128)
-floor_kernel(const float* __restrict__ part_sc, int parts, int nq, int k, float* __restrict__ floor_out) {
-  const int lane = threadIdx.x & 31;
-  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= nq) return;
-  float g = kNoScore;
-  int c = 0;
-  for (; c + 4 <= parts; c += 4) {
-    const float a0 = __ldg(part_sc + (size_t(c) * nq + q) * kGroups + lane);
-    const float a1 = __ldg(part_sc + (size_t(c + 1) * nq + q) * kGroups + lane);
-    const float a2 = __ldg(part_sc + (size_t(c + 2) * nq + q) * kGroups + lane);
-    const float a3 = __ldg(part_sc + (size_t(c + 3) * nq + q) * kGroups + lane);
-    g = fmaxf(fmaxf(g, a0), fmaxf(fmaxf(a1, a2), a3));
-  }
-  for (; c < parts; ++c) g = fmaxf(g, __ldg(part_sc + (size_t(c) * nq + q) * kGroups + lane));
-  float kth = kNoScore;
-  for (int j = 0; j < k; ++j) {
-    float bs = g; int bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (os > bs || (os == bs && ol < bl)) { bs = os; bl = ol; }
-    }
-    if (lane == bl) g = kNoScore;          // pop
-    kth = bs;
-  }
-  if (lane == 0) floor_out[q] = kth;      // -1 when the sample held fewer than k usable groups
 }
 
 // ------------------------------------------------------------------------------------------ stage 3
@@ -430,7 +431,7 @@ __device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], 
 }
 
 constexpr int kSelectWarps = 2;
-constexpr int kMaxChunks = 160;       // >= SM count of the part: candidate segments per query
+constexpr int kMaxChunks = 160;       // >= SM count of the part (multiple of 32): candidate segments per query
 
 template <int K>
 __global__ void __launch_bounds__(kSelectWarps * 32)
@@ -455,9 +456,16 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg
   const int2* mine = cand + size_t(q) * chunks * seg;
   bool overflow = false;
   int n = 0;
-  for (int c0 = 0; c0 < chunks; c0 += 32) {
-    const int c = c0 + lane;
-    int have = c < chunks ? cnt[c] : 0;
+  int have_all[kMaxChunks / 32];
+#pragma unroll
+  for (int i = 0; i < kMaxChunks / 32; ++i) {          // all count loads in flight at once
+    const int c = i * 32 + lane;
+    have_all[i] = c < chunks ? __ldg(cnt + c) : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxChunks / 32; ++i) {
+    const int c = i * 32 + lane;
+    int have = have_all[i];
     if (have > seg) { overflow = true; have = seg; }
     int incl = have;
 #pragma unroll
@@ -528,31 +536,33 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg
   if (m > kMaxKeep) { overflow = true; m = kMaxKeep; }
   __syncwarp();
 
-  // (c) exact fp32 rescoring, 4 rows in flight per warp (coalesced 16-byte loads, same element ->
+  // (c) exact fp32 rescoring, 8 rows in flight per warp (coalesced 16-byte loads, same element ->
   //     lane mapping and summation order as the streaming scan)
+  constexpr int kRescoreRows = 8;
   const int nvec = dim >> 2;
   const float4* qq = reinterpret_cast<const float4*>(qn + size_t(q) * dim);
-  for (int i0 = 0; i0 < m; i0 += 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4* g[4];
+  for (int i0 = 0; i0 < m; i0 += kRescoreRows) {
+    float a[kRescoreRows];
+    const float4* g[kRescoreRows];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kRescoreRows; ++u) {
+      a[u] = 0.f;
       const int i = i0 + u < m ? i0 + u : i0;
       g[u] = reinterpret_cast<const float4*>(master + size_t(keep_row[w][i]) * dim);
     }
     for (int v = lane; v < nvec; v += 32) {
       const float4 y = __ldg(qq + v);
-      float4 x[4];
+      float4 x[kRescoreRows];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = __ldg(g[u] + v);
+      for (int u = 0; u < kRescoreRows; ++u) x[u] = __ldg(g[u] + v);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kRescoreRows; ++u) {
         a[u] = fmaf(x[u].x, y.x, a[u]); a[u] = fmaf(x[u].y, y.y, a[u]);
         a[u] = fmaf(x[u].z, y.z, a[u]); a[u] = fmaf(x[u].w, y.w, a[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kRescoreRows; ++u) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
       if (lane == 0 && i0 + u < m) keep_sc[w][i0 + u] = a[u];
@@ -627,7 +637,7 @@ int tc_supported(int dim, int metric, const char** why) {
 
 struct TcPlan {
   int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
-  size_t off_pre_sc, off_floor, off_cnt, off_cand, off_flag, total;
+  size_t off_keys, off_cnt, off_cand, off_flag, total;
 };
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
@@ -666,11 +676,10 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   pl->seg = seg;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-  pl->off_pre_sc = take(size_t(pl->chunks_pre) * nq * kGroups * 4);
-  pl->off_floor = take(size_t(nq) * 4);
+  pl->off_keys = take(size_t(nq) * kGroups * 4);
   pl->off_cnt = take(size_t(nq) * pl->chunks_main * 4);
   pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
-  pl->off_flag = take(size_t(nq) * 4 + 4);
+  pl->off_flag = take(size_t(nq) * 4 + 8);     // flagged[nq], count, ticket
   pl->total = off;
 }
 
@@ -699,6 +708,15 @@ size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
   return pl.total;
 }
 
+// the two pieces of the workspace the query-prep kernel initialises (group keys := key(-1), flag count := 0)
+void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_count, unsigned char* ws,
+                               uint32_t** keys, int** n_flagged) {
+  TcPlan pl;
+  tc_plan(rows, dim, nq, k, sm_count, &pl);
+  *keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
+  *n_flagged = reinterpret_cast<int*>(ws + pl.off_flag) + nq;
+}
+
 // qn / qb: normalised fp32 queries and their bf16 image [nq][dim]; ws: tc_workspace_bytes() of scratch.
 // Leaves the overflowed queries in (flagged, n_flagged) for the caller's exact fallback pass.
 int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
@@ -707,8 +725,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
                     int** n_flagged_out, cudaStream_t st) {
   TcPlan pl;
   tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
-  float* pre_sc = reinterpret_cast<float*>(ws + pl.off_pre_sc);
-  float* floor_sc = reinterpret_cast<float*>(ws + pl.off_floor);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
@@ -720,23 +737,16 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   CUtensorMap qm, gm_full;
   FRG_CHECK(make_map(&qm, qb, s->dim, nq, size_t(s->dim) * 2, kTileQ));
   FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));
-  FRG_CUDA(cudaMemsetAsync(n_flagged, 0, sizeof(int), st));
 
   TcScanParams p{};
   p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   // 1. pre-pass over the sampled tiles
-  p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.part_sc = pre_sc;
+  p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.group_key = keys; p.k = k;
   profile_begin(st, kStagePrepass);
   FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
   profile_end(st, 1);
-  profile_begin(st, kStageFloor);
-  FRG_CUDA(cudaFuncSetAttribute(floor_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  floor_kernel<<<(nq + 3) / 4, 128, 0, st>>>(pre_sc, pl.chunks_pre, nq, k, floor_sc);
-  note_launch(nullptr);
-  FRG_CUDA(cudaGetLastError());
-  profile_end(st, 1);
   // 2. filter over the whole plane
-  p.tile_scale = 1; p.floor_sc = floor_sc; p.seg = pl.seg;
+  p.tile_scale = 1; p.seg = pl.seg;
   p.seg_count = cnt; p.cand = cand;
   profile_begin(st, kStageDominant);
   int rc = launch_tc_scan_m<kModeFilter>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
