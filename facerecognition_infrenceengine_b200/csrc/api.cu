@@ -460,7 +460,7 @@ static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_mat
   FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + part_bytes, st));
   float* qn = reinterpret_cast<float*>(ws);
   a.qn = qn;
-  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE, qn, nullptr, nullptr, nullptr, st);
+  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE, qn, nullptr, nullptr, nullptr, nullptr, st);
   if (rc == FRG_OK)
     rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
   g_variant = "scan_f32";
@@ -484,10 +484,10 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   float* qn = reinterpret_cast<float*>(ws);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes);
   int* flagged = nullptr; int* n_flagged = nullptr;
-  uint32_t* keys = nullptr; int* nf0 = nullptr;
-  tc_workspace_init_targets(s->rows, s->dim, nq, k, sm_count, ws + qn_bytes + qb_bytes, &keys, &nf0);
+  uint32_t* keys = nullptr; int* ct0 = nullptr; int* nf0 = nullptr;
+  tc_workspace_init_targets(s->rows, s->dim, nq, k, sm_count, ws + qn_bytes + qb_bytes, &keys, &ct0, &nf0);
   profile_begin(st, kStagePrep);
-  int rc = launch_normalise_queries(q, nq, s->dim, true, qn, qb, keys, nf0, st);
+  int rc = launch_normalise_queries(q, nq, s->dim, true, qn, qb, keys, ct0, nf0, st);
   profile_end(st, 1);
   if (rc == FRG_OK)
     rc = launch_tc_match(s, qn, qb, nq, k, p->tenant, rescore, p->threshold, p->row_offset, ws + qn_bytes + qb_bytes,

@@ -95,7 +95,8 @@ int store_begin_read(frg_store* s, cudaStream_t stream);
 // ---- kernels' host launchers (defined in the .cu named in the comment) ----------------------
 // queries.cu: qn[f] = q[f] / ||q[f]|| (fp32), optional bf16 image
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
-                             __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* n_flagged, cudaStream_t st);
+                             __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* cand_total, int* n_flagged,
+                             cudaStream_t st);
 
 // scan_f32.cu: exact scan; writes nq x k best (score desc, row asc) into rows32/scores
 struct ScanArgs {
@@ -124,7 +125,7 @@ int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq
 int tc_supported(int dim, int metric, const char** why);
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count);
 void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_count, unsigned char* ws,
-                               uint32_t** keys, int** n_flagged);
+                               uint32_t** keys, int** cand_total, int** n_flagged);
 int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
                     bool rescore, float threshold, int64_t row_offset, unsigned char* ws, int sm_count,
                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,

@@ -9,13 +9,15 @@ namespace frg {
 __global__ void __launch_bounds__(128)
 normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int normalise,
                          float* __restrict__ qn, __nv_bfloat16* __restrict__ qb,
-                         uint32_t* __restrict__ group_keys, int* __restrict__ n_flagged) {
+                         uint32_t* __restrict__ group_keys, int* __restrict__ cand_total,
+                         int* __restrict__ n_flagged) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= nq) return;
   // per-query scratch of the tensor-core pipeline starts from "nothing seen": 32 group maxima at the
   // ordered key of -1.0f, flagged-query counter at 0 (saves a memset node per match)
   if (group_keys) group_keys[size_t(w) * 32 + lane] = 0x407FFFFFu;
+  if (cand_total && lane == 0) cand_total[w] = 0;
   if (n_flagged && w == 0 && lane < 2) n_flagged[lane] = 0;      // count, ticket
   const float4* src = reinterpret_cast<const float4*>(q + size_t(w) * dim);
   const int nvec = dim >> 2;
@@ -49,13 +51,14 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
 }
 
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
-                             __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* n_flagged, cudaStream_t st) {
+                             __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* cand_total, int* n_flagged,
+                             cudaStream_t st) {
   if (nq <= 0) return FRG_OK;
   const int warps_per_block = 4;
   // same smem/L1 split as the tensor-core kernels that follow: no carve-out switch between launches
   FRG_CUDA(cudaFuncSetAttribute(normalise_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   normalise_queries_kernel<<<(nq + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(
-      q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, n_flagged);
+      q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, cand_total, n_flagged);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;

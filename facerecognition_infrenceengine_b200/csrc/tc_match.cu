@@ -173,9 +173,11 @@ struct TcScanParams {
   uint32_t* group_key;
   // FILTER inputs / outputs
   int k;                   // L[q] = k-th largest of the 32 group maxima (computed in the prologue)
-  int seg;                 // candidate slots per (query, chunk) segment
-  int* seg_count;          // [nq][chunks]
-  int2* cand;              // [nq][chunks][seg] (row, score bits)
+  int seg;                 // candidate slots per (query, chunk) private segment
+  int2* cand;              // [nq][chunks][seg] (row, score bits): written while scanning
+  int* cand_total;         // [nq] candidates of the query over all chunks (atomicAdd at the CTA's end)
+  int2* dense;             // [nq][dense_cap]: the segments, packed per query for the select kernel
+  int dense_cap;
 };
 
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
@@ -379,7 +381,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         for (int j = 0; j < kGroups; ++j)
           if (gmax[j] > kNoScore) atomicMax(o + j, float_key(gmax[j]));
       } else {
-        p.seg_count[size_t(q) * chunks + chunk] = emitted;      // > seg means the segment overflowed
+        // pack this thread's few candidates into the query's dense list: one atomicAdd per (query, CTA),
+        // outside the scan loop.  A private-segment overflow poisons the total so that select flags it.
+        const int base = atomicAdd(p.cand_total + q, emitted > p.seg ? (1 << 24) : emitted);
+        const int mine_n = emitted < p.seg ? emitted : p.seg;
+        for (int i = 0; i < mine_n; ++i)
+          if (base + i < p.dense_cap) p.dense[size_t(q) * p.dense_cap + base + i] = my_seg[i];
       }
     }
   }
@@ -435,7 +442,7 @@ constexpr int kMaxChunks = 160;       // >= SM count of the part (multiple of 32
 
 template <int K>
 __global__ void __launch_bounds__(kSelectWarps * 32)
-select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg_count, int chunks, int seg,
+select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ cand_total,
                       int kStage, int nq, int k, int dim, const float* __restrict__ qn,
                       const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
@@ -449,44 +456,17 @@ select_rescore_kernel(const int2* __restrict__ cand, const int* __restrict__ seg
   if (q >= nq) return;
   int2* stage = stage_all + size_t(w) * kStage;
 
-  // gather this query's segments into shared memory: exclusive prefix of the segment counts, then
-  // every staged slot finds its (segment, offset) by binary search - all candidate loads independent
-  __shared__ int seg_prefix[kSelectWarps][kMaxChunks + 1];
-  const int* cnt = seg_count + size_t(q) * chunks;
-  const int2* mine = cand + size_t(q) * chunks * seg;
-  bool overflow = false;
-  int n = 0;
-  int have_all[kMaxChunks / 32];
+  // stage this query's dense candidate list in shared memory (coalesced, 4 loads in flight per lane)
+  const int total = cand_total[q];
+  bool overflow = total > kStage;                    // also set by a poisoned total (segment overflow)
+  const int n = overflow ? kStage : total;
+  const int2* mine = dense + size_t(q) * kStage;
+  for (int c0 = lane; c0 < n; c0 += 128) {
+    int2 e[4];
 #pragma unroll
-  for (int i = 0; i < kMaxChunks / 32; ++i) {          // all count loads in flight at once
-    const int c = i * 32 + lane;
-    have_all[i] = c < chunks ? __ldg(cnt + c) : 0;
-  }
+    for (int u = 0; u < 4; ++u) if (c0 + 32 * u < n) e[u] = mine[c0 + 32 * u];
 #pragma unroll
-  for (int i = 0; i < kMaxChunks / 32; ++i) {
-    const int c = i * 32 + lane;
-    int have = have_all[i];
-    if (have > seg) { overflow = true; have = seg; }
-    int incl = have;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    if (c < chunks) seg_prefix[w][c] = n + incl - have;
-    n += __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lane == 0) seg_prefix[w][chunks] = n;
-  overflow = __any_sync(0xffffffffu, overflow);
-  if (n > kStage) { overflow = true; n = kStage; }
-  __syncwarp();
-  for (int pos = lane; pos < n; pos += 32) {
-    int lo = 0, hi = chunks;                 // largest c with seg_prefix[c] <= pos
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (seg_prefix[w][mid] <= pos) lo = mid; else hi = mid;
-    }
-    stage[pos] = mine[size_t(lo) * seg + (pos - seg_prefix[w][lo])];
+    for (int u = 0; u < 4; ++u) if (c0 + 32 * u < n) stage[c0 + 32 * u] = e[u];
   }
   __syncwarp();
 
@@ -637,7 +617,7 @@ int tc_supported(int dim, int metric, const char** why) {
 
 struct TcPlan {
   int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
-  size_t off_keys, off_cnt, off_cand, off_flag, total;
+  size_t off_keys, off_cnt, off_cand, off_dense, off_flag, total;
 };
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
@@ -677,8 +657,9 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   pl->off_keys = take(size_t(nq) * kGroups * 4);
-  pl->off_cnt = take(size_t(nq) * pl->chunks_main * 4);
+  pl->off_cnt = take(size_t(nq) * 4);
   pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
+  pl->off_dense = take(size_t(nq) * stage_entries * 8);
   pl->off_flag = take(size_t(nq) * 4 + 8);     // flagged[nq], count, ticket
   pl->total = off;
 }
@@ -708,12 +689,13 @@ size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
   return pl.total;
 }
 
-// the two pieces of the workspace the query-prep kernel initialises (group keys := key(-1), flag count := 0)
+// the pieces of the workspace the query-prep kernel initialises (group keys := key(-1), counters := 0)
 void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_count, unsigned char* ws,
-                               uint32_t** keys, int** n_flagged) {
+                               uint32_t** keys, int** cand_total, int** n_flagged) {
   TcPlan pl;
   tc_plan(rows, dim, nq, k, sm_count, &pl);
   *keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
+  *cand_total = reinterpret_cast<int*>(ws + pl.off_cnt);
   *n_flagged = reinterpret_cast<int*>(ws + pl.off_flag) + nq;
 }
 
@@ -728,6 +710,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
+  int2* dense = reinterpret_cast<int2*>(ws + pl.off_dense);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
   int* n_flagged = flagged + nq;
   *flagged_out = flagged;
@@ -747,7 +730,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   profile_end(st, 1);
   // 2. filter over the whole plane
   p.tile_scale = 1; p.seg = pl.seg;
-  p.seg_count = cnt; p.cand = cand;
+  p.cand = cand; p.cand_total = cnt; p.dense = dense; p.dense_cap = pl.stage_entries;
   profile_begin(st, kStageDominant);
   int rc = launch_tc_scan_m<kModeFilter>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
   FRG_CHECK(rc);
@@ -761,9 +744,8 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                 int(kSelectWarps * 8192 * sizeof(int2))));                                      \
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-  select_rescore_kernel<KK><<<grid, kSelectWarps * 32, sel_smem, st>>>(cand, cnt, pl.chunks_main, pl.seg,       \
-      pl.stage_entries, nq, k, s->dim, qn, s->master, rs, threshold, row_offset, out_rows, out_scores,          \
-      out_accept, flagged, n_flagged)
+  select_rescore_kernel<KK><<<grid, kSelectWarps * 32, sel_smem, st>>>(dense, cnt, pl.stage_entries, nq, k,     \
+      s->dim, qn, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
   switch (pl.kreg) {
     case 1: FRG_SELECT(1); break;
     case 4: FRG_SELECT(4); break;
