@@ -459,7 +459,12 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   // stage this query's dense candidate list in shared memory (coalesced, 4 loads in flight per lane)
   const int total = cand_total[q];
   bool overflow = total > kStage;                    // also set by a poisoned total (segment overflow)
-  const int n = overflow ? kStage : total;
+  if (overflow) {
+    // the dense list is incomplete (and partly unwritten): leave the query to the exact fallback
+    if (lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
+    return;
+  }
+  const int n = total;
   const int2* mine = dense + size_t(q) * kStage;
   for (int c0 = lane; c0 < n; c0 += 128) {
     int2 e[4];
