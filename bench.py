@@ -175,12 +175,25 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, batch):
-    return {"workload": "configs[1]: 512-d cosine, 1M-template gallery, top-5, single B200",
-            "gallery_rows": args.rows, "dim": args.dim, "batch": batch, "k": args.k, "threshold": 0.45,
-            "variant": args.variant,
+def workload_config(args, batch, world=1):
+    cfg = {"workload": "configs[1]: 512-d cosine, 1M-template gallery, top-5, single B200",
+           "gallery_rows": args.rows, "dim": args.dim, "batch": batch, "k": args.k, "threshold": 0.45,
+           "variant": args.variant}
+    if world > 1 and args.shard == "gallery":
+        cfg.update({"workload": "configs[1] per GPU, gallery row-sharded over %d GPUs (%d rows each, %d total), "
+                                "queries replicated, NCCL all-gather of per-rank top-k + k-way merge" % (
+                                    world, args.rows, args.rows * world),
+                    "sharding": "gallery rows", "gallery_rows_total": args.rows * world,
+                    "value_definition": "1M-row-gallery-equivalent queries/s = batch * (total_rows / gallery_rows) / "
+                                        "step time: a query matched against N x 1M rows counts as N queries at "
+                                        "1M x 512; raw queries/s is in queries_per_s_raw"})
+    elif world > 1:
+        cfg.update({"workload": "configs[1] replicated on %d GPUs, query stream sharded across ranks, no collective" % world,
+                    "sharding": "queries (replicas)"})
+    cfg.update({
             "l2_policy": "inputs larger than L2 (gallery %.2f GB fp32 + %.2f GB bf16 plane vs 126 MB L2)" % (
-                args.rows * args.dim * 4 / 1e9, args.rows * args.dim * 2 / 1e9)}
+                args.rows * args.dim * 4 / 1e9, args.rows * args.dim * 2 / 1e9)})
+    return cfg
 
 
 def roofline_for(variant, n, dim, F, dom_launch_ms, peaks):
@@ -212,17 +225,28 @@ def ours_arm(args, rank, world):
     peaks = load_peaks()
     n, dim, k = args.rows, args.dim, args.k
 
+    sharded = world > 1 and args.shard == "gallery"
     store = frg.GalleryStore(dim=dim, capacity=n, device=local)
-    store.fill_synthetic(n, 0, args.seed)
+    if sharded:
+        from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+        sg = ShardedGallery(dim=dim, device=local, store=store)
+        sg.fill_synthetic(n * world, args.seed)          # this rank: rows [rank*n, (rank+1)*n)
+        smatcher = ShardedMatcher(sg)
+    else:
+        store.fill_synthetic(n, 0, args.seed)
     torch.cuda.synchronize()
     matcher = frg.Matcher(store)
     stream = torch.cuda.current_stream(dev)
     nb = 4
+    n_total = n * world if sharded else n
+    # units of work per step: sharded -> every query is matched against world x n rows
+    scale = float(world)
 
     def make_batches(F):
         # a ring of distinct query batches (50 % genuine / 50 % impostor);
         # every rank takes its own slice of the query stream
-        Qh = [synth.queries(F, n, dim, q0=(rank * nb + i) * F)[0] for i in range(nb)]
+        # (row-sharded: every rank needs the SAME batch; replicas: each rank its own slice)
+        Qh = [synth.queries(F, n_total, dim, q0=((0 if sharded else rank) * nb + i) * F)[0] for i in range(nb)]
         Qd = [torch.from_numpy(q).to(dev) for q in Qh]
         outs = [(torch.empty((F, k), dtype=torch.int64, device=dev),
                  torch.empty((F, k), dtype=torch.float32, device=dev),
@@ -231,7 +255,10 @@ def ours_arm(args, rank, world):
 
     def time_device(F, steps, warmup, Qd, outs, clocks=False):
         def step(i):
-            matcher.match_device(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
+            if sharded:
+                smatcher.match(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
+            else:
+                matcher.match_device(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
         for i in range(warmup):
             step(i)
         torch.cuda.synchronize()
@@ -264,7 +291,7 @@ def ours_arm(args, rank, world):
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             total_ms = float(t.item())
         ms = total_ms / steps
-        return {"batch": F, "value": F * world / (ms * 1e-3), "ms_per_step": ms, "variant": variant,
+        return {"batch": F, "value": F * scale / (ms * 1e-3), "ms_per_step": ms, "variant": variant,
                 "launches_per_step": launches_per_step, "dom_ms": dom_ms, "dom_launches": dom_launches,
                 "total_ms": total_ms, "clocks": ck, "stage_ms": stages}
 
@@ -278,7 +305,26 @@ def ours_arm(args, rank, world):
 
     # ---- parity spot-check of what was just timed (never inside the timed region)
     parity = None
-    if rank == 0 and not args.no_check:
+    if sharded and not args.no_check:
+        # every rank checks the merged result restricted to ITS rows against the oracle on its shard:
+        # merged rows that fall into this shard must be exactly the shard-local oracle rows that survive
+        nchk = min(F, 16)
+        G, _ = store.read_rows()
+        loc_rows, loc_scores, _ = mo.match_topk(Qh[0][:nchk], G, k, 0.45)
+        smatcher.match(Qd[0], k, 0.45, variant=args.variant, out=outs[0])
+        torch.cuda.synchronize()
+        got_r, got_s, _ = (x.cpu().numpy() for x in outs[0])
+        ok = True
+        for f in range(nchk):
+            mine = (got_r[f] >= sg.offset) & (got_r[f] < sg.offset + n)
+            exp = loc_rows[f][loc_scores[f] >= got_s[f, k - 1] + 1e-4] + sg.offset   # clearly above the merged k-th
+            ok &= set(exp) <= set(got_r[f][mine])
+            ok &= bool(np.all(np.diff(got_s[f]) <= 0))
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+        parity = {"checked_queries": nchk, "sharded_ids_ok_all_ranks": bool(t.item() > 0)}
+        del G
+    elif rank == 0 and not args.no_check:
         nchk = min(F, 32)
         G, _ = store.read_rows()
         ref_rows, ref_scores, ref_acc = mo.match_topk(Qh[0][:nchk], G, k + 1, 0.45)
@@ -297,25 +343,39 @@ def ours_arm(args, rank, world):
     sc_p = torch.empty((F, k), dtype=torch.float32).pin_memory()
     ac_p = torch.empty((F,), dtype=torch.uint8).pin_memory()
     res = frg.MatchResult(rows_p.numpy(), sc_p.numpy(), ac_p.numpy())
+    q_dev = torch.empty((F, dim), dtype=torch.float32, device=dev)
+
+    def e2e_step(i):
+        if sharded:
+            # host batch in (pinned) -> H2D on every rank -> sharded match -> D2H of the merged result
+            q_dev.copy_(Qp[i % nb], non_blocking=True)
+            r_, s_, a_ = smatcher.match(q_dev, k, 0.45, variant=args.variant, out=outs[0])
+            rows_p.copy_(r_, non_blocking=True); sc_p.copy_(s_, non_blocking=True); ac_p.copy_(a_, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        else:
+            matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
+
     for i in range(max(3, args.warmup)):
-        matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
+        e2e_step(i)
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
+        e2e_step(i)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": F * world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
+    e2e = {"value": F * scale * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
            "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / args.steps * 1e3,
-           "api": "frg_match_host via Matcher.match (pinned host buffers)"}
+           "api": ("ShardedMatcher.match: pinned host batch -> H2D -> frg_match per shard -> all-gather -> "
+                   "frg_merge_topk_strided -> D2H" if sharded else
+                   "frg_match_host via Matcher.match (pinned host buffers)")}
 
     # ---- other batch sizes of configs[1] ("batch 1-1024"): device-timed, same method
     sweep = []
-    if args.sweep and world == 1:
+    if args.sweep and world == 1 and not sharded:
         for Fs in [int(x) for x in args.sweep.split(",") if x]:
             if Fs == F:
                 r = main
@@ -345,7 +405,7 @@ def ours_arm(args, rank, world):
         q_cpu = args.cpu_queries or procs
         Qc, _ = synth.queries(q_cpu, n, dim)
         qps, per_step, results = run_cpu_loop(G, Qc, 0.45, procs, 1, 0)
-        # the same queries through the GPU: identical ids and decisions
+        # the same queries through the GPU (rank 0's rows): identical ids and decisions
         r = matcher.match(Qc, 1, 0.45, variant=args.variant)
         same = all((res_[0] == gid[0] or (res_[0] is None and gid[0] is None)) and (res_[2] == bool(a))
                    for res_, gid, a in zip(results, r.ids, r.accept))
@@ -358,7 +418,8 @@ def ours_arm(args, rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
-            "data": "synthetic", "config": workload_config(args, F), "variant": variant,
+            "data": "synthetic", "config": workload_config(args, F, world), "variant": variant,
+            "queries_per_s_raw": value / scale if sharded else value,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": main["launches_per_step"] * args.steps,
             "clocks": clocks, "parity": parity, "sweep": sweep, "peaks": peaks}
@@ -400,6 +461,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--variant", default="auto")
     ap.add_argument("--sweep", default="1,8,64,128,256,512,1024")
+    ap.add_argument("--shard", default="gallery", choices=["gallery", "queries"],
+                    help="N>1: row-shard the gallery (all-gather + merge) or replicate it and shard the query stream")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)

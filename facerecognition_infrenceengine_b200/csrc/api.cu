@@ -580,4 +580,19 @@ int frg_merge_topk(int32_t device, const float* scores, const int64_t* rows, int
                           out_accept, static_cast<cudaStream_t>(stream));
 }
 
+int frg_merge_topk_strided(int32_t device, const float* scores, int64_t score_part_stride,
+                           const int64_t* rows, int64_t row_part_stride, int32_t parts, int32_t nq, int32_t k,
+                           int32_t metric, float threshold, int64_t* out_rows, float* out_scores,
+                           uint8_t* out_accept, void* stream) {
+  reset_launches();
+  if (parts < 0 || nq < 0 || (nq > 0 && (!out_rows || !out_scores)) || (parts > 0 && nq > 0 && (!scores || !rows))) {
+    set_error("merge_topk_strided: bad argument");
+    return FRG_ERR_INVALID;
+  }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
+  return launch_merge_i64_strided(scores, score_part_stride, rows, row_part_stride, parts, nq, k, metric, threshold,
+                                  out_rows, out_scores, out_accept, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

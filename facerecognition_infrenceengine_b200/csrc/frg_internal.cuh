@@ -117,6 +117,9 @@ int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, int* n_flagge
 int launch_merge_i64(const float* scores, const int64_t* rows, int parts, int nq, int k_in, int k_out,
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
+int launch_merge_i64_strided(const float* scores, int64_t score_stride, const int64_t* rows, int64_t row_stride,
+                             int parts, int nq, int k, int metric, float threshold, int64_t* out_rows,
+                             float* out_scores, uint8_t* out_accept, cudaStream_t st);
 int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq, int k_in, int k_out,
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);

@@ -24,6 +24,7 @@ template <typename RowT, int KMAX>
 __device__ __forceinline__ void merge_one(const float* __restrict__ scores, const RowT* __restrict__ rows,
                                           int parts, int nq, int k_in, int k_out, int metric, float threshold,
                                           int64_t row_offset, int internal_euclid, int slot, int q,
+                                          int64_t score_stride, int64_t row_stride,
                                           int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
                                           uint8_t* __restrict__ out_accept) {
   const int lane = threadIdx.x & 31;
@@ -47,9 +48,9 @@ __device__ __forceinline__ void merge_one(const float* __restrict__ scores, cons
       s[u] = sentinel;
       if (c < total) {
         const int part = c / k_in, j = c - part * k_in;
-        const size_t off = (size_t(part) * nq + slot) * k_in + j;
-        r[u] = rows[off];
-        s[u] = scores[off];
+        const size_t in_part = size_t(slot) * k_in + j;
+        r[u] = rows[size_t(part) * row_stride + in_part];
+        s[u] = scores[size_t(part) * score_stride + in_part];
       }
     }
 #pragma unroll

@@ -244,7 +244,8 @@ scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restr
   __threadfence();
   for (int slot = threadIdx.x >> 5; slot < nf; slot += kScanWarps)
     merge_one<int32_t, KMAX>(part_sc, part_ix, int(gridDim.x), nq_total, K, K, METRIC, threshold, row_offset, 0,
-                             slot, flagged[slot], out_rows, out_scores, out_accept);
+                             slot, flagged[slot], int64_t(nq_total) * K, int64_t(nq_total) * K, out_rows, out_scores,
+                             out_accept);
 }
 
 static int scan_grid(const ScanArgs& a) {

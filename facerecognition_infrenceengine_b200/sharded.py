@@ -1,0 +1,152 @@
+"""Row-sharded gallery over the GPUs of one box (BASELINE config 4).
+
+One process per GPU (``torch.distributed``; NCCL on GPUs, gloo in the CPU tests).  Rank r holds the
+contiguous block of gallery rows ``[offset_r, offset_r + n_r)``; a match is
+
+    local fused match on every rank           (frg_match, rows returned as GLOBAL rows)
+    -> ONE all-gather of the packed [rows | scores] block, F*k*12 bytes per rank, latency-sized
+    -> k-way merge on every rank               (frg_merge_topk_strided)
+
+Contiguous blocks keep global row order = enrolment order, so the merge's (score desc, row asc)
+order reproduces the reference's strict-'>' tie rule (infrenceServer.py:538-542) across shards.
+Queries are replicated: every rank passes the same batch (``broadcast=True`` ships rank 0's).
+
+The reference has no distributed code at all; this file is new capability, not a port.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .gallery import GalleryStore
+from .matcher import LIVE_THRESHOLD, Matcher
+
+
+def shard_bounds(n_rows: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced row blocks: rank r owns [lo, hi)."""
+    return [((n_rows * r) // world, (n_rows * (r + 1)) // world) for r in range(world)]
+
+
+def owner_of(row: int, bounds: List[Tuple[int, int]]) -> int:
+    for r, (lo, hi) in enumerate(bounds):
+        if lo <= row < hi:
+            return r
+    return len(bounds) - 1
+
+
+class ShardedGallery:
+    """The local shard plus the shared view of who owns what."""
+
+    def __init__(self, dim: int = 512, device: Optional[int] = None, group=None, store: Optional[GalleryStore] = None,
+                 rank: Optional[int] = None, world: Optional[int] = None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.dim = dim
+        self.device = device
+        self.store = store           # None in host-logic tests that inject their own local matcher
+        self.bounds: List[Tuple[int, int]] = [(0, 0)] * self.world
+
+    # ---- layout ---------------------------------------------------------------------------------
+    @property
+    def offset(self) -> int:
+        return self.bounds[self.rank][0]
+
+    @property
+    def local_rows(self) -> int:
+        lo, hi = self.bounds[self.rank]
+        return hi - lo
+
+    @property
+    def total_rows(self) -> int:
+        return self.bounds[-1][1]
+
+    def plan(self, n_rows: int):
+        self.bounds = shard_bounds(n_rows, self.world)
+        return self.bounds[self.rank]
+
+    def fill_synthetic(self, n_rows: int, seed: int = 1234):
+        """Every rank materialises ITS block of the frg-synth-v1 gallery on its own GPU; row r depends
+        only on (seed, r), so the data is identical at 1, 2, 4 or 8 GPUs and never touches the host."""
+        lo, hi = self.plan(n_rows)
+        self.store.fill_synthetic(hi - lo, lo, seed)
+
+    def append_local(self, vecs: np.ndarray, tags=None, prenormalised: bool = False):
+        """Collective enrolment: every rank passes the SAME batch; each keeps the rows whose global
+        position falls into its block after the gallery has been re-planned to the new size... which
+        would move rows between ranks.  Appends therefore go to the LAST rank (global order is kept,
+        blocks become unbalanced; rebalancing is a maintenance operation)."""
+        n = len(vecs)
+        lo, hi = self.bounds[-1]
+        self.bounds = self.bounds[:-1] + [(lo, hi + n)]
+        if self.rank == self.world - 1 and self.store is not None:
+            self.store.append_rows(vecs, tags, prenormalised)
+
+
+class ShardedMatcher:
+    def __init__(self, gallery: ShardedGallery,
+                 local_match: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.g = gallery
+        self._local = local_match or self._local_cuda
+        self._merge = merge or self._merge_cuda
+        self._matcher = Matcher(gallery.store) if gallery.store is not None else None
+        self._buf = None
+
+    # ---- CUDA pieces ------------------------------------------------------------------------------
+    def _local_cuda(self, Q, k, threshold, variant, rows_out, scores_out):
+        acc = self._accept_scratch(Q)
+        self._matcher.match_device(Q, k, threshold, variant=variant, row_offset=self.g.offset,
+                                   out=(rows_out, scores_out, acc))
+
+    def _accept_scratch(self, Q):
+        import torch
+        if self._buf is None or self._buf.shape[0] < Q.shape[0]:
+            self._buf = torch.empty((Q.shape[0],), dtype=torch.uint8, device=Q.device)
+        return self._buf[:Q.shape[0]]
+
+    def _merge_cuda(self, gathered, parts, F, k, threshold, out):
+        import torch
+        rows, scores, accept = out
+        stride_bytes = F * k * 12
+        base = gathered.data_ptr()
+        stream = torch.cuda.current_stream(gathered.device).cuda_stream
+        N.check(N.lib.frg_merge_topk_strided(
+            gathered.device.index, C.c_void_p(base + F * k * 8), stride_bytes // 4, C.c_void_p(base),
+            stride_bytes // 8, parts, F, k, N.METRIC_COSINE, float(np.float32(threshold)),
+            C.c_void_p(rows.data_ptr()), C.c_void_p(scores.data_ptr()), C.c_void_p(accept.data_ptr()),
+            C.c_void_p(stream)))
+
+    # ---- the collective match ---------------------------------------------------------------------
+    def match(self, Q, k: int = 1, threshold: float = LIVE_THRESHOLD, variant: str = "auto",
+              broadcast: bool = False, out=None):
+        """Q: float32 [F, dim] tensor on this rank's device, identical on every rank (or rank 0's with
+        broadcast=True).  Returns (rows int64 [F,k] GLOBAL rows, scores fp32 [F,k], accept uint8 [F])
+        on every rank."""
+        import torch
+        import torch.distributed as dist
+        F = Q.shape[0]
+        if broadcast and self.g.world > 1:
+            dist.broadcast(Q, src=0, group=self.g.group)
+        # packed per-rank block: F*k int64 rows, then F*k fp32 scores  (12 bytes per slot)
+        block = F * k * 12
+        if (F * k) % 2:                      # keep every block 8-byte aligned
+            raise ValueError("F*k must be even (pad the batch)")
+        local = torch.empty((block,), dtype=torch.uint8, device=Q.device)
+        rows_l = local[:F * k * 8].view(torch.int64).view(F, k)
+        scores_l = local[F * k * 8:].view(torch.float32).view(F, k)
+        self._local(Q, k, threshold, variant, rows_l, scores_l)
+        if self.g.world > 1:
+            gathered = torch.empty((self.g.world * block,), dtype=torch.uint8, device=Q.device)
+            dist.all_gather_into_tensor(gathered, local, group=self.g.group)
+        else:
+            gathered = local
+        if out is None:
+            out = (torch.empty((F, k), dtype=torch.int64, device=Q.device),
+                   torch.empty((F, k), dtype=torch.float32, device=Q.device),
+                   torch.empty((F,), dtype=torch.uint8, device=Q.device))
+        self._merge(gathered, self.g.world, F, k, threshold, out)
+        return out

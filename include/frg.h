@@ -144,6 +144,12 @@ FRG_API int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, 
 FRG_API int frg_merge_topk(int32_t device, const float* scores, const int64_t* rows, int32_t parts,
                    int32_t nq, int32_t k, int32_t metric, float threshold,
                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
+/* Same, for lists that sit `score_part_stride` floats / `row_part_stride` int64s apart (0 = nq*k,
+ * i.e. contiguous): lets ONE all-gather of a packed [rows | scores] block per rank feed the merge. */
+FRG_API int frg_merge_topk_strided(int32_t device, const float* scores, int64_t score_part_stride,
+                           const int64_t* rows, int64_t row_part_stride, int32_t parts, int32_t nq, int32_t k,
+                           int32_t metric, float threshold, int64_t* out_rows, float* out_scores,
+                           uint8_t* out_accept, void* stream);
 
 /* ---- introspection for tests / bench: name and launch count of the kernels the LAST frg_match /
  * frg_match_host on this thread enqueued (bench.py reports it as gpu_launches). */

@@ -1,0 +1,71 @@
+"""Row-sharded match on real GPUs.  world=1 runs everywhere; the 2-rank NCCL case needs >= 2 devices
+(it is launched as its own torchrun job) and is skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import matcher_oracle as mo
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_world1_equals_plain_matcher():
+    import torch
+    import facerecognition_infrenceengine_b200 as frg
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+    n, d, f, k = 50000, 512, 24, 5
+    store = frg.GalleryStore(dim=d, capacity=n)
+    g = ShardedGallery(dim=d, device=0, store=store, rank=0, world=1)
+    g.fill_synthetic(n, 1234)
+    Q, _ = synth.queries(f, n, d)
+    rows, scores, acc = ShardedMatcher(g).match(torch.from_numpy(Q).cuda(), k, 0.45)
+    torch.cuda.synchronize()
+    ref = frg.Matcher(store).match(Q, k, 0.45)
+    assert (rows.cpu().numpy() == ref.rows).all() and (scores.cpu().numpy() == ref.scores).all()
+    assert (acc.cpu().numpy().astype(bool) == ref.accept).all()
+    store.close()
+
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import facerecognition_infrenceengine_b200 as frg
+from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+from oracle import matcher_oracle as mo, synth
+local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n, d, f, k = 300001, 512, 64, 10
+store = frg.GalleryStore(dim=d, capacity=n, device=local)
+g = ShardedGallery(dim=d, device=local, store=store)
+g.fill_synthetic(n, 1234)
+Q, target = synth.queries(f, n, d)
+rows, scores, acc = ShardedMatcher(g).match(torch.from_numpy(Q).cuda(), k, 0.45)
+torch.cuda.synchronize()
+if dist.get_rank() == 0:
+    G = synth.gallery(n, d)
+    rr, rs, ra = mo.match_topk(Q, G, k + 1, 0.45)
+    assert mo.ids_match_with_gap(rr, rs, rows.cpu().numpy(), 1e-4).all()
+    assert np.abs(scores.cpu().numpy() - rs[:, :k]).max() <= 1e-4
+    assert (acc.cpu().numpy().astype(bool) == ra).all()
+    print("SHARDED_OK world=%%d" %% dist.get_world_size())
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_two_ranks_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SHARDED_OK world=2" in r.stdout
