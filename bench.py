@@ -474,7 +474,13 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank, world)
     else:
-        ours_arm(args, rank, world)
+        try:
+            ours_arm(args, rank, world)
+        finally:
+            if world > 1:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
