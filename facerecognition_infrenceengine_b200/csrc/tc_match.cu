@@ -84,6 +84,55 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// CTA-pair (cta_group::2) flavours: both CTAs of the pair issue their half of the load, the
+// transaction bytes land on the LEADER's mbarrier (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the same-offset mbarrier of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [r];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the same-offset mbarrier of BOTH CTAs of the pair once the issued MMAs have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(uint16_t(3)) : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -135,18 +184,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 // ------------------------------------------------------------------------------------------ shapes
-constexpr int kTileQ = 128;          // UMMA M: queries per CTA tile (TMEM lanes)
-constexpr int kTileR = 128;          // UMMA N: gallery rows per accumulator (TMEM columns)
+constexpr int kTileQ = 128;          // queries per CTA tile (TMEM lanes); UMMA M = 128, or 256 across a CTA pair
+constexpr int kTileR = 128;          // gallery rows staged per CTA and k-block (TMA box rows)
 constexpr int kBlockK = 64;          // one 128-byte swizzle row of bf16
 constexpr int kStages = 6;
 constexpr int kStageBytes = kTileR * kBlockK * 2;          // 16 KB
 constexpr int kTcThreads = 192;
-constexpr int kTmemCols = 2 * kTileR;                      // double-buffered accumulator
+// accumulator: double-buffered, N columns each (N = 128 single CTA, 256 for a CTA pair)
 constexpr float kCoarseEps = 4e-3f;                        // |bf16 filter score - fp32 score| bound
 // instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(kTileR >> 3) << 17) |
-                            (uint32_t(kTileQ >> 4) << 24);
+constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
 
 enum TcMode { kModeGroupMax = 0, kModeFilter = 1 };
 constexpr int kGroups = 32;
@@ -183,10 +233,20 @@ struct TcScanParams {
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
 // once per 32-row block, one row per lane, and turned into a warp-uniform bit mask with a ballot -
 // no per-candidate global load sits on the epilogue's dependent path.
-template <int MODE, bool MASKED>
+// PAIR: the CTA pair variant (cluster of 2 along x = two query tiles against the same gallery rows).
+// tcgen05.mma.cta_group::2 multiplies M = 256 queries (128 per CTA) by N = 256 gallery rows, each CTA
+// staging only ITS 128-row half of every B tile: half the shared-memory operand traffic per flop of
+// the single-CTA form, which is what lifts the tensor pipe at large batches.  The leader CTA (rank 0)
+// owns the full/tmem_empty barriers and issues the MMAs; commits are multicast to both CTAs.
+template <int MODE, bool MASKED, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map,
                const TcScanParams p) {
+  constexpr int kAccN = PAIR ? 2 * kTileR : kTileR;        // accumulator columns = gallery rows per tile
+  constexpr int kTmemCols = 2 * kAccN;
+  constexpr uint32_t kIdesc = make_idesc(PAIR ? 2 * kTileQ : kTileQ, kAccN);
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   extern __shared__ unsigned char smem_raw[];
   // 128B swizzle wants 1024-byte aligned tiles
   const uint32_t raw = smem_u32(smem_raw);
@@ -211,20 +271,24 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   const int chunk = blockIdx.y, chunks = gridDim.y;
   // view tile v stands for gallery tile v * tile_scale (the pre-pass samples whole 128-row tiles:
   // contiguous 128 KB reads, spread evenly over the gallery)
-  const int tiles_all = (p.n_rows + kTileR - 1) / kTileR;
+  const int tiles_all = (p.n_rows + kAccN - 1) / kAccN;
   const int tiles_total = (tiles_all + p.tile_scale - 1) / p.tile_scale;
   const int tile_begin = int((int64_t(tiles_total) * chunk) / chunks);
   const int tile_end = int((int64_t(tiles_total) * (chunk + 1)) / chunks);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), PAIR ? 8 : 4); }
     mbar_init(bar_q, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(smem_u32(tmem_holder), kTmemCols);
+    else tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();        // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -233,23 +297,35 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     if (lane == 0) {
       tma_prefetch_desc(&q_map);
       tma_prefetch_desc(&g_map);
-      mbar_expect_tx(bar_q, q_bytes);
-      for (int kb = 0; kb < kblocks; ++kb)
-        tma_load_2d(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
+      const uint64_t g_hint = gridDim.x > (PAIR ? 2 : 1) ? kEvictLast : kEvictFirst;
+      if (PAIR) {
+        if (leader) mbar_expect_tx(bar_q, 2 * q_bytes);
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d_pair(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
+      } else {
+        mbar_expect_tx(bar_q, q_bytes);
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_2d(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int t = tile_begin; t < tile_end; ++t) {
+        const int row0 = t * p.tile_scale * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_expect_tx(bar_full(stage), kStageBytes);
-          tma_load_2d(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK,
-                      t * p.tile_scale * kTileR, gridDim.x > 1 ? kEvictLast : kEvictFirst);
+          if (PAIR) {
+            if (leader) mbar_expect_tx(bar_full(stage), 2 * kStageBytes);
+            tma_load_2d_pair(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK, row0, g_hint);
+          } else {
+            mbar_expect_tx(bar_full(stage), kStageBytes);
+            tma_load_2d(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK, row0, g_hint);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (leader CTA only in pair mode) =====
+    if (lane == 0 && leader) {
       mbar_wait(bar_q, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
@@ -257,7 +333,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       for (int t = tile_begin; t < tile_end; ++t) {
         mbar_wait(bar_tempty(buf), tphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(buf * kTileR);
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * kAccN);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_full(stage), phase);
           tc_fence_after();
@@ -266,10 +342,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, (kb | kk) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, (kb | kk) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty(stage));                 // smem slot reusable once these MMAs retire
-          if (kb == kblocks - 1) umma_commit(bar_tfull(buf));
+          // smem slot reusable / accumulator readable once these MMAs retire (both CTAs in pair mode)
+          if (PAIR) {
+            umma_commit_pair(bar_empty(stage));
+            if (kb == kblocks - 1) umma_commit_pair(bar_tfull(buf));
+          } else {
+            umma_commit(bar_empty(stage));
+            if (kb == kblocks - 1) umma_commit(bar_tfull(buf));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++buf == 2) { buf = 0; tphase ^= 1; }
@@ -323,11 +406,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 
     int buf = 0; uint32_t tphase = 0;
     for (int t = tile_begin; t < tile_end; ++t) {
-      // validity of this tile's 4 x 32 rows, fetched while the MMAs of the tile are still running
-      uint32_t vmask[kTileR / 32];
+      // validity of this tile's rows (32 per ballot), fetched while the tile's MMAs are still running
+      uint32_t vmask[kAccN / 32];
 #pragma unroll
-      for (int b = 0; b < kTileR / 32; ++b) {
-        const int row = t * p.tile_scale * kTileR + b * 32 + lane;
+      for (int b = 0; b < kAccN / 32; ++b) {
+        const int row = t * p.tile_scale * kAccN + b * 32 + lane;
         bool ok = row < p.n_rows;
         if (MASKED && ok) {
           const int32_t tag = __ldg(p.tags + row);
@@ -337,9 +420,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       }
       mbar_wait(bar_tfull(buf), tphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kTileR);
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kAccN);
 #pragma unroll
-      for (int b = 0; b < kTileR / 32; ++b) {
+      for (int b = 0; b < kAccN / 32; ++b) {
         float v[32];
         __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after the slow path
         tmem_ld32(taddr + b * 32, v);
@@ -350,7 +433,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = (vm >> j) & 1u ? v[j] : -INFINITY;
         }
         if (MODE == kModeGroupMax) {
-          // column j of every 32-row block belongs to group j (tiles start at multiples of 128)
+          // column j of every 32-row block belongs to group j (tiles start at multiples of 32)
 #pragma unroll
           for (int j = 0; j < 32; ++j) gmax[j] = fmaxf(gmax[j], v[j]);
         } else {
@@ -358,7 +441,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
           if (m >= thr) {
-            const int row0 = t * p.tile_scale * kTileR + b * 32;
+            const int row0 = t * p.tile_scale * kAccN + b * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (v[j] >= thr) {
@@ -371,7 +454,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(buf));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(bar_tempty(buf), 0);      // the leader's MMA thread waits on it
+        else mbar_arrive(bar_tempty(buf));
+      }
       if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
     if (q_real) {
@@ -392,10 +478,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();        // the leader's MMAs read the peer's shared memory until the very end
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -621,6 +709,7 @@ int tc_supported(int dim, int metric, const char** why) {
 }
 
 struct TcPlan {
+  bool pair;              // CTA-pair kernels (F > 128)
   int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
   size_t off_keys, off_cnt, off_cand, off_dense, off_flag, total;
 };
@@ -630,14 +719,21 @@ static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); 
 static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
   (void)dim;
   pl->qtiles = (nq + kTileQ - 1) / kTileQ;
+  static const int pair_env = []() { const char* e = getenv("FRG_TC_PAIR"); return e ? atoi(e) : 1; }();
+  pl->pair = pair_env != 0 && pl->qtiles >= 2;
+  if (pl->pair) pl->qtiles = (pl->qtiles + 1) & ~1;      // clusters of 2 along x; a padding tile holds no query
+  const int tile_rows = pl->pair ? 2 * kTileR : kTileR;
   // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
   // leaves >= 16 K sampled rows
   int stride = 1;
   while (stride < 64 && rows / (stride * 2) >= 16384) stride *= 2;
   pl->stride = stride;
-  const int tiles_all = int((rows + kTileR - 1) / kTileR);
+  const int tiles_all = int((rows + tile_rows - 1) / tile_rows);
   auto chunks_for = [&](int tiles) {
-    int c = sm_count / gcd_int(sm_count, pl->qtiles);
+    // (query tiles x chunks) a whole number of waves over the SMs (SM pairs in pair mode)
+    const int units = pl->pair ? sm_count / 2 : sm_count;
+    const int cols = pl->pair ? pl->qtiles / 2 : pl->qtiles;
+    int c = units / gcd_int(units, cols);
     if (c > kMaxChunks) c = kMaxChunks;
     if (c > tiles) c = tiles;
     return c < 1 ? 1 : c;
@@ -669,23 +765,37 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   pl->total = off;
 }
 
-template <int MODE, bool MASKED>
+template <int MODE, bool MASKED, bool PAIR>
 static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p, int qtiles, int chunks,
                           cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p.dim);
-  FRG_CUDA(cudaFuncSetAttribute(tc_scan_kernel<MODE, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                int(tc_smem_bytes(512))));
-  tc_scan_kernel<MODE, MASKED><<<dim3(qtiles, chunks), kTcThreads, smem, st>>>(qm, gm, p);
+  auto kern = tc_scan_kernel<MODE, MASKED, PAIR>;
+  FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes(512))));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(qtiles, chunks);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FRG_CUDA(cudaLaunchKernelEx(&cfg, kern, qm, gm, p));
   note_launch(nullptr);
-  FRG_CUDA(cudaGetLastError());
   return FRG_OK;
 }
 
 template <int MODE>
-static int launch_tc_scan_m(bool masked, const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p,
-                            int qtiles, int chunks, cudaStream_t st) {
-  return masked ? launch_tc_scan<MODE, true>(qm, gm, p, qtiles, chunks, st)
-                : launch_tc_scan<MODE, false>(qm, gm, p, qtiles, chunks, st);
+static int launch_tc_scan_m(bool masked, bool pair, const CUtensorMap& qm, const CUtensorMap& gm,
+                            const TcScanParams& p, int qtiles, int chunks, cudaStream_t st) {
+  if (pair)
+    return masked ? launch_tc_scan<MODE, true, true>(qm, gm, p, qtiles, chunks, st)
+                  : launch_tc_scan<MODE, false, true>(qm, gm, p, qtiles, chunks, st);
+  return masked ? launch_tc_scan<MODE, true, false>(qm, gm, p, qtiles, chunks, st)
+                : launch_tc_scan<MODE, false, false>(qm, gm, p, qtiles, chunks, st);
 }
 
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
@@ -724,20 +834,20 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
 
   CUtensorMap qm, gm_full;
   FRG_CHECK(make_map(&qm, qb, s->dim, nq, size_t(s->dim) * 2, kTileQ));
-  FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));
+  FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));   // box = one CTA's half
 
   TcScanParams p{};
   p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   // 1. pre-pass over the sampled tiles
   p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.group_key = keys; p.k = k;
   profile_begin(st, kStagePrepass);
-  FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
+  FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
   profile_end(st, 1);
   // 2. filter over the whole plane
   p.tile_scale = 1; p.seg = pl.seg;
   p.cand = cand; p.cand_total = cnt; p.dense = dense; p.dense_cap = pl.stage_entries;
   profile_begin(st, kStageDominant);
-  int rc = launch_tc_scan_m<kModeFilter>(masked, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
+  int rc = launch_tc_scan_m<kModeFilter>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
   FRG_CHECK(rc);
   profile_end(st, 1);
   // 3. select + exact rescoring
