@@ -66,6 +66,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();
   }
 }
+// one lane of a converged warp (PTX elect.sync): lets the rest of the warp stay on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -325,11 +335,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only in pair mode) =====
-    if (lane == 0 && leader) {
+    // The whole warp runs the loop (waits, descriptor arithmetic) so that every operand of
+    // tcgen05.mma is warp-uniform and lives in uniform registers; only the tcgen05 instructions
+    // themselves are issued by one elected lane.  (Running the loop under `lane == 0` costs an
+    // ELECT + R2UR chain per MMA operand and makes the issue path, not the tensor pipe, the limit.)
+    if (leader) {
       mbar_wait(bar_q, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
       int buf = 0; uint32_t tphase = 0;
+      const uint64_t a_base = umma_desc_sw128(q_smem);
+      const uint64_t b_base = umma_desc_sw128(stage_smem);
       for (int t = tile_begin; t < tile_end; ++t) {
         mbar_wait(bar_tempty(buf), tphase ^ 1);
         tc_fence_after();
@@ -337,22 +353,27 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_full(stage), phase);
           tc_fence_after();
-          const uint64_t a0 = umma_desc_sw128(q_smem + kb * (kTileQ * kBlockK * 2));
-          const uint64_t b0 = umma_desc_sw128(stage_smem + stage * kStageBytes);
+          // descriptor start-address field is (addr >> 4): a k-block of A is 16 KB, a stage of B 16 KB
+          const uint64_t a0 = a_base + uint64_t(kb * ((kTileQ * kBlockK * 2) >> 4));
+          const uint64_t b0 = b_base + uint64_t(stage * (kStageBytes >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_bf16_pair(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, (kb | kk) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+              if (PAIR) umma_bf16_pair(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, acc);
+              else umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, acc);
+            }
+            // smem slot reusable / accumulator readable once these MMAs retire (both CTAs in pair mode)
+            if (PAIR) {
+              umma_commit_pair(bar_empty(stage));
+              if (kb == kblocks - 1) umma_commit_pair(bar_tfull(buf));
+            } else {
+              umma_commit(bar_empty(stage));
+              if (kb == kblocks - 1) umma_commit(bar_tfull(buf));
+            }
           }
-          // smem slot reusable / accumulator readable once these MMAs retire (both CTAs in pair mode)
-          if (PAIR) {
-            umma_commit_pair(bar_empty(stage));
-            if (kb == kblocks - 1) umma_commit_pair(bar_tfull(buf));
-          } else {
-            umma_commit(bar_empty(stage));
-            if (kb == kblocks - 1) umma_commit(bar_tfull(buf));
-          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++buf == 2) { buf = 0; tphase ^= 1; }
