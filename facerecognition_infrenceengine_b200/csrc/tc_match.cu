@@ -442,12 +442,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       mbar_wait(bar_tfull(buf), tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kAccN);
-#pragma unroll
-      for (int b = 0; b < kAccN / 32; ++b) {
-        float v[32];
-        __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after the slow path
-        tmem_ld32(taddr + b * 32, v);
-        tmem_ld_wait();
+      // software-pipelined TMEM reads: the load of block b+1 is in flight while block b is processed
+      float va[32], vb[32];
+      auto process = [&](float (&v)[32], int b) {
         const uint32_t vm = vmask[b];
         if (vm != 0xffffffffu) {           // warp-uniform: tombstones / other tenants / rows past the end
 #pragma unroll
@@ -472,6 +469,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
             }
           }
         }
+      };
+      __syncwarp();
+      tmem_ld32(taddr, va);
+#pragma unroll
+      for (int b = 0; b < kAccN / 32; b += 2) {
+        tmem_ld_wait();                    // va (block b) has landed
+        __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after a slow path
+        tmem_ld32(taddr + (b + 1) * 32, vb);
+        process(va, b);
+        tmem_ld_wait();                    // vb (block b + 1)
+        __syncwarp();
+        if (b + 2 < kAccN / 32) tmem_ld32(taddr + (b + 2) * 32, va);
+        process(vb, b + 1);
       }
       tc_fence_before();
       __syncwarp();
