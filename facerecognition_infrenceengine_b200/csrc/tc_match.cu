@@ -18,12 +18,13 @@
 //   4. queries whose lists overflowed (adversarial duplicates, sparse tenants) are re-done by the
 //      exact streaming scan inside the same enqueue (fallback_* kernels) - never by the host.
 //
-// Kernel anatomy (one CTA per SM, 192 threads):
+// Kernel anatomy (one CTA per SM, 320 threads):
 //   warp 0   TMA producer: gallery tiles [128 rows x 64 k] bf16, 128B-swizzled, 6-stage mbarrier ring
 //   warp 1   MMA issuer: one elected lane, tcgen05.mma cta_group::1 kind::f16, M=128 (queries) x N=128
 //            (gallery rows) x K=16, A = the query tile resident in smem (128 x 512 bf16 = 128 KB),
 //            B = the staged gallery tile; accumulators in TMEM, double buffered (2 x 128 columns)
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns; thread = one query, columns = gallery rows:
+//   warps 2-9 epilogue (two per TMEM lane quarter, splitting the columns): tcgen05.ld 32 lanes x 32
+//            columns, software-pipelined; thread = one query, columns = gallery rows:
 //            a running max against the query's threshold (1 FMNMX per score), rare slow path.
 // The gallery is read once per 128-query tile: algorithmic bytes = rows * dim * 2 per launch and
 // query tile; flops = 2 * 128 * rows * dim.
@@ -199,7 +200,8 @@ constexpr int kTileR = 128;          // gallery rows staged per CTA and k-block 
 constexpr int kBlockK = 64;          // one 128-byte swizzle row of bf16
 constexpr int kStages = 6;
 constexpr int kStageBytes = kTileR * kBlockK * 2;          // 16 KB
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;          // two per TMEM lane quarter: they split a tile's columns
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 // accumulator: double-buffered, N columns each (N = 128 single CTA, 256 for a CTA pair)
 constexpr float kCoarseEps = 4e-3f;                        // |bf16 filter score - fp32 score| bound
 // instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major both,
@@ -288,7 +290,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), PAIR ? 8 : 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), PAIR ? 2 * kEpiWarps : kEpiWarps); }
     mbar_init(bar_q, 1);
     fence_barrier_init();
   }
@@ -382,6 +384,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   } else {
     // ===== epilogue: thread = query (TMEM lane), columns = gallery rows =====
     const int quarter = warp & 3;                        // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+    const int half = (warp - 2) >> 2;                    // which half of every tile's columns this warp scans
+    constexpr int kBlocksPerWarp = (kAccN / 32) / (kEpiWarps / 4);
     const int q_local = quarter * 32 + lane;
     const int q = qtile * kTileQ + q_local;
     const bool q_real = q < p.nq;
@@ -421,17 +425,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         // fewer than k usable groups in the sample: no bound, every valid row is a candidate
         // (finite, so that masked columns, which are set to -inf, still fail the comparison)
         thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
-        my_seg = p.cand + (size_t(q) * chunks + chunk) * p.seg;
+        my_seg = p.cand + ((size_t(q) * chunks + chunk) * (kEpiWarps / 4) + half) * p.seg;
       }
     }
 
     int buf = 0; uint32_t tphase = 0;
     for (int t = tile_begin; t < tile_end; ++t) {
       // validity of this tile's rows (32 per ballot), fetched while the tile's MMAs are still running
-      uint32_t vmask[kAccN / 32];
+      uint32_t vmask[kBlocksPerWarp];
 #pragma unroll
-      for (int b = 0; b < kAccN / 32; ++b) {
-        const int row = t * p.tile_scale * kAccN + b * 32 + lane;
+      for (int b = 0; b < kBlocksPerWarp; ++b) {
+        const int row = t * p.tile_scale * kAccN + (half * kBlocksPerWarp + b) * 32 + lane;
         bool ok = row < p.n_rows;
         if (MASKED && ok) {
           const int32_t tag = __ldg(p.tags + row);
@@ -441,7 +445,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       }
       mbar_wait(bar_tfull(buf), tphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kAccN);
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) +
+                             uint32_t(buf * kAccN + half * kBlocksPerWarp * 32);
       // software-pipelined TMEM reads: the load of block b+1 is in flight while block b is processed
       float va[32], vb[32];
       auto process = [&](float (&v)[32], int b) {
@@ -459,7 +464,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
           if (m >= thr) {
-            const int row0 = t * p.tile_scale * kAccN + b * 32;
+            const int row0 = t * p.tile_scale * kAccN + (half * kBlocksPerWarp + b) * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (v[j] >= thr) {
@@ -473,14 +478,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       __syncwarp();
       tmem_ld32(taddr, va);
 #pragma unroll
-      for (int b = 0; b < kAccN / 32; b += 2) {
+      for (int b = 0; b < kBlocksPerWarp; b += 2) {
         tmem_ld_wait();                    // va (block b) has landed
         __syncwarp();                      // tcgen05.ld is .sync.aligned: reconverge after a slow path
         tmem_ld32(taddr + (b + 1) * 32, vb);
         process(va, b);
         tmem_ld_wait();                    // vb (block b + 1)
         __syncwarp();
-        if (b + 2 < kAccN / 32) tmem_ld32(taddr + (b + 2) * 32, va);
+        if (b + 2 < kBlocksPerWarp) tmem_ld32(taddr + (b + 2) * 32, va);
         process(vb, b + 1);
       }
       tc_fence_before();
@@ -783,14 +788,16 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   if (stage_entries < 256) stage_entries = 256;
   if (stage_entries > 8192) stage_entries = 8192;
   pl->stage_entries = stage_entries;
-  int seg = (2 * stage_entries + pl->chunks_main - 1) / pl->chunks_main;   // x2: imbalance across chunks
-  if (seg < 16) seg = 16;
+  // private segments: one per (query, chunk, column half); x2 headroom for imbalance across them
+  const int nseg = pl->chunks_main * (kEpiWarps / 4);
+  int seg = (2 * stage_entries + nseg - 1) / nseg;
+  if (seg < 12) seg = 12;
   pl->seg = seg;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   pl->off_keys = take(size_t(nq) * kGroups * 4);
   pl->off_cnt = take(size_t(nq) * 4);
-  pl->off_cand = take(size_t(nq) * pl->chunks_main * seg * 8);
+  pl->off_cand = take(size_t(nq) * nseg * seg * 8);
   pl->off_dense = take(size_t(nq) * stage_entries * 8);
   pl->off_flag = take(size_t(nq) * 4 + 8);     // flagged[nq], count, ticket
   pl->total = off;
