@@ -384,8 +384,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   } else {
     // ===== epilogue: thread = query (TMEM lane), columns = gallery rows =====
     const int quarter = warp & 3;                        // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
-    const int half = (warp - 2) >> 2;                    // which half of every tile's columns this warp scans
-    constexpr int kBlocksPerWarp = (kAccN / 32) / (kEpiWarps / 4);
+    // FILTER: the two warps of a quarter split every tile's columns (the epilogue is issue-latency
+    // bound, two warps per scheduler hide it).  GROUPMAX: one warp per quarter does all columns (the
+    // other only keeps the barrier protocol), so each (query, group) maximum costs ONE atomic per CTA.
+    constexpr int kSplit = MODE == kModeFilter ? kEpiWarps / 4 : 1;
+    const int half = MODE == kModeFilter ? (warp - 2) >> 2 : 0;
+    const bool idle = MODE == kModeGroupMax && warp >= 6;
+    constexpr int kBlocksPerWarp = (kAccN / 32) / kSplit;
     const int q_local = quarter * 32 + lane;
     const int q = qtile * kTileQ + q_local;
     const bool q_real = q < p.nq;
@@ -431,6 +436,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 
     int buf = 0; uint32_t tphase = 0;
     for (int t = tile_begin; t < tile_end; ++t) {
+      if (idle) {
+        mbar_wait(bar_tfull(buf), tphase);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(bar_tempty(buf), 0);
+          else mbar_arrive(bar_tempty(buf));
+        }
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+        continue;
+      }
       // validity of this tile's rows (32 per ballot), fetched while the tile's MMAs are still running
       uint32_t vmask[kBlocksPerWarp];
 #pragma unroll
@@ -496,7 +510,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       }
       if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
-    if (q_real) {
+    if (q_real && !idle) {
       if (MODE == kModeGroupMax) {
         uint32_t* o = p.group_key + size_t(q) * kGroups;
 #pragma unroll
