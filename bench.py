@@ -456,7 +456,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--variant", default="auto")
