@@ -168,7 +168,7 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, q_per_step),
+            "config": dict(workload_config(args, args.batch), cpu_sample_queries_per_step=q_per_step),
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "setup_s": gen_s}
