@@ -17,6 +17,7 @@ METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 VARIANT_AUTO, VARIANT_SCAN_F32, VARIANT_TC_EXACT, VARIANT_TC_BF16 = 0, 1, 2, 3
 STORE_BF16_PLANE, STORE_RAW = 1, 2
 ROWS_PRENORMALISED = 1
+FIRST_STRICT, QUERY_PRENORMALISED = 1, 2
 MAX_K = 16
 
 VARIANTS = {"auto": VARIANT_AUTO, "scan_f32": VARIANT_SCAN_F32, "tc_exact": VARIANT_TC_EXACT,
@@ -61,6 +62,8 @@ SIGNATURES = {
     "frg_store_fill_synthetic": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, _P]),
     "frg_match": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(MatchParams), _P, _P, _P, _P]),
     "frg_match_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(MatchParams), _P, _P, _P]),
+    "frg_first_match": (C.c_int, [_P, _P, C.c_int32, C.POINTER(MatchParams), _P, _P, _P]),
+    "frg_first_match_host": (C.c_int, [_P, _P, C.c_int32, C.POINTER(MatchParams), _P, _P]),
     "frg_merge_topk": (C.c_int, [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_float, _P, _P, _P, _P]),
     "frg_merge_topk_strided": (C.c_int, [C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,

@@ -460,7 +460,7 @@ static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_mat
   FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + part_bytes, st));
   float* qn = reinterpret_cast<float*>(ws);
   a.qn = qn;
-  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE, qn, nullptr, nullptr, nullptr, nullptr, st);
+  int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE && !(p->flags & FRG_QUERY_PRENORMALISED), qn, nullptr, nullptr, nullptr, nullptr, st);
   if (rc == FRG_OK)
     rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
   g_variant = "scan_f32";
@@ -487,7 +487,7 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   uint32_t* keys = nullptr; int* ct0 = nullptr; int* nf0 = nullptr;
   tc_workspace_init_targets(s->rows, s->dim, nq, k, sm_count, ws + qn_bytes + qb_bytes, &keys, &ct0, &nf0);
   profile_begin(st, kStagePrep);
-  int rc = launch_normalise_queries(q, nq, s->dim, true, qn, qb, keys, ct0, nf0, st);
+  int rc = launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, qb, keys, ct0, nf0, st);
   profile_end(st, 1);
   if (rc == FRG_OK)
     rc = launch_tc_match(s, qn, qb, nq, k, p->tenant, rescore, p->threshold, p->row_offset, ws + qn_bytes + qb_bytes,
@@ -559,6 +559,60 @@ int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const fr
     e = cudaMemcpyAsync(out_rows, d + o_r, rb, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d + o_s, sb, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out_accept) e = cudaMemcpyAsync(out_accept, d + o_a, ab, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "D2H results", __FILE__, __LINE__);
+  }
+  cudaFreeAsync(d, st);
+  return rc;
+}
+
+int frg_first_match(frg_store* s, const float* q, int32_t nq, const frg_match_params_t* p,
+                    int64_t* out_rows, float* out_scores, void* stream) {
+  reset_launches();
+  if (!s || !p || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("first_match: bad argument"); return FRG_ERR_INVALID; }
+  if (p->metric != FRG_METRIC_COSINE) { set_error("first_match: cosine / dot only"); return FRG_ERR_UNSUPPORTED; }
+  if (nq == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  if (!g.ok) { set_error("cannot select device %d", s->device); return FRG_ERR_CUDA; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceInfo di;
+  FRG_CHECK(device_info(s->device, &di));
+  std::lock_guard<std::mutex> lk(s->mu);
+  FRG_CHECK(store_begin_read(s, st));
+  const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
+  unsigned char* ws = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + size_t(nq) * 8, st));
+  float* qn = reinterpret_cast<float*>(ws);
+  int rc = launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, nullptr, nullptr,
+                                    nullptr, nullptr, st);
+  if (rc == FRG_OK)
+    rc = launch_first_match(s->master, s->tags, s->rows, s->dim, qn, nq, p->tenant, p->threshold,
+                            (p->flags & FRG_FIRST_STRICT) != 0, p->row_offset,
+                            reinterpret_cast<unsigned long long*>(ws + qn_bytes), di.sm_count, out_rows, out_scores, st);
+  cudaError_t e = cudaFreeAsync(ws, st);
+  if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
+  return rc;
+}
+
+int frg_first_match_host(frg_store* s, const float* q, int32_t nq, const frg_match_params_t* p,
+                         int64_t* out_rows, float* out_scores) {
+  if (!s || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("first_match_host: bad argument"); return FRG_ERR_INVALID; }
+  if (nq == 0) return FRG_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t st = cudaStreamPerThread;
+  const size_t qb = size_t(nq) * s->dim * sizeof(float);
+  const size_t o_r = (qb + 255) & ~size_t(255), o_s = o_r + ((size_t(nq) * 8 + 255) & ~size_t(255));
+  unsigned char* d = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d), o_s + size_t(nq) * 4, st));
+  int rc = FRG_OK;
+  cudaError_t e = cudaMemcpyAsync(d, q, qb, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) rc = cuda_fail(e, "H2D queries", __FILE__, __LINE__);
+  if (rc == FRG_OK)
+    rc = frg_first_match(s, reinterpret_cast<float*>(d), nq, p, reinterpret_cast<int64_t*>(d + o_r),
+                         reinterpret_cast<float*>(d + o_s), st);
+  if (rc == FRG_OK) {
+    e = cudaMemcpyAsync(out_rows, d + o_r, size_t(nq) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d + o_s, size_t(nq) * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "D2H results", __FILE__, __LINE__);
   }

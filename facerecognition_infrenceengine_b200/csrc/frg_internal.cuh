@@ -134,6 +134,11 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,
                     int** n_flagged_out, cudaStream_t st);
 
+// first_match.cu
+int launch_first_match(const float* master, const int32_t* tags, int64_t rows, int dim, const float* qn, int nq,
+                       int32_t tenant, float threshold, bool strict, int64_t row_offset, unsigned long long* scratch,
+                       int sm_count, int64_t* out_rows, float* out_scores, cudaStream_t st);
+
 // store_kernels.cu
 int launch_ingest(const float* vecs, const int64_t* rows, const int32_t* tags, int64_t n, int64_t append_at,
                   int dim, bool normalise, float* master, __nv_bfloat16* plane, int32_t* tag_out,

@@ -14,6 +14,8 @@ reference's strict ``>`` scan resolves exact ties by that order (infrenceServer.
 from __future__ import annotations
 
 import ctypes as C
+import json
+import struct
 import threading
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -224,3 +226,57 @@ class GalleryStore:
             vecs, tags = self.read_rows(0, self._rows)
             live = np.nonzero(tags >= 0)[0]
             return [self.id_of(int(r)) for r in live], vecs[live], tags[live]
+
+    # ------------------------------------------------------------------ bulk snapshot (section 8f-3)
+    SNAP_MAGIC = b"FRGSNAP1"
+
+    def save(self, path: str, chunk_rows: int = 65536) -> int:
+        """Write the LIVE rows, in gallery order, to one file: header, id/tenant/metadata table (JSON),
+        int32 tags, raw fp32 unit vectors.  Replaces the reference's one-pickle-blob-per-person in
+        GridFS (producer trainingServer.py:383-398; consumers infrenceServer.py:269-271,
+        peopleCount.py:786-788): nothing to unpickle, one sequential read, and the vectors reload
+        bit for bit (they are stored normalised and re-ingested as such).  Returns the row count."""
+        with self._lock:
+            n_all = self._rows
+            _, tags_all = self.read_rows(0, n_all) if n_all else (None, np.zeros(0, np.int32))
+            live = np.nonzero(tags_all >= 0)[0]
+            ids = [self.id_of(int(r)) for r in live]
+            table = json.dumps({"ids": ids, "tenants": self._tenants,
+                                "meta": {i: self._meta[i] for i in ids if i in self._meta}},
+                               default=str).encode("utf-8")
+            with open(path, "wb") as f:
+                f.write(self.SNAP_MAGIC)
+                f.write(struct.pack("<IIQQ", self.dim, 0, len(live), len(table)))
+                f.write(table)
+                f.write(np.ascontiguousarray(tags_all[live], np.int32).tobytes())
+                # vectors: contiguous runs of live rows are read back chunk by chunk
+                for a in range(0, len(live), chunk_rows):
+                    idx = live[a:a + chunk_rows]
+                    lo, hi = int(idx[0]), int(idx[-1]) + 1
+                    vecs, _ = self.read_rows(lo, hi - lo)
+                    f.write(np.ascontiguousarray(vecs[idx - lo], np.float32).tobytes())
+            return int(len(live))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, bf16_plane: bool = True, chunk_rows: int = 65536,
+             capacity_slack: float = 0.0) -> "GalleryStore":
+        """Rebuild a store from :meth:`save` output: rows land in the saved order (so ties resolve as
+        before), vectors are ingested as stored (no second normalisation)."""
+        with open(path, "rb") as f:
+            if f.read(8) != cls.SNAP_MAGIC:
+                raise ValueError("%s is not a gallery snapshot" % path)
+            dim, _flags, n, tlen = struct.unpack("<IIQQ", f.read(24))
+            table = json.loads(f.read(tlen).decode("utf-8"))
+            tags = np.frombuffer(f.read(4 * n), dtype=np.int32)
+            store = cls(dim=dim, capacity=int(n * (1.0 + capacity_slack)) + 1, device=device, bf16_plane=bf16_plane)
+            for a in range(0, n, chunk_rows):
+                b = min(n, a + chunk_rows)
+                vecs = np.frombuffer(f.read(4 * dim * (b - a)), dtype=np.float32).reshape(b - a, dim)
+                store.append_rows(vecs, tags[a:b], prenormalised=True)
+        ids = table["ids"]
+        store._tenants = {str(k): int(v) for k, v in table["tenants"].items()}
+        store._meta = dict(table.get("meta", {}))
+        for r, pid in enumerate(ids):
+            store._row_of[pid] = r
+            store._id_of[r] = pid
+        return store

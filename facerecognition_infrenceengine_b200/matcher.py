@@ -85,6 +85,23 @@ class Matcher:
         return rows, scores, accept
 
 
+    # ---- first row, in gallery order, whose score reaches the threshold (exact fp32)
+    def first_above(self, Q: np.ndarray, threshold: float, strict: bool = False, company_id: Optional[str] = None,
+                    query_prenormalised: bool = False):
+        """(rows int64 [F], scores fp32 [F]); row -1 / score -1.0 when no row qualifies.  The scan rule of
+        the enrol-time duplicate check (trainingServer.py:170-200, strict) and of unknown-person
+        clustering (peopleCount.py:446-452)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.store.dim)
+        F = len(Q)
+        rows, scores = np.empty(F, np.int64), np.empty(F, np.float32)
+        tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
+        p = _params(self.metric, "scan_f32", threshold, tenant, 0)
+        p.flags = (N.FIRST_STRICT if strict else 0) | (N.QUERY_PRENORMALISED if query_prenormalised else 0)
+        N.check(N.lib.frg_first_match_host(self.store.handle, Q.ctypes.data_as(C.c_void_p), F, C.byref(p),
+                                           rows.ctypes.data_as(C.c_void_p), scores.ctypes.data_as(C.c_void_p)))
+        return rows, scores
+
+
 class FaceRecognitionProcessor:
     """Drop-in for the matching half of infrenceServer.FaceRecognitionProcessor (:400-563).
 

@@ -86,7 +86,7 @@ typedef struct frg_match_params_t {
   int32_t tenant;      /* < 0: all tenants (peopleCount.py:848); else only rows with this tag
                           (company subset, infrenceServer.py:343-380) */
   int64_t row_offset;  /* added to every returned row (global row of a shard's first row) */
-  uint32_t flags;      /* reserved, 0 */
+  uint32_t flags;      /* FRG_QUERY_PRENORMALISED (match and first_match), FRG_FIRST_STRICT (first_match) */
   uint32_t reserved;
 } frg_match_params_t;
 
@@ -137,6 +137,22 @@ FRG_API int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const
               int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
 FRG_API int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
                    int64_t* out_rows, float* out_scores, uint8_t* out_accept);
+
+/* ---- first row, in gallery order, whose score reaches the threshold (exact fp32).  Replaces the two
+ *      "first hit" scans next to the matching path:
+ *        trainingServer.py:170-200  duplicate face at enrolment: first stored template with cos > 0.4
+ *                                   (FRG_FIRST_STRICT)
+ *        peopleCount.py:446-452     unknown-person clustering: first cluster, in creation order, with
+ *                                   dot(avg_embedding, q) >= 0.65 (a FRG_STORE_RAW store of cluster means,
+ *                                   FRG_QUERY_PRENORMALISED)
+ *      p->flags: FRG_FIRST_STRICT ('>' instead of '>='), FRG_QUERY_PRENORMALISED (use q as given).
+ *      out_rows [nq] (-1 = none), out_scores [nq] (score of that row, -1.0f = none). */
+#define FRG_FIRST_STRICT        1u
+#define FRG_QUERY_PRENORMALISED 2u
+FRG_API int frg_first_match(frg_store* s, const float* q, int32_t nq, const frg_match_params_t* p,
+                    int64_t* out_rows, float* out_scores, void* stream);
+FRG_API int frg_first_match_host(frg_store* s, const float* q, int32_t nq, const frg_match_params_t* p,
+                         int64_t* out_rows, float* out_scores);
 
 /* ---- k-way merge of per-shard results (multi-GPU tail).
  * scores/rows: [parts][nq][k] (each list best-first, unfilled slots row -1), e.g. the output of an
