@@ -308,29 +308,33 @@ int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, 
           return FRG_ERR_STATE;
         }
   }
-  float* dv = nullptr; int64_t* dr = nullptr; int32_t* dt = nullptr;
-  int rc = FRG_OK;
-  cudaStream_t st = nullptr;
-  auto cleanup = [&]() { cudaFree(dv); cudaFree(dr); cudaFree(dt); };
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dv), size_t(n) * s->dim * sizeof(float));
-  if (e == cudaSuccess) e = cudaMemcpy(dv, vecs, size_t(n) * s->dim * sizeof(float), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && rows) {
-    e = cudaMalloc(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMemcpy(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice);
+  // stream-ordered staging (no cudaMalloc / cudaFree: those synchronise the whole device and would
+  // stall every match in flight): one allocation [vecs | rows | tags], async copies, ingest, one
+  // stream synchronize so that the caller's host buffers may be reused on return
+  cudaStream_t st = cudaStreamPerThread;
+  const size_t vb = (size_t(n) * s->dim * sizeof(float) + 255) & ~size_t(255);
+  const size_t rb = rows ? ((size_t(n) * sizeof(int64_t) + 255) & ~size_t(255)) : 0;
+  const size_t tb = tags ? size_t(n) * sizeof(int32_t) : 0;
+  unsigned char* d = nullptr;
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d), vb + rb + tb + 16, st));
+  float* dv = reinterpret_cast<float*>(d);
+  int64_t* dr = rows ? reinterpret_cast<int64_t*>(d + vb) : nullptr;
+  int32_t* dt = tags ? reinterpret_cast<int32_t*>(d + vb + rb) : nullptr;
+  cudaError_t e = cudaMemcpyAsync(dv, vecs, size_t(n) * s->dim * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && rows) e = cudaMemcpyAsync(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && tags) e = cudaMemcpyAsync(dt, tags, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  int rc = e == cudaSuccess ? FRG_OK : cuda_fail(e, "upsert_host staging", __FILE__, __LINE__);
+  if (rc == FRG_OK) {
+    bool negative = false;
+    if (tags) for (int64_t i = 0; i < n; ++i) negative |= tags[i] < 0;
+    rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative);
   }
-  if (e == cudaSuccess && tags) {
-    e = cudaMalloc(reinterpret_cast<void**>(&dt), size_t(n) * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMemcpy(dt, tags, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice);
-  }
-  if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upsert_host staging", __FILE__, __LINE__); }
-  bool negative = false;
-  if (tags) for (int64_t i = 0; i < n; ++i) negative |= tags[i] < 0;
-  rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative);
+  cudaError_t ef = cudaFreeAsync(d, st);
   if (rc == FRG_OK) {
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    else if (ef != cudaSuccess) rc = cuda_fail(ef, "cudaFreeAsync", __FILE__, __LINE__);
   }
-  cleanup();
   return rc;
 }
 
@@ -351,15 +355,16 @@ int frg_store_remove_host(frg_store* s, const int64_t* rows, int64_t n) {
   if (!s || (n > 0 && !rows) || n < 0) { set_error("remove_host: bad argument"); return FRG_ERR_INVALID; }
   if (n == 0) return FRG_OK;
   DeviceGuard g(s->device);
+  cudaStream_t st = cudaStreamPerThread;
   int64_t* dr = nullptr;
-  FRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(int64_t)));
-  cudaError_t e = cudaMemcpy(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice);
-  int rc = e == cudaSuccess ? frg_store_remove(s, dr, n, nullptr) : cuda_fail(e, "cudaMemcpy", __FILE__, __LINE__);
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(int64_t), st));
+  cudaError_t e = cudaMemcpyAsync(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  int rc = e == cudaSuccess ? frg_store_remove(s, dr, n, st) : cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+  cudaFreeAsync(dr, st);
   if (rc == FRG_OK) {
-    e = cudaStreamSynchronize(nullptr);
+    e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
   }
-  cudaFree(dr);
   return rc;
 }
 

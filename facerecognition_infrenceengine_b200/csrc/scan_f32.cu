@@ -131,39 +131,35 @@ __device__ __forceinline__ void scan_pass(const float* __restrict__ master, cons
   const int64_t gw = int64_t(blockIdx.x) * kScanWarps + warp;
   const int64_t tw = int64_t(gridDim.x) * kScanWarps;
 
-  for (int64_t r0 = gw; r0 < rows; r0 += 2 * tw) {
-    const int64_t r1 = r0 + tw;
-    const bool has1 = r1 < rows;
-    float4 g0[NJ], g1[NJ];
-    const float4* p0 = reinterpret_cast<const float4*>(master + r0 * DIM) + lane;
-    const float4* p1 = reinterpret_cast<const float4*>(master + (has1 ? r1 : r0) * DIM) + lane;
+  // R rows in flight per warp (R * NJ 16-byte loads per lane): enough bytes in flight per SM to
+  // cover the HBM latency even for short rows
+  constexpr int R = NJ >= 4 ? 2 : (NJ == 2 ? 4 : 8);
+  for (int64_t rb = gw; rb < rows; rb += int64_t(R) * tw) {
+    float4 g[R][NJ];
+    int32_t tg[R];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) g0[j] = ldg_stream(p0 + j * 32);
+    for (int u = 0; u < R; ++u) {
+      const int64_t r = rb + int64_t(u) * tw;
+      const bool has = r < rows;
+      const float4* pr = reinterpret_cast<const float4*>(master + (has ? r : rb) * DIM) + lane;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) g1[j] = ldg_stream(p1 + j * 32);
-    const int32_t t0 = __ldg(tags + r0);
-    const int32_t t1 = has1 ? __ldg(tags + r1) : -1;
-
-    float a0[QB], a1[QB];
-    row_dots<NJ, QB, METRIC>(g0, q, a0);
-    row_dots<NJ, QB, METRIC>(g1, q, a1);
-    float s0 = butterfly<QB>(a0, lane);
-    float s1 = butterfly<QB>(a1, lane);
-    if (METRIC == FRG_METRIC_EUCLIDEAN) { s0 = -s0; s1 = -s1; }
-    // removed rows (tag -1) and other tenants never take part (infrenceServer.py:343-380)
-    const bool v0 = t0 >= 0 && (tenant < 0 || t0 == tenant);
-    const bool v1 = t1 >= 0 && (tenant < 0 || t1 == tenant);
-    const bool in0 = v0 && s0 > kth;          // false for NaN
-    if (__any_sync(0xffffffffu, in0)) {
-      if (in0 && rep) list_insert(my_sc, my_ix, K, s0, int32_t(r0));
-      __syncwarp();
-      kth = my_sc[K - 1];
+      for (int j = 0; j < NJ; ++j) g[u][j] = ldg_stream(pr + j * 32);
+      tg[u] = has ? __ldg(tags + r) : -1;
     }
-    const bool in1 = v1 && s1 > kth;
-    if (__any_sync(0xffffffffu, in1)) {
-      if (in1 && rep) list_insert(my_sc, my_ix, K, s1, int32_t(r1));
-      __syncwarp();
-      kth = my_sc[K - 1];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      float a[QB];
+      row_dots<NJ, QB, METRIC>(g[u], q, a);
+      float sdot = butterfly<QB>(a, lane);
+      if (METRIC == FRG_METRIC_EUCLIDEAN) sdot = -sdot;
+      // removed rows (tag -1) and other tenants never take part (infrenceServer.py:343-380)
+      const bool valid = tg[u] >= 0 && (tenant < 0 || tg[u] == tenant);
+      const bool ins = valid && sdot > kth;          // false for NaN
+      if (__any_sync(0xffffffffu, ins)) {
+        if (ins && rep) list_insert(my_sc, my_ix, K, sdot, int32_t(rb + int64_t(u) * tw));
+        __syncwarp();
+        kth = my_sc[K - 1];
+      }
     }
   }
   __syncthreads();
@@ -249,7 +245,8 @@ scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restr
 }
 
 static int scan_grid(const ScanArgs& a) {
-  int64_t want = (a.rows + kScanWarps * 2 - 1) / (kScanWarps * 2);
+  const int r = a.dim >= 512 ? 2 : (a.dim == 256 ? 4 : 8);     // rows in flight per warp (scan_pass)
+  int64_t want = (a.rows + kScanWarps * r - 1) / (kScanWarps * r);
   int64_t cap = int64_t(a.sm_count) * 2;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -259,7 +256,7 @@ static int scan_grid(const ScanArgs& a) {
 static int scan_qb(int dim, int nq) {
   const int nj = dim / 128;
   int qb = 16 / nj;                 // register budget: QB * NJ float4 <= 16 (64 registers of queries)
-  if (qb > 4) qb = 4;
+  if (qb > 8) qb = 8;               // 16 would spill under the 128-register cap of 2 CTAs / SM
   if (qb < 1) qb = 1;
   while (qb > 1 && qb / 2 >= nq) qb /= 2;
   return qb;
@@ -293,6 +290,7 @@ static int launch_qb(const ScanArgs& a, int qb, int grid, int q0, int nq_pass, f
   if (qb == 1) return launch_metric<NJ, 1>(a, grid, q0, nq_pass, ps, pi, st);
   if (qb == 2) return launch_metric<NJ, 2>(a, grid, q0, nq_pass, ps, pi, st);
   if constexpr (NJ <= 4) { if (qb == 4) return launch_metric<NJ, 4>(a, grid, q0, nq_pass, ps, pi, st); }
+  if constexpr (NJ <= 2) { if (qb == 8) return launch_metric<NJ, 8>(a, grid, q0, nq_pass, ps, pi, st); }
   set_error("scan_f32: unsupported queries-per-pass %d for dim %d", qb, NJ * 128);
   return FRG_ERR_UNSUPPORTED;
 }
