@@ -393,6 +393,7 @@ def ours_arm(args, rank, world):
         return
 
     roof = roofline_for(variant, n, dim, F, main["dom_ms"] / max(main["dom_launches"], 1), peaks)
+    roof["traffic"], roof["traffic_source"] = ncu_traffic(variant, n, dim, F, world)
     roof["launches_per_step"] = main["dom_launches"] / args.steps
     roof["kernel_share_of_step"] = main["dom_ms"] / main["total_ms"]
     roof["step_frac_of_roofline"] = step_roofline_ms(n, dim, F, peaks) / ms_per_step
@@ -409,7 +410,12 @@ def ours_arm(args, rank, world):
         r = matcher.match(Qc, 1, 0.45, variant=args.variant)
         same = all((res_[0] == gid[0] or (res_[0] is None and gid[0] is None)) and (res_[2] == bool(a))
                    for res_, gid, a in zip(results, r.ids, r.accept))
+        # BASELINE config 1 as the reference runs it: 10 000 x 512 gallery, 64 faces, ONE core
+        G1 = G[:10000]
+        Q1, _ = synth.queries(64, 10000, dim)
+        qps1, _, _ = run_cpu_loop(G1, Q1, 0.45, 1, 1, 0)
         cpu = {"value": qps, "unit": UNIT, "cores": procs, "kind": "port",
+               "config1_10k_x_64_one_core_queries_per_s": qps1,
                "sample": "%d queries (1 per worker process) x %d rows, top-1 + threshold 0.45, "
                          "per-face Python loop of peopleCount.py:860-887" % (q_cpu, n),
                "seconds": per_step, "gpu_agrees": bool(same)}
@@ -424,6 +430,32 @@ def ours_arm(args, rank, world):
             "gpu_launches": main["launches_per_step"] * args.steps,
             "clocks": clocks, "parity": parity, "sweep": sweep, "peaks": peaks}
     print(json.dumps(line), flush=True)
+
+
+def ncu_traffic(variant, n, dim, F, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
+    capture committed under profiles/ (only when it was taken on this very workload), else None."""
+    if world != 1 or variant != "tc_exact" or (n, dim) != (1_000_000, 512):
+        return None, None
+    name = {1024: "r01_ncu_full_tc_scan_b1024_v3.txt", 64: "r01_ncu_full_tc_scan_b64_v1.txt"}.get(F)
+    path = os.path.join(ROOT, "profiles", name) if name else None
+    if not path or not os.path.exists(path):
+        return None, None
+    rd = wr = None
+    in_filter = False
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for line in open(path):
+        if line.startswith("== "):
+            in_filter = "tc_scan_kernel<1" in line
+        elif in_filter and "dram__bytes_read.sum" in line:
+            f = line.split()
+            rd = float(f[1]) * scale[f[2]]
+        elif in_filter and "dram__bytes_write.sum" in line:
+            f = line.split()
+            wr = float(f[1]) * scale[f[2]]
+    if rd is None or wr is None:
+        return None, None
+    return rd + wr, "profiles/" + name
 
 
 def step_roofline_ms(n, dim, F, peaks, bytes_per_elem=2):
