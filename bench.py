@@ -179,7 +179,12 @@ def workload_config(args, batch, world=1):
     cfg = {"workload": "configs[1]: 512-d cosine, 1M-template gallery, top-5, single B200",
            "gallery_rows": args.rows, "dim": args.dim, "batch": batch, "k": args.k, "threshold": 0.45,
            "variant": args.variant}
-    if world > 1 and args.shard == "gallery":
+    if args.rows_total:
+        cfg.update({"workload": "configs[3]: 512-d cosine, %d-template gallery row-sharded over %d B200 (%d rows each), "
+                                "batch %d, top-%d, NCCL all-gather + k-way merge" % (
+                                    args.rows_total, world, args.rows, batch, args.k),
+                    "sharding": "gallery rows", "gallery_rows_total": args.rows_total})
+    elif world > 1 and args.shard == "gallery":
         cfg.update({"workload": "configs[1] per GPU, gallery row-sharded over %d GPUs (%d rows each, %d total), "
                                 "queries replicated, NCCL all-gather of per-rank top-k + k-way merge" % (
                                     world, args.rows, args.rows * world),
@@ -223,6 +228,8 @@ def ours_arm(args, rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    if args.rows_total:                      # BASELINE configs[3]: a FIXED gallery row-sharded over the ranks
+        args.rows = args.rows_total // world
     n, dim, k = args.rows, args.dim, args.k
 
     sharded = world > 1 and args.shard == "gallery"
@@ -240,7 +247,7 @@ def ours_arm(args, rank, world):
     nb = 4
     n_total = n * world if sharded else n
     # units of work per step: sharded -> every query is matched against world x n rows
-    scale = float(world)
+    scale = 1.0 if args.rows_total else float(world)     # fixed gallery: plain queries/s (strong scaling)
 
     def make_batches(F):
         # a ring of distinct query batches (50 % genuine / 50 % impostor);
@@ -422,7 +429,8 @@ def ours_arm(args, rank, world):
         del G
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.rows_total else "weak",
             "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
             "data": "synthetic", "config": workload_config(args, F, world), "variant": variant,
             "queries_per_s_raw": value / scale if sharded else value,
@@ -493,6 +501,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--variant", default="auto")
     ap.add_argument("--sweep", default="1,8,64,128,256,512,1024")
+    ap.add_argument("--rows-total", type=int, default=0,
+                    help="fixed total gallery, row-sharded over the ranks (BASELINE configs[3]: 100000000 with "
+                         "--batch 4096 --k 10); default: --rows per GPU")
     ap.add_argument("--shard", default="gallery", choices=["gallery", "queries"],
                     help="N>1: row-shard the gallery (all-gather + merge) or replicate it and shard the query stream")
     ap.add_argument("--no-cpu", action="store_true")
