@@ -9,6 +9,7 @@ loads on a machine without libcuda.so (symbol checks) and fails only when comput
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import shutil
@@ -23,9 +24,9 @@ LIB = os.path.join(CSRC, "libfrg.so")
 OBJ = os.path.join(CSRC, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function",
-              "-I", INCLUDE, "-I", CSRC]
+BASE_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function"]
+NVCC_FLAGS = BASE_FLAGS + ["-I", INCLUDE, "-I", CSRC]
 
 
 class NoCompiler(RuntimeError):
@@ -50,16 +51,32 @@ def _digest() -> str:
             h.update(f.encode())
             h.update(open(os.path.join(CSRC, f), "rb").read())
     h.update(open(os.path.join(INCLUDE, "frg.h"), "rb").read())
-    h.update(" ".join(ARCH + NVCC_FLAGS).encode())
+    h.update(" ".join(ARCH + BASE_FLAGS).encode())     # no absolute paths: the tree moves (GPU box)
     return h.hexdigest()
+
+
+def _fresh(stamp: str, digest: str) -> bool:
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if not force and _fresh(stamp, digest):
         return LIB
+    # one builder at a time (torchrun starts N ranks at once); the others wait, then find it fresh
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _fresh(stamp, digest):
+                return LIB
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp: str, digest: str, verbose: bool) -> str:
     cc = nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
 
@@ -77,11 +94,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for _, log in results:
             sys.stderr.write(log)
     objs = [o for o, _ in results]
-    cmd = [cc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-cudart", "static",
+    tmp = "%s.tmp.%d" % (LIB, os.getpid())
+    cmd = [cc, *ARCH, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fPIC", "-cudart", "static",
            "-Xlinker", "--exclude-libs,ALL"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)                      # atomic: a concurrent dlopen never sees a partial file
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB
