@@ -222,7 +222,7 @@ __device__ __forceinline__ uint32_t float_key(float x) {
 __device__ __forceinline__ float key_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
-constexpr uint32_t kNoScoreKey = 0x407FFFFFu;     // float_key(-1.0f)
+// (float_key(-1.0f) == 0x407FFFFF: the value normalise_queries_kernel resets the keys to)
 
 struct TcScanParams {
   int dim;                 // 512 etc. (multiple of 64)
@@ -576,7 +576,6 @@ __device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], 
 }
 
 constexpr int kSelectWarps = 2;
-constexpr int kMaxChunks = 160;       // >= SM count of the part (multiple of 32): candidate segments per query
 
 template <int K>
 __global__ void __launch_bounds__(kSelectWarps * 32)
@@ -733,7 +732,7 @@ static int get_encode(EncodeTiledFn* out) {
 
 // 2-D bf16 row-major [rows][dim] view with a row pitch (bytes), box = 64 k x box_rows, 128B swizzle
 static int make_map(CUtensorMap* map, const void* ptr, int dim, int64_t rows, size_t pitch_bytes, int box_rows) {
-  EncodeTiledFn enc;
+  EncodeTiledFn enc = nullptr;
   FRG_CHECK(get_encode(&enc));
   cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(rows)};
   cuuint64_t gstride[1] = {cuuint64_t(pitch_bytes)};
@@ -784,7 +783,6 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
     const int units = pl->pair ? sm_count / 2 : sm_count;
     const int cols = pl->pair ? pl->qtiles / 2 : pl->qtiles;
     int c = units / gcd_int(units, cols);
-    if (c > kMaxChunks) c = kMaxChunks;
     if (c > tiles) c = tiles;
     return c < 1 ? 1 : c;
   };
