@@ -575,51 +575,47 @@ __device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], 
   *best_s = bs; *best_r = br;
 }
 
-constexpr int kSelectWarps = 2;
+constexpr int kSelectWarps = 4;
 
+// The dense candidate list of a query (a few hundred entries, L2-resident: the filter kernel has just
+// written it) is read twice straight from global memory - no shared-memory staging, so every query's
+// warp is resident at once and the DRAM/L2 latencies of different queries overlap.
 template <int K>
 __global__ void __launch_bounds__(kSelectWarps * 32)
 select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ cand_total,
-                      int kStage, int nq, int k, int dim, const float* __restrict__ qn,
+                      int dense_cap, int nq, int k, int dim, const float* __restrict__ qn,
                       const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
                       uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged) {
-  extern __shared__ int2 stage_all[];                // [warp][kStage] candidates staged per warp
   __shared__ int keep_row[kSelectWarps][kMaxKeep];
   __shared__ float keep_sc[kSelectWarps][kMaxKeep];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const int q = blockIdx.x * kSelectWarps + w;
   if (q >= nq) return;
-  int2* stage = stage_all + size_t(w) * kStage;
 
-  // stage this query's dense candidate list in shared memory (coalesced, 4 loads in flight per lane)
   const int total = cand_total[q];
-  bool overflow = total > kStage;                    // also set by a poisoned total (segment overflow)
+  bool overflow = total > dense_cap;                 // also set by a poisoned total (segment overflow)
   if (overflow) {
     // the dense list is incomplete (and partly unwritten): leave the query to the exact fallback
     if (lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
     return;
   }
   const int n = total;
-  const int2* mine = dense + size_t(q) * kStage;
-  for (int c0 = lane; c0 < n; c0 += 128) {
-    int2 e[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (c0 + 32 * u < n) e[u] = mine[c0 + 32 * u];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (c0 + 32 * u < n) stage[c0 + 32 * u] = e[u];
-  }
-  __syncwarp();
+  const int2* mine = dense + size_t(q) * dense_cap;
 
   // (a) tau = k-th best coarse score: lane-local top-K, then k rounds of warp arg-max
   float sc[K];
   int32_t ix[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) { sc[j] = -INFINITY; ix[j] = 0x7fffffff; }
-  for (int c = lane; c < n; c += 32) {
-    const int2 e = stage[c];
-    lane_insert<K>(sc, ix, __int_as_float(e.y), e.x);
+  for (int c0 = lane; c0 < n; c0 += 128) {
+    int2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = c0 + 32 * u < n ? mine[c0 + 32 * u] : make_int2(0x7fffffff, __float_as_int(-INFINITY));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (c0 + 32 * u < n) lane_insert<K>(sc, ix, __int_as_float(e[u].y), e[u].x);
   }
   float tau = -INFINITY;
   float top_sc = 0.f; int32_t top_ix = -1;     // lane j keeps the j-th coarse winner (TC_BF16 output)
@@ -649,7 +645,7 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
     const int c = c0 + lane;
     int2 e = make_int2(-1, 0);
     bool kp = false;
-    if (c < n) { e = stage[c]; kp = __int_as_float(e.y) >= keep_thr; }
+    if (c < n) { e = mine[c]; kp = __int_as_float(e.y) >= keep_thr; }
     const unsigned bal = __ballot_sync(0xffffffffu, kp);
     const int pos = m + __popc(bal & ((1u << lane) - 1));
     if (kp && pos < kMaxKeep) keep_row[w][pos] = e.x;
@@ -904,12 +900,9 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   profile_begin(st, kStageSelect);
   const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
   const int rs = rescore ? 1 : 0;
-  const size_t sel_smem = size_t(kSelectWarps) * pl.stage_entries * sizeof(int2);
 #define FRG_SELECT(KK)                                                                                          \
-  FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                int(kSelectWarps * 8192 * sizeof(int2))));                                      \
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-  select_rescore_kernel<KK><<<grid, kSelectWarps * 32, sel_smem, st>>>(dense, cnt, pl.stage_entries, nq, k,     \
+  select_rescore_kernel<KK><<<grid, kSelectWarps * 32, 0, st>>>(dense, cnt, pl.stage_entries, nq, k,            \
       s->dim, qn, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
   switch (pl.kreg) {
     case 1: FRG_SELECT(1); break;
