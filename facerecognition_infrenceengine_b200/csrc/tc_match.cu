@@ -641,15 +641,21 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   // (b) compact the rows that can still be in the true top-k
   const float keep_thr = tau - 2.0f * kCoarseEps;
   int m = 0;
-  for (int c0 = 0; c0 < n; c0 += 32) {
-    const int c = c0 + lane;
-    int2 e = make_int2(-1, 0);
-    bool kp = false;
-    if (c < n) { e = mine[c]; kp = __int_as_float(e.y) >= keep_thr; }
-    const unsigned bal = __ballot_sync(0xffffffffu, kp);
-    const int pos = m + __popc(bal & ((1u << lane) - 1));
-    if (kp && pos < kMaxKeep) keep_row[w][pos] = e.x;
-    m += __popc(bal);
+  for (int c0 = 0; c0 < n; c0 += 128) {             // 4 independent loads per lane per round
+    int2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u + lane;
+      e[u] = c < n ? mine[c] : make_int2(-1, __float_as_int(-INFINITY));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool kp = (c0 + 32 * u + lane < n) && __int_as_float(e[u].y) >= keep_thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, kp);
+      const int pos = m + __popc(bal & ((1u << lane) - 1));
+      if (kp && pos < kMaxKeep) keep_row[w][pos] = e[u].x;
+      m += __popc(bal);
+    }
   }
   if (m > kMaxKeep) { overflow = true; m = kMaxKeep; }
   __syncwarp();
