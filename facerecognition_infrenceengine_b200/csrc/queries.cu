@@ -18,7 +18,7 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
   // ordered key of -1.0f, flagged-query counter at 0 (saves a memset node per match)
   if (group_keys) group_keys[size_t(w) * 32 + lane] = 0x407FFFFFu;
   if (cand_total && lane == 0) cand_total[w] = 0;
-  if (n_flagged && w == 0 && lane < 2) n_flagged[lane] = 0;      // count, ticket
+  if (n_flagged && w == 0 && lane < 3) n_flagged[lane] = 0;      // count, ticket, probe arrivals
   const float4* src = reinterpret_cast<const float4*>(q + size_t(w) * dim);
   const int nvec = dim >> 2;
   float norm = 1.0f;

@@ -210,7 +210,7 @@ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
-enum TcMode { kModeGroupMax = 0, kModeFilter = 1 };
+enum TcMode { kModeGroupMax = 0, kModeFilter = 1, kModeFused = 2 };
 constexpr int kGroups = 32;
 
 // order-preserving float <-> uint32 key, so that the group maxima of all pre-pass CTAs can be folded
@@ -235,6 +235,8 @@ struct TcScanParams {
   uint32_t* group_key;
   // FILTER inputs / outputs
   int k;                   // L[q] = k-th largest of the 32 group maxima (computed in the prologue)
+  int* arrive;             // FUSED: CTAs that have published their probe-tile maxima
+  int arrive_target;       // FUSED: wait (bounded) for this many before deriving the floor; 0 = do not wait
   int seg;                 // candidate slots per (query, chunk) private segment
   int2* cand;              // [nq][chunks][seg] (row, score bits): written while scanning
   int* cand_total;         // [nq] candidates of the query over all chunks (atomicAdd at the CTA's end)
@@ -287,6 +289,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   const int tiles_total = (tiles_all + p.tile_scale - 1) / p.tile_scale;
   const int tile_begin = int((int64_t(tiles_total) * chunk) / chunks);
   const int tile_end = int((int64_t(tiles_total) * (chunk + 1)) / chunks);
+  // FUSED: the CTA's first n_probe tiles (1/64 of its chunk, at least one) are visited twice - first as
+  // a probe (group maxima only, published to all CTAs so that everyone can derive the floor L[q]),
+  // and once more at the very end to emit from them
+  const int n_tiles = tile_end - tile_begin;
+  const int n_probe = MODE == kModeFused ? (n_tiles + 63) / 64 : 0;
+  const int n_iter = n_tiles + n_probe;
+  auto tile_of = [&](int it) { return it < n_tiles ? tile_begin + it : tile_begin + (it - n_tiles); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
@@ -320,7 +329,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
           tma_load_2d(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
       }
       int stage = 0; uint32_t phase = 0;
-      for (int t = tile_begin; t < tile_end; ++t) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int t = tile_of(it);
         const int row0 = t * p.tile_scale * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty(stage), phase ^ 1);
@@ -348,7 +358,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       int buf = 0; uint32_t tphase = 0;
       const uint64_t a_base = umma_desc_sw128(q_smem);
       const uint64_t b_base = umma_desc_sw128(stage_smem);
-      for (int t = tile_begin; t < tile_end; ++t) {
+      for (int it = 0; it < n_iter; ++it) {
         mbar_wait(bar_tempty(buf), tphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(buf * kAccN);
@@ -387,55 +397,65 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     // FILTER: the two warps of a quarter split every tile's columns (the epilogue is issue-latency
     // bound, two warps per scheduler hide it).  GROUPMAX: one warp per quarter does all columns (the
     // other only keeps the barrier protocol), so each (query, group) maximum costs ONE atomic per CTA.
-    constexpr int kSplit = MODE == kModeFilter ? kEpiWarps / 4 : 1;
-    const int half = MODE == kModeFilter ? (warp - 2) >> 2 : 0;
+    constexpr int kSplit = MODE != kModeGroupMax ? kEpiWarps / 4 : 1;
+    const int half = MODE != kModeGroupMax ? (warp - 2) >> 2 : 0;
     const bool idle = MODE == kModeGroupMax && warp >= 6;
     constexpr int kBlocksPerWarp = (kAccN / 32) / kSplit;
     const int q_local = quarter * 32 + lane;
     const int q = qtile * kTileQ + q_local;
     const bool q_real = q < p.nq;
 
-    float gmax[kGroups];                                 // GROUPMAX: running maximum per row group
+    float gmax[kGroups];                                 // GROUPMAX / FUSED probe: running maximum per row group
     float thr = INFINITY;
     int emitted = 0;
     int2* my_seg = nullptr;
-    if (MODE == kModeGroupMax) {
+    // L[q] = k-th largest of the 32 group maxima published so far.  The groups are disjoint row sets,
+    // so that value is reached by k distinct valid rows: L[q] <= tau, whatever subset has been seen.
+    auto derive_thr = [&]() {
+      const uint4* src = reinterpret_cast<const uint4*>(p.group_key + size_t(q) * kGroups);
+      float g[kGroups];
+#pragma unroll
+      for (int j = 0; j < kGroups; j += 4) {
+        uint4 x;
+        if (MODE == kModeFused) {           // other CTAs are still publishing: bypass the non-coherent path
+          asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(src + j / 4) : "memory");
+        } else {
+          x = __ldg(src + j / 4);
+        }
+        g[j] = key_float(x.x); g[j + 1] = key_float(x.y); g[j + 2] = key_float(x.z); g[j + 3] = key_float(x.w);
+      }
+      float floor_v = kNoScore;
+      for (int r = 0; r < p.k; ++r) {
+        float m = g[0];
+#pragma unroll
+        for (int j = 1; j < kGroups; ++j) m = fmaxf(m, g[j]);
+        floor_v = m;
+        bool popped = false;                 // remove ONE instance of the maximum
+#pragma unroll
+        for (int j = 0; j < kGroups; ++j) {
+          const bool hit = !popped && g[j] == m;
+          g[j] = hit ? -INFINITY : g[j];
+          popped |= hit;
+        }
+      }
+      // fewer than k usable groups so far: no bound, every valid row is a candidate
+      // (finite, so that masked columns, which are set to -inf, still fail the comparison)
+      return (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
+    };
+    if (MODE != kModeFilter) {
 #pragma unroll
       for (int j = 0; j < kGroups; ++j) gmax[j] = kNoScore;
-    } else {
-      // L[q] = k-th largest of the 32 group maxima the pre-pass left behind.  The groups are
-      // disjoint row sets, so that value is reached by k distinct valid rows: L[q] <= tau.
-      if (q_real) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.group_key + size_t(q) * kGroups);
-#pragma unroll
-        for (int j = 0; j < kGroups; j += 4) {
-          const uint4 x = __ldg(src + j / 4);
-          gmax[j] = key_float(x.x); gmax[j + 1] = key_float(x.y);
-          gmax[j + 2] = key_float(x.z); gmax[j + 3] = key_float(x.w);
-        }
-        float floor_v = kNoScore;
-        for (int r = 0; r < p.k; ++r) {
-          float m = gmax[0];
-#pragma unroll
-          for (int j = 1; j < kGroups; ++j) m = fmaxf(m, gmax[j]);
-          floor_v = m;
-          bool popped = false;                 // remove ONE instance of the maximum
-#pragma unroll
-          for (int j = 0; j < kGroups; ++j) {
-            const bool hit = !popped && gmax[j] == m;
-            gmax[j] = hit ? -INFINITY : gmax[j];
-            popped |= hit;
-          }
-        }
-        // fewer than k usable groups in the sample: no bound, every valid row is a candidate
-        // (finite, so that masked columns, which are set to -inf, still fail the comparison)
-        thr = (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
-        my_seg = p.cand + ((size_t(q) * chunks + chunk) * (kEpiWarps / 4) + half) * p.seg;
-      }
+    }
+    if (MODE != kModeGroupMax && q_real) {
+      if (MODE == kModeFilter) thr = derive_thr();
+      my_seg = p.cand + ((size_t(q) * chunks + chunk) * (kEpiWarps / 4) + half) * p.seg;
     }
 
     int buf = 0; uint32_t tphase = 0;
-    for (int t = tile_begin; t < tile_end; ++t) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int t = tile_of(it);
+      const bool probe = MODE == kModeGroupMax || (MODE == kModeFused && it < n_probe);
       if (idle) {
         mbar_wait(bar_tfull(buf), tphase);
         if (lane == 0) {
@@ -473,6 +493,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
           // column j of every 32-row block belongs to group j (tiles start at multiples of 32)
 #pragma unroll
           for (int j = 0; j < 32; ++j) gmax[j] = fmaxf(gmax[j], v[j]);
+        } else if (MODE == kModeFused && probe) {
+          // this warp sees half of the tile's rows: it owns 16 of the 32 groups, (column mod 16)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gmax[j & 15] = fmaxf(gmax[j & 15], v[j]);
         } else {
           float m = v[0];
 #pragma unroll
@@ -509,6 +533,33 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         else mbar_arrive(bar_tempty(buf));
       }
       if (++buf == 2) { buf = 0; tphase ^= 1; }
+
+      if (MODE == kModeFused) {
+        const int since = it - (n_probe - 1);           // 0 at the last probe tile
+        if (since == 0) {
+          // publish the probe tile's maxima (groups half*16 .. +15), tell the grid, derive the floor
+          if (q_real) {
+            uint32_t* o = p.group_key + size_t(q) * kGroups + half * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (gmax[j] > kNoScore) atomicMax(o + j, float_key(gmax[j]));
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // the epilogue warps only
+          if (warp == 2 && lane == 0) atomicAdd(p.arrive, 1);
+          if (p.arrive_target > 0) {
+            // single-wave grid: give the other CTAs a few microseconds to publish too.  Bounded: a late
+            // CTA only makes this one's floor a little looser, never wrong.
+            for (int spin = 0; spin < 48; ++spin) {
+              if (*reinterpret_cast<volatile int*>(p.arrive) >= p.arrive_target) break;
+              __nanosleep(128);
+            }
+          }
+          if (q_real) thr = derive_thr();
+        } else if (since > 0 && (since & (since - 1)) == 0 && q_real && it < n_iter - 1) {
+          thr = derive_thr();              // late publishers: refresh 1, 2, 4, 8, ... tiles later
+        }
+      }
     }
     if (q_real && !idle) {
       if (MODE == kModeGroupMax) {
@@ -761,6 +812,7 @@ int tc_supported(int dim, int metric, const char** why) {
 
 struct TcPlan {
   bool pair;              // CTA-pair kernels (F > 128)
+  bool fused;             // pre-pass folded into the filter kernel (probe tile + published group maxima)
   int qtiles, stride, chunks_pre, chunks_main, kreg, seg, stage_entries;
   size_t off_keys, off_cnt, off_cand, off_dense, off_flag, total;
 };
@@ -773,6 +825,8 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   static const int pair_env = []() { const char* e = getenv("FRG_TC_PAIR"); return e ? atoi(e) : 1; }();
   pl->pair = pair_env != 0 && pl->qtiles >= 2;
   if (pl->pair) pl->qtiles = (pl->qtiles + 1) & ~1;      // clusters of 2 along x; a padding tile holds no query
+  static const int fused_env = []() { const char* e = getenv("FRG_TC_FUSED"); return e ? atoi(e) : 1; }();
+  pl->fused = fused_env != 0;
   const int tile_rows = pl->pair ? 2 * kTileR : kTileR;
   // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
   // leaves >= 16 K sampled rows
@@ -798,7 +852,14 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   // at tail mass Gamma(k)/n_view, and the 2*eps widening about doubles the count at dim 512.  Room for
   // mean + ~10 sigma keeps the overflow probability negligible; the exact fallback covers the rest.
   // (x1.5: the group-max floor is a little looser than an exact k-th best of the sample)
-  int stage_entries = int(3.0 * stride * (k + 10.0 * sqrt(double(k)) + 10.0));
+  // fused: the probe is 1/64 of every chunk, or one tile per CTA if that is more
+  int eff_stride = stride;
+  if (pl->fused) {
+    const int64_t probe_rows = int64_t((tiles_all / pl->chunks_main + 63) / 64) * pl->chunks_main * tile_rows;
+    eff_stride = int(rows / (probe_rows > 0 ? probe_rows : 1)) + 1;
+    if (eff_stride > 64) eff_stride = 64;
+  }
+  int stage_entries = int(3.0 * eff_stride * (k + 10.0 * sqrt(double(k)) + 10.0));
   if (stage_entries < 256) stage_entries = 256;
   if (stage_entries > 8192) stage_entries = 8192;
   pl->stage_entries = stage_entries;
@@ -813,7 +874,7 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   pl->off_cnt = take(size_t(nq) * 4);
   pl->off_cand = take(size_t(nq) * nseg * seg * 8);
   pl->off_dense = take(size_t(nq) * stage_entries * 8);
-  pl->off_flag = take(size_t(nq) * 4 + 8);     // flagged[nq], count, ticket
+  pl->off_flag = take(size_t(nq) * 4 + 12);    // flagged[nq], count, ticket, probe-arrival counter
   pl->total = off;
 }
 
@@ -890,18 +951,36 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
 
   TcScanParams p{};
   p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
-  // 1. pre-pass over the sampled tiles
-  p.n_rows = int(s->rows); p.tile_scale = pl.stride; p.group_key = keys; p.k = k;
-  profile_begin(st, kStagePrepass);
-  FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
-  profile_end(st, 1);
-  // 2. filter over the whole plane
-  p.tile_scale = 1; p.seg = pl.seg;
-  p.cand = cand; p.cand_total = cnt; p.dense = dense; p.dense_cap = pl.stage_entries;
-  profile_begin(st, kStageDominant);
-  int rc = launch_tc_scan_m<kModeFilter>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
-  FRG_CHECK(rc);
-  profile_end(st, 1);
+  p.n_rows = int(s->rows); p.group_key = keys; p.k = k;
+  p.seg = pl.seg; p.cand = cand; p.cand_total = cnt; p.dense = dense; p.dense_cap = pl.stage_entries;
+  int rc;
+  if (pl.fused) {
+    // 1+2. ONE kernel: every CTA probes its first tile, publishes the group maxima, derives L[q] from
+    // what all CTAs published, filters the rest of its chunk and finally the probe tile itself
+    p.tile_scale = 1;
+    p.arrive = n_flagged + 2;
+    {
+      // the first wave holds min(all CTAs, one per SM): later waves find the counter already there
+      const int ctas = pl.qtiles * pl.chunks_main;
+      p.arrive_target = ctas < sm_count ? ctas : sm_count;
+    }
+    profile_begin(st, kStageDominant);
+    rc = launch_tc_scan_m<kModeFused>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
+    FRG_CHECK(rc);
+    profile_end(st, 1);
+  } else {
+    // 1. pre-pass over the sampled tiles
+    p.tile_scale = pl.stride;
+    profile_begin(st, kStagePrepass);
+    FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
+    profile_end(st, 1);
+    // 2. filter over the whole plane
+    p.tile_scale = 1;
+    profile_begin(st, kStageDominant);
+    rc = launch_tc_scan_m<kModeFilter>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
+    FRG_CHECK(rc);
+    profile_end(st, 1);
+  }
   // 3. select + exact rescoring
   profile_begin(st, kStageSelect);
   const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
