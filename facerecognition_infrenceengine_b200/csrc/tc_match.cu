@@ -825,8 +825,12 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   static const int pair_env = []() { const char* e = getenv("FRG_TC_PAIR"); return e ? atoi(e) : 1; }();
   pl->pair = pair_env != 0 && pl->qtiles >= 2;
   if (pl->pair) pl->qtiles = (pl->qtiles + 1) & ~1;      // clusters of 2 along x; a padding tile holds no query
-  static const int fused_env = []() { const char* e = getenv("FRG_TC_FUSED"); return e ? atoi(e) : 1; }();
-  pl->fused = fused_env != 0;
+  // Fusing the pre-pass into the filter kernel saves a launch and a query-tile reload but probes a
+  // smaller sample (one tile per CTA), i.e. a looser floor and more candidates: measured on B200 it
+  // wins for a handful of queries (F = 1: 198 vs 208 us) and loses from F = 64 on (F = 1024: 814 vs
+  // 735 us).  FRG_TC_FUSED=0/1 forces either path.
+  static const int fused_env = []() { const char* e = getenv("FRG_TC_FUSED"); return e ? atoi(e) : -1; }();
+  pl->fused = fused_env >= 0 ? fused_env != 0 : nq <= 8;
   const int tile_rows = pl->pair ? 2 * kTileR : kTileR;
   // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
   // leaves >= 16 K sampled rows
