@@ -87,8 +87,11 @@ class ClockSampler:
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        # drop the first sample (taken while the GPU was still ramping up)
+        under = sm[1:] if len(sm) > 2 else sm
+        return {"sm_mhz": float(np.median(under)) if under else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": min(under) if under else None, "samples": len(sm), "reasons": sorted(reasons),
+                "window": "identical load for ~1 s immediately before + the timed region"}
 
 
 # ------------------------------------------------------------------------------------ CPU baseline
@@ -272,9 +275,19 @@ def ours_arm(args, rank, world):
         launches_per_step, variant = N.last_launch_count(), N.last_variant()
         sampler = None
         if clocks:
+            # nvidia-smi samples every 100 ms: keep the GPU under the SAME load for ~1 s right before the
+            # timed region (untimed), so that the clock / throttle record describes the state the timed
+            # steps run in even when K steps last only milliseconds
             sampler = ClockSampler(local)
             sampler.start()
-            time.sleep(0.3)
+            t_end = time.perf_counter() + args.clock_preload_s
+            i = 0
+            while time.perf_counter() < t_end:
+                step(i)
+                i += 1
+                if i % 64 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
         N.profile_enable(True)
         N.profile_collect()
         if world > 1:
@@ -491,7 +504,7 @@ def tc_roofline(variant, n, dim, F, launch_ms, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
@@ -501,6 +514,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--variant", default="auto")
     ap.add_argument("--sweep", default="1,8,64,128,256,512,1024")
+    ap.add_argument("--clock-preload-s", type=float, default=1.2,
+                    help="seconds of untimed identical load before the timed region, for the clock sampler")
     ap.add_argument("--rows-total", type=int, default=0,
                     help="fixed total gallery, row-sharded over the ranks (BASELINE configs[3]: 100000000 with "
                          "--batch 4096 --k 10); default: --rows per GPU")
