@@ -444,7 +444,10 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
 // --------------------------------------------------------------------------------------------- match
 static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq) {
   const char* why = "";
-  const bool tc_ok = s->plane != nullptr && tc_supported(s->dim, p->metric, &why);
+  // The filter's error bound assumes unit-norm rows and queries: raw stores (Euclidean galleries,
+  // cluster means) and caller-normalised queries always take the exact scan.
+  const bool unit = !(s->flags & FRG_STORE_RAW) && !(p->flags & FRG_QUERY_PRENORMALISED);
+  const bool tc_ok = s->plane != nullptr && unit && tc_supported(s->dim, p->metric, &why);
   if (p->variant != FRG_VARIANT_AUTO) return p->variant;
   // dispatch table: the tensor-core filter reads 2 B/element instead of 4 and wins from
   // the smallest batches on; the exact scan remains for galleries without a scan plane, for the
@@ -479,6 +482,10 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   const char* why = "";
   if (!s->plane) { set_error("match: the store was created without FRG_STORE_BF16_PLANE"); return FRG_ERR_UNSUPPORTED; }
   if (!tc_supported(s->dim, p->metric, &why)) { set_error("match: %s", why); return FRG_ERR_UNSUPPORTED; }
+  if ((s->flags & FRG_STORE_RAW) || (p->flags & FRG_QUERY_PRENORMALISED)) {
+    set_error("match: tensor-core variants need unit-norm rows and queries (raw store / prenormalised query given)");
+    return FRG_ERR_UNSUPPORTED;
+  }
   if (s->rows > 0x7fffffff) { set_error("match: more than 2^31-1 rows in one shard"); return FRG_ERR_UNSUPPORTED; }
   if (s->rows == 0) return match_scan(s, q, nq, k, p, sm_count, out_rows, out_scores, out_accept, st);
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
