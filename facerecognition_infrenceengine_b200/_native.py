@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libfrg.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE = range(6)
 METRIC_COSINE, METRIC_EUCLIDEAN = 0, 1
 VARIANT_AUTO, VARIANT_SCAN_F32, VARIANT_TC_EXACT, VARIANT_TC_BF16 = 0, 1, 2, 3
-STORE_BF16_PLANE, STORE_RAW = 1, 2
+STORE_BF16_PLANE, STORE_RAW, STORE_BF16_ONLY = 1, 2, 4
 ROWS_PRENORMALISED = 1
 FIRST_STRICT, QUERY_PRENORMALISED = 1, 2
 MAX_K = 16

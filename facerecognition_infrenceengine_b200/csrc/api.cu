@@ -101,16 +101,20 @@ int store_begin_read(frg_store* s, cudaStream_t stream) {
   return FRG_OK;
 }
 
+static bool has_master(const frg_store* s) { return !(s->flags & FRG_STORE_BF16_ONLY); }
+static bool has_plane(const frg_store* s) { return (s->flags & (FRG_STORE_BF16_PLANE | FRG_STORE_BF16_ONLY)) != 0; }
+
 static size_t row_bytes(const frg_store* s) {
-  return size_t(s->dim) * (sizeof(float) + ((s->flags & FRG_STORE_BF16_PLANE) ? sizeof(__nv_bfloat16) : 0)) +
+  return size_t(s->dim) * ((has_master(s) ? sizeof(float) : 0) + (has_plane(s) ? sizeof(__nv_bfloat16) : 0)) +
          sizeof(int32_t);
 }
 
 static int alloc_arrays(frg_store* s, int64_t cap, float** m, __nv_bfloat16** p, int32_t** t) {
   *m = nullptr; *p = nullptr; *t = nullptr;
   const int64_t c = cap > 0 ? cap : 1;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(m), size_t(c) * s->dim * sizeof(float));
-  if (e == cudaSuccess && (s->flags & FRG_STORE_BF16_PLANE))
+  cudaError_t e = cudaSuccess;
+  if (has_master(s)) e = cudaMalloc(reinterpret_cast<void**>(m), size_t(c) * s->dim * sizeof(float));
+  if (e == cudaSuccess && has_plane(s))
     e = cudaMalloc(reinterpret_cast<void**>(p), size_t(c) * s->dim * sizeof(__nv_bfloat16));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(t), size_t(c) * sizeof(int32_t));
   if (e != cudaSuccess) {
@@ -128,7 +132,7 @@ static int grow_locked(frg_store* s, int64_t cap) {
   float* m; __nv_bfloat16* p; int32_t* t;
   FRG_CHECK(alloc_arrays(s, cap, &m, &p, &t));
   if (s->rows > 0) {
-    FRG_CUDA(cudaMemcpy(m, s->master, size_t(s->rows) * s->dim * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (m) FRG_CUDA(cudaMemcpy(m, s->master, size_t(s->rows) * s->dim * sizeof(float), cudaMemcpyDeviceToDevice));
     if (p) FRG_CUDA(cudaMemcpy(p, s->plane, size_t(s->rows) * s->dim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
     FRG_CUDA(cudaMemcpy(t, s->tags, size_t(s->rows) * sizeof(int32_t), cudaMemcpyDeviceToDevice));
   }
@@ -215,6 +219,10 @@ int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t fla
   *out = nullptr;
   if (dim <= 0 || dim % 8 != 0) { set_error("dim %d must be a positive multiple of 8", dim); return FRG_ERR_INVALID; }
   if (capacity < 0) { set_error("negative capacity"); return FRG_ERR_INVALID; }
+  if ((flags & FRG_STORE_BF16_ONLY) && (flags & FRG_STORE_RAW)) {
+    set_error("a bf16-only store holds unit rows for the cosine filter; it cannot be raw");
+    return FRG_ERR_INVALID;
+  }
   DeviceInfo di;
   FRG_CHECK(device_info(device, &di));
   DeviceGuard g(device);
@@ -419,7 +427,17 @@ int frg_store_read_host(frg_store* s, int64_t row0, int64_t n, float* vecs, int3
   if (row0 + n > s->rows) { set_error("read_host: rows [%lld, %lld) beyond %lld", (long long)row0, (long long)(row0 + n), (long long)s->rows); return FRG_ERR_STATE; }
   FRG_CUDA(cudaDeviceSynchronize());
   if (n == 0) return FRG_OK;
-  if (vecs) FRG_CUDA(cudaMemcpy(vecs, s->master + row0 * s->dim, size_t(n) * s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+  if (vecs && s->master) {
+    FRG_CUDA(cudaMemcpy(vecs, s->master + row0 * s->dim, size_t(n) * s->dim * sizeof(float), cudaMemcpyDeviceToHost));
+  } else if (vecs) {
+    // bf16-only store: copy the plane and widen on the host (bf16 -> fp32 is exact)
+    std::vector<uint16_t> h(size_t(n) * s->dim);
+    FRG_CUDA(cudaMemcpy(h.data(), s->plane + row0 * s->dim, h.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) {
+      const uint32_t b = uint32_t(h[i]) << 16;
+      memcpy(vecs + i, &b, sizeof(float));
+    }
+  }
   if (tags) FRG_CUDA(cudaMemcpy(tags, s->tags + row0, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
   return FRG_OK;
 }
@@ -449,6 +467,7 @@ static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq)
   const bool unit = !(s->flags & FRG_STORE_RAW) && !(p->flags & FRG_QUERY_PRENORMALISED);
   const bool tc_ok = s->plane != nullptr && unit && tc_supported(s->dim, p->metric, &why);
   if (p->variant != FRG_VARIANT_AUTO) return p->variant;
+  if (!s->master) return FRG_VARIANT_TC_BF16;          // bf16-only store: the coarse scores are the scores
   // dispatch table: the tensor-core filter reads 2 B/element instead of 4 and wins from
   // the smallest batches on; the exact scan remains for galleries without a scan plane, for the
   // Euclidean metric and for dims the tile shapes do not cover.
@@ -458,6 +477,10 @@ static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq)
 
 static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, int sm_count,
                       int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+  if (!s->master && s->rows > 0) {
+    set_error("match: a bf16-only store has no fp32 master for the exact scan (use FRG_VARIANT_TC_BF16 / AUTO)");
+    return FRG_ERR_UNSUPPORTED;
+  }
   ScanArgs a;
   a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
   a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = sm_count;
@@ -488,6 +511,10 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   }
   if (s->rows > 0x7fffffff) { set_error("match: more than 2^31-1 rows in one shard"); return FRG_ERR_UNSUPPORTED; }
   if (s->rows == 0) return match_scan(s, q, nq, k, p, sm_count, out_rows, out_scores, out_accept, st);
+  if (rescore && !s->master) {
+    set_error("match: FRG_VARIANT_TC_EXACT needs the fp32 master; this store is bf16-only");
+    return FRG_ERR_UNSUPPORTED;
+  }
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
   const size_t qb_bytes = (size_t(nq) * s->dim * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
   const size_t tc_bytes = tc_workspace_bytes(s->rows, s->dim, nq, k, sm_count);
@@ -507,7 +534,7 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   if (rc == FRG_OK) {
     // queries whose candidate lists overflowed are redone exactly, inside the same enqueue
     ScanArgs a;
-    a.master = s->master; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
+    a.master = s->master; a.plane = s->plane; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
     a.qn = qn; a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = sm_count;
     profile_begin(st, kStageFallback);
     rc = launch_scan_f32_flagged(a, flagged, n_flagged, p->row_offset, p->threshold, out_rows, out_scores,
@@ -583,6 +610,7 @@ int frg_first_match(frg_store* s, const float* q, int32_t nq, const frg_match_pa
   reset_launches();
   if (!s || !p || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("first_match: bad argument"); return FRG_ERR_INVALID; }
   if (p->metric != FRG_METRIC_COSINE) { set_error("first_match: cosine / dot only"); return FRG_ERR_UNSUPPORTED; }
+  if (!s->master) { set_error("first_match: needs the fp32 master; this store is bf16-only"); return FRG_ERR_UNSUPPORTED; }
   if (nq == 0) return FRG_OK;
   DeviceGuard g(s->device);
   if (!g.ok) { set_error("cannot select device %d", s->device); return FRG_ERR_CUDA; }

@@ -100,7 +100,8 @@ int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, fl
 
 // scan_f32.cu: exact scan; writes nq x k best (score desc, row asc) into rows32/scores
 struct ScanArgs {
-  const float* master; const int32_t* tags; int64_t rows; int dim;
+  const float* master; const __nv_bfloat16* plane = nullptr;   // master == nullptr: bf16-only store, scan the plane
+  const int32_t* tags; int64_t rows; int dim;
   const float* qn; int nq; int k; int metric; int32_t tenant;
   int sm_count;
 };

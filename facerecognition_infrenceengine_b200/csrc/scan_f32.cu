@@ -24,6 +24,14 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return v;
 }
 
+// the same 4 elements per lane and 128-element chunk, from the bf16 scan plane (bf16-only stores)
+__device__ __forceinline__ float4 ldg_stream_bf16(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                     __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+
 // Reduce QB per-lane partial dots across the warp.  After the call, the returned value on lane L is
 // the full dot for query `lane_query<QB>(L)`, replicated on the 32/QB lanes that share it.
 template <int QB>
@@ -97,8 +105,9 @@ __device__ __forceinline__ void list_insert(float* sc, int32_t* ix, int K, float
 }
 
 // One pass over the gallery for the queries q_of[0..nq_pass): fills part_[sc|ix][(block*part_stride + part_q0 + b)*K ..].
-template <int NJ, int QB, int METRIC>
-__device__ __forceinline__ void scan_pass(const float* __restrict__ master, const int32_t* __restrict__ tags,
+// ROW = float: fp32 master rows.  ROW = __nv_bfloat16: rows of the bf16 scan plane, widened exactly.
+template <int NJ, int QB, int METRIC, typename ROW = float>
+__device__ __forceinline__ void scan_pass(const ROW* __restrict__ master, const int32_t* __restrict__ tags,
                                           int64_t rows, const float* __restrict__ qn, const int (&q_of)[QB],
                                           int nq_pass, int part_stride, int part_q0, int K, int32_t tenant,
                                           float* __restrict__ part_sc, int32_t* __restrict__ part_ix,
@@ -141,9 +150,15 @@ __device__ __forceinline__ void scan_pass(const float* __restrict__ master, cons
     for (int u = 0; u < R; ++u) {
       const int64_t r = rb + int64_t(u) * tw;
       const bool has = r < rows;
-      const float4* pr = reinterpret_cast<const float4*>(master + (has ? r : rb) * DIM) + lane;
+      if constexpr (sizeof(ROW) == 4) {
+        const float4* pr = reinterpret_cast<const float4*>(master + (has ? r : rb) * DIM) + lane;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) g[u][j] = ldg_stream(pr + j * 32);
+        for (int j = 0; j < NJ; ++j) g[u][j] = ldg_stream(pr + j * 32);
+      } else {
+        const uint2* pr = reinterpret_cast<const uint2*>(master + (has ? r : rb) * DIM) + lane;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) g[u][j] = ldg_stream_bf16(pr + j * 32);
+      }
       tg[u] = has ? __ldg(tags + r) : -1;
     }
 #pragma unroll
@@ -209,9 +224,9 @@ scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ ta
 // and its length live on the device; the kernel loops over it, so nothing waits for the host, and
 // the CTA that finishes last folds the per-CTA lists into the final results (ticket counter), so an
 // empty list costs ONE idle launch.  ctl[0] = number of flagged queries, ctl[1] = ticket (starts 0).
-template <int NJ, int QB, int METRIC, int KMAX>
+template <int NJ, int QB, int METRIC, int KMAX, typename ROW>
 __global__ void __launch_bounds__(kScanWarps * 32, 2)
-scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
+scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
                         const float* __restrict__ qn, int nq_total, const int* __restrict__ flagged,
                         int* __restrict__ ctl, int K, int32_t tenant, float threshold, int64_t row_offset,
                         float* __restrict__ part_sc, int32_t* __restrict__ part_ix,
@@ -227,8 +242,8 @@ scan_f32_flagged_kernel(const float* __restrict__ master, const int32_t* __restr
     int q_of[QB];
 #pragma unroll
     for (int b = 0; b < QB; ++b) q_of[b] = b < nq_pass ? flagged[q0 + b] : 0;
-    scan_pass<NJ, QB, METRIC>(master, tags, rows, qn, q_of, nq_pass, nq_total, q0, K, tenant, part_sc, part_ix,
-                              l_sc, l_ix);
+    scan_pass<NJ, QB, METRIC, ROW>(master, tags, rows, qn, q_of, nq_pass, nq_total, q0, K, tenant, part_sc,
+                                   part_ix, l_sc, l_ix);
     __syncthreads();
   }
   if (nf == 0) return;
@@ -334,10 +349,18 @@ static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int
                             int64_t row_offset, float* ps, int32_t* pi, int64_t* out_rows, float* out_scores,
                             uint8_t* out_accept, cudaStream_t st) {
   const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
-  auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX>;
-  FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
-                                            threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+  if (a.master) {
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float>;
+    FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
+                                              threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+  } else {
+    // bf16-only store: the exact re-do reads the scan plane (fp32 query x bf16 row, fp32 accumulation)
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, __nv_bfloat16>;
+    FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<grid, kScanWarps * 32, smem, st>>>(a.plane, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
+                                              threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+  }
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;

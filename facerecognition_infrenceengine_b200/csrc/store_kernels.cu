@@ -44,14 +44,14 @@ ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
       }
       inv_or_norm = __fsqrt_rn(warp_sum(ss));
     }
-    float4* m = reinterpret_cast<float4*>(master + dst * dim);
+    float4* m = master ? reinterpret_cast<float4*>(master + dst * dim) : nullptr;   // null: bf16-only store
     for (int v = lane; v < nvec; v += 32) {
       float4 x = __ldg(src + v);
       if (normalise) {
         x.x = __fdiv_rn(x.x, inv_or_norm); x.y = __fdiv_rn(x.y, inv_or_norm);
         x.z = __fdiv_rn(x.z, inv_or_norm); x.w = __fdiv_rn(x.w, inv_or_norm);
       }
-      m[v] = x;
+      if (m) m[v] = x;
       if (plane) store_bf16x4(plane + dst * dim + v * 4, x);
     }
     if (lane == 0) tag_out[dst] = tags ? tags[i] : 0;
@@ -78,9 +78,11 @@ gather_rows_kernel(const int64_t* __restrict__ src_rows, int64_t n, int dim,
   const int nvec = dim >> 2;
   for (int64_t i = warp; i < n; i += nwarps) {
     const int64_t s = src_rows[i];
-    const float4* mi = reinterpret_cast<const float4*>(master_in + s * dim);
-    float4* mo = reinterpret_cast<float4*>(master_out + i * dim);
-    for (int v = lane; v < nvec; v += 32) mo[v] = mi[v];
+    if (master_in) {
+      const float4* mi = reinterpret_cast<const float4*>(master_in + s * dim);
+      float4* mo = reinterpret_cast<float4*>(master_out + i * dim);
+      for (int v = lane; v < nvec; v += 32) mo[v] = mi[v];
+    }
     if (plane_in) {
       const uint2* pi = reinterpret_cast<const uint2*>(plane_in + s * dim);
       uint2* po = reinterpret_cast<uint2*>(plane_out + i * dim);
@@ -149,8 +151,10 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
         lo.z = __fdiv_rn(float(x[j][2]), norm); lo.w = __fdiv_rn(float(x[j][3]), norm);
         hi.x = __fdiv_rn(float(x[j][4]), norm); hi.y = __fdiv_rn(float(x[j][5]), norm);
         hi.z = __fdiv_rn(float(x[j][6]), norm); hi.w = __fdiv_rn(float(x[j][7]), norm);
-        float4* m = reinterpret_cast<float4*>(master + dst * dim + b * 8);
-        m[0] = lo; m[1] = hi;
+        if (master) {
+          float4* m = reinterpret_cast<float4*>(master + dst * dim + b * 8);
+          m[0] = lo; m[1] = hi;
+        }
         if (plane) {
           store_bf16x4(plane + dst * dim + b * 8, lo);
           store_bf16x4(plane + dst * dim + b * 8 + 4, hi);

@@ -58,6 +58,9 @@ extern "C" {
 /* frg_store_create flags */
 #define FRG_STORE_BF16_PLANE  1u /* keep the bf16 scan plane next to the fp32 master (needed by TC variants) */
 #define FRG_STORE_RAW         2u /* never normalise on ingest (Euclidean galleries) */
+#define FRG_STORE_BF16_ONLY   4u /* keep ONLY the bf16 scan plane (1 KB / 512-d row instead of 3 KB): "bf16 gallery
+                                   mode".  Matches run as FRG_VARIANT_TC_BF16 (scores within 4e-3 of fp32);
+                                   the exact variants, first_match and the Euclidean metric are not available. */
 
 /* upsert flags */
 #define FRG_ROWS_PRENORMALISED 1u /* store vectors as given (snapshot reload; exact-score fixtures) */

@@ -476,3 +476,57 @@ def test_full_size_1m_gallery(frg):
         assert (np.diff(r.scores, axis=1) <= 0).all()
         assert all(len(set(x)) == k for x in r.rows)
     store.close()
+
+
+def _bf16_round(a):
+    """numpy round-to-nearest-even fp32 -> bf16 -> fp32 (what the store keeps in bf16-only mode)."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return (((u + r) >> 16) << 16).astype(np.uint32).view(np.float32)
+
+
+def test_bf16_only_store(frg, tmp_path):
+    """FRG_STORE_BF16_ONLY: only the bf16 scan plane is resident (1 KB per 512-d row).  Scores are the
+    bf16 filter's: |delta| <= 4e-3 against the fp32 oracle; ids exact outside a 2 x 4e-3 band; the exact
+    variants are refused; overflowed queries are redone from the plane; snapshot / compaction work."""
+    n, d, f, k = 60000, 512, 70, 5
+    G = synth.gallery(n, d, 21)
+    G[np.arange(2000, 9000, 2)] = G[11]                       # 3500 duplicates: forces the overflow fallback
+    store = frg.GalleryStore(dim=d, capacity=n, bf16_only=True)
+    store.append_rows(G, prenormalised=True)
+    st = store.stats()
+    assert st.bytes == st.capacity * (d * 2 + 4)              # no fp32 master
+    Gd, _ = store.read_rows()
+    assert np.array_equal(Gd, _bf16_round(G))
+    Q, target = synth.queries(f, n, d, seed=9, gallery_seed=21)
+    Q[3] = G[11]
+    m = frg.Matcher(store)
+    r = m.match(Q, k, 0.45)
+    assert r.variant == "tc_bf16"
+    S = mo.cosine_scores(Q, G)
+    ref_rows, ref_scores = mo.topk_from_scores(S, k)
+    assert np.abs(r.scores - ref_scores).max() <= COARSE_EPS
+    for f_ in range(f):
+        true_of_returned = S[f_, r.rows[f_]]
+        assert (true_of_returned >= ref_scores[f_, k - 1] - 2 * COARSE_EPS).all()
+        must = ref_rows[f_][ref_scores[f_] > ref_scores[f_, k - 1] + 2 * COARSE_EPS]
+        assert set(must) <= set(r.rows[f_])
+    assert list(r.rows[3]) == sorted([11] + list(range(2000, 9000, 2)))[:k]     # exact ties -> lowest rows
+    hit = (target >= 0) & ~np.isin(target, np.arange(2000, 9000, 2))
+    assert (r.rows[hit, 0] == target[hit]).all()
+    for variant in ("scan_f32", "tc_exact"):
+        with pytest.raises(frg.NativeError):
+            m.match(Q, k, 0.45, variant=variant)
+    with pytest.raises(frg.NativeError):
+        m.first_above(Q[:1], 0.4)
+    # snapshot round trip and compaction keep working without a master
+    store.remove_rows([0, 1, 2])
+    store.compact()
+    assert store.stats().rows == n - 3
+    path = str(tmp_path / "bf16.frgsnap")
+    store.save(path)
+    again = frg.GalleryStore.load(path)                       # reloads as a full store from the widened rows
+    a, _ = again.read_rows()
+    b, _ = store.read_rows()
+    assert np.array_equal(a, b)
+    store.close(); again.close()
