@@ -530,7 +530,7 @@ def main():
     ap.add_argument("--sweep", default="1,8,64,128,256,512,1024")
     ap.add_argument("--bf16-only", action="store_true",
                     help="bf16 gallery mode: only the bf16 scan plane is resident (1 KB / row); scores within 4e-3")
-    ap.add_argument("--clock-preload-s", type=float, default=1.2,
+    ap.add_argument("--clock-preload-s", type=float, default=1.0,
                     help="seconds of untimed identical load before the timed region, for the clock sampler")
     ap.add_argument("--rows-total", type=int, default=0,
                     help="fixed total gallery, row-sharded over the ranks (BASELINE configs[3]: 100000000 with "
