@@ -105,8 +105,8 @@ static bool has_master(const frg_store* s) { return !(s->flags & FRG_STORE_BF16_
 static bool has_plane(const frg_store* s) { return (s->flags & (FRG_STORE_BF16_PLANE | FRG_STORE_BF16_ONLY)) != 0; }
 
 static size_t row_bytes(const frg_store* s) {
-  return size_t(s->dim) * ((has_master(s) ? sizeof(float) : 0) + (has_plane(s) ? sizeof(__nv_bfloat16) : 0)) +
-         sizeof(int32_t);
+  return size_t(s->dim) * (has_master(s) ? sizeof(float) : 0) +
+         size_t(s->plane_dim) * (has_plane(s) ? sizeof(__nv_bfloat16) : 0) + sizeof(int32_t);
 }
 
 static int alloc_arrays(frg_store* s, int64_t cap, float** m, __nv_bfloat16** p, int32_t** t) {
@@ -115,7 +115,7 @@ static int alloc_arrays(frg_store* s, int64_t cap, float** m, __nv_bfloat16** p,
   cudaError_t e = cudaSuccess;
   if (has_master(s)) e = cudaMalloc(reinterpret_cast<void**>(m), size_t(c) * s->dim * sizeof(float));
   if (e == cudaSuccess && has_plane(s))
-    e = cudaMalloc(reinterpret_cast<void**>(p), size_t(c) * s->dim * sizeof(__nv_bfloat16));
+    e = cudaMalloc(reinterpret_cast<void**>(p), size_t(c) * s->plane_dim * sizeof(__nv_bfloat16));
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(t), size_t(c) * sizeof(int32_t));
   if (e != cudaSuccess) {
     cudaFree(*m); cudaFree(*p); cudaFree(*t);
@@ -133,7 +133,7 @@ static int grow_locked(frg_store* s, int64_t cap) {
   FRG_CHECK(alloc_arrays(s, cap, &m, &p, &t));
   if (s->rows > 0) {
     if (m) FRG_CUDA(cudaMemcpy(m, s->master, size_t(s->rows) * s->dim * sizeof(float), cudaMemcpyDeviceToDevice));
-    if (p) FRG_CUDA(cudaMemcpy(p, s->plane, size_t(s->rows) * s->dim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+    if (p) FRG_CUDA(cudaMemcpy(p, s->plane, size_t(s->rows) * s->plane_dim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
     FRG_CUDA(cudaMemcpy(t, s->tags, size_t(s->rows) * sizeof(int32_t), cudaMemcpyDeviceToDevice));
   }
   cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
@@ -230,7 +230,20 @@ int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t fla
   frg_store* s = new (std::nothrow) frg_store();
   if (!s) { set_error("out of host memory"); return FRG_ERR_NOMEM; }
   s->device = device; s->dim = dim; s->flags = flags;
+  // a raw store's scan plane is the Euclidean one (norm terms in kEuclidPad more columns) where the
+  // tensor-core tile shapes cover it; other raw stores keep a plain image nobody scans
+  const char* why = "";
+  s->plane_dim = ((flags & FRG_STORE_RAW) && (flags & FRG_STORE_BF16_PLANE) && tc_supported(dim, FRG_METRIC_EUCLIDEAN, &why))
+                     ? dim + kEuclidPad : dim;
   int rc = alloc_arrays(s, capacity, &s->master, &s->plane, &s->tags);
+  if (rc == FRG_OK) {
+    cudaError_t eg = cudaMalloc(reinterpret_cast<void**>(&s->gmax_bits), sizeof(uint32_t));
+    if (eg == cudaSuccess) eg = cudaMemset(s->gmax_bits, 0, sizeof(uint32_t));
+    if (eg != cudaSuccess) {
+      cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
+      rc = cuda_fail(eg, "cudaMalloc(gmax)", __FILE__, __LINE__);
+    }
+  }
   if (rc != FRG_OK) { delete s; return rc; }
   s->capacity = capacity > 0 ? capacity : 1;
   cudaError_t e = cudaEventCreateWithFlags(&s->last_write, cudaEventDisableTiming);
@@ -250,7 +263,7 @@ int frg_store_destroy(frg_store* s) {
   {
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();
-    cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
+    cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
     if (s->last_write) cudaEventDestroy(s->last_write);
     ::operator delete(s->tmap_plane);
   }
@@ -287,7 +300,8 @@ static int upsert_impl(frg_store* s, const int64_t* rows, const float* vecs, con
   if (!rows && s->rows + n > s->capacity) FRG_CHECK(grow_locked(s, next_capacity(s->capacity, s->rows + n)));
   FRG_CHECK(store_begin_write(s, st));
   const bool normalise = !(flags & FRG_ROWS_PRENORMALISED) && !(s->flags & FRG_STORE_RAW);
-  FRG_CHECK(launch_ingest(vecs, rows, tags, n, s->rows, s->dim, normalise, s->master, s->plane, s->tags, st));
+  FRG_CHECK(launch_ingest(vecs, rows, tags, n, s->rows, s->dim, normalise, s->master, s->plane, s->plane_dim,
+                          s->gmax_bits, s->tags, st));
   if (!rows) s->rows += n;
   s->live = -1;
   if (tags && tags_may_be_negative) s->maybe_dead = true;
@@ -404,7 +418,7 @@ int frg_store_compact(frg_store* s, int64_t* old_to_new) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dsrc), size_t(m) * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMemcpy(dsrc, src.data(), size_t(m) * sizeof(int64_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = cuda_fail(e, "compact staging", __FILE__, __LINE__);
-    if (rc == FRG_OK) rc = launch_gather_rows(dsrc, m, s->dim, s->master, s->plane, s->tags, nm, np, nt, nullptr);
+    if (rc == FRG_OK) rc = launch_gather_rows(dsrc, m, s->dim, s->plane_dim, s->master, s->plane, s->tags, nm, np, nt, nullptr);
     if (rc == FRG_OK) {
       e = cudaDeviceSynchronize();
       if (e != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
@@ -452,7 +466,8 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
   std::lock_guard<std::mutex> lk(s->mu);
   if (s->rows + n > s->capacity) FRG_CHECK(grow_locked(s, s->rows + n));
   FRG_CHECK(store_begin_write(s, st));
-  FRG_CHECK(launch_synth(n, s->rows, global_row0, seed, tag, s->dim, s->master, s->plane, s->tags, st));
+  FRG_CHECK(launch_synth(n, s->rows, global_row0, seed, tag, s->dim, s->master, s->plane, s->plane_dim,
+                         s->gmax_bits, s->tags, st));
   s->rows += n;
   if (s->live >= 0 && tag >= 0) s->live += n;
   if (tag < 0) s->maybe_dead = true;
@@ -462,10 +477,13 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
 // --------------------------------------------------------------------------------------------- match
 static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq) {
   const char* why = "";
-  // The filter's error bound assumes unit-norm rows and queries: raw stores (Euclidean galleries,
-  // cluster means) and caller-normalised queries always take the exact scan.
+  // Raw stores queried with the cosine metric (cluster means) and caller-normalised queries always
+  // take the exact scan.
+  // Cosine filter: its error bound assumes unit rows and queries.  Euclidean filter: needs the raw
+  // store's augmented plane (norm terms), its bound scales with the norms (queries.cu).
   const bool unit = !(s->flags & FRG_STORE_RAW) && !(p->flags & FRG_QUERY_PRENORMALISED);
-  const bool tc_ok = s->plane != nullptr && unit && tc_supported(s->dim, p->metric, &why);
+  const bool fits = p->metric == FRG_METRIC_EUCLIDEAN ? s->plane_dim == s->dim + kEuclidPad : unit;
+  const bool tc_ok = s->plane != nullptr && fits && tc_supported(s->dim, p->metric, &why);
   if (p->variant != FRG_VARIANT_AUTO) return p->variant;
   if (!s->master) return FRG_VARIANT_TC_BF16;          // bf16-only store: the coarse scores are the scores
   // dispatch table: the tensor-core filter reads 2 B/element instead of 4 and wins from
@@ -503,10 +521,20 @@ static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_mat
 static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, bool rescore,
                     int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
   const char* why = "";
+  const bool euclid = p->metric == FRG_METRIC_EUCLIDEAN;
   if (!s->plane) { set_error("match: the store was created without FRG_STORE_BF16_PLANE"); return FRG_ERR_UNSUPPORTED; }
   if (!tc_supported(s->dim, p->metric, &why)) { set_error("match: %s", why); return FRG_ERR_UNSUPPORTED; }
-  if ((s->flags & FRG_STORE_RAW) || (p->flags & FRG_QUERY_PRENORMALISED)) {
-    set_error("match: tensor-core variants need unit-norm rows and queries (raw store / prenormalised query given)");
+  if (euclid) {
+    if (s->plane_dim != s->dim + kEuclidPad) {
+      set_error("match: the Euclidean tensor-core filter needs a FRG_STORE_RAW store with a scan plane");
+      return FRG_ERR_UNSUPPORTED;
+    }
+    if (!rescore) {
+      set_error("match: FRG_VARIANT_TC_BF16 is cosine-only (a distance from the bf16 score would cancel near d = 0)");
+      return FRG_ERR_UNSUPPORTED;
+    }
+  } else if ((s->flags & FRG_STORE_RAW) || (p->flags & FRG_QUERY_PRENORMALISED)) {
+    set_error("match: the cosine tensor-core variants need unit-norm rows and queries (raw store / prenormalised query given)");
     return FRG_ERR_UNSUPPORTED;
   }
   if (s->rows > 0x7fffffff) { set_error("match: more than 2^31-1 rows in one shard"); return FRG_ERR_UNSUPPORTED; }
@@ -516,20 +544,25 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
     return FRG_ERR_UNSUPPORTED;
   }
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
-  const size_t qb_bytes = (size_t(nq) * s->dim * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
+  const size_t qb_bytes = (size_t(nq) * s->plane_dim * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
+  const size_t eps_bytes = euclid ? ((size_t(nq) * sizeof(float) + 255) & ~size_t(255)) : 0;
   const size_t tc_bytes = tc_workspace_bytes(s->rows, s->dim, nq, k, sm_count);
   unsigned char* ws = nullptr;
-  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + tc_bytes, st));
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + eps_bytes + tc_bytes, st));
   float* qn = reinterpret_cast<float*>(ws);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes);
+  float* eps = euclid ? reinterpret_cast<float*>(ws + qn_bytes + qb_bytes) : nullptr;
+  unsigned char* tc_ws = ws + qn_bytes + qb_bytes + eps_bytes;
   int* flagged = nullptr; int* n_flagged = nullptr;
   uint32_t* keys = nullptr; int* ct0 = nullptr; int* nf0 = nullptr;
-  tc_workspace_init_targets(s->rows, s->dim, nq, k, sm_count, ws + qn_bytes + qb_bytes, &keys, &ct0, &nf0);
+  tc_workspace_init_targets(s->rows, s->dim, nq, k, sm_count, tc_ws, &keys, &ct0, &nf0);
   profile_begin(st, kStagePrep);
-  int rc = launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, qb, keys, ct0, nf0, st);
+  int rc = euclid ? launch_prepare_queries_euclid(q, nq, s->dim, s->gmax_bits, qn, qb, eps, keys, ct0, nf0, st)
+                  : launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, qb, keys, ct0,
+                                             nf0, st);
   profile_end(st, 1);
   if (rc == FRG_OK)
-    rc = launch_tc_match(s, qn, qb, nq, k, p->tenant, rescore, p->threshold, p->row_offset, ws + qn_bytes + qb_bytes,
+    rc = launch_tc_match(s, p->metric, qn, qb, eps, nq, k, p->tenant, rescore, p->threshold, p->row_offset, tc_ws,
                          sm_count, out_rows, out_scores, out_accept, &flagged, &n_flagged, st);
   if (rc == FRG_OK) {
     // queries whose candidate lists overflowed are redone exactly, inside the same enqueue

@@ -72,7 +72,12 @@ struct frg_store {
   int64_t version = 0;
   bool maybe_dead = false;            // a row was tombstoned since the last compaction (or tag -1 was upserted)
   float* master = nullptr;            // [capacity][dim] fp32, unit rows
-  __nv_bfloat16* plane = nullptr;     // [capacity][dim] bf16 image (scan plane) or null
+  __nv_bfloat16* plane = nullptr;     // [capacity][plane_dim] bf16 image (scan plane) or null
+  // plane_dim == dim for unit-row stores.  A FRG_STORE_RAW store's plane is the EUCLIDEAN scan plane:
+  // plane_dim = dim + 64, columns dim..dim+2 hold -0.5*||g||^2 split exactly into three bf16 terms
+  // (the rest 0), so that Qaug . Gaug = q.g - 0.5*||g||^2 with Qaug = [q, 1, 1, 1, 0...] (tc_match.cu)
+  int plane_dim = 0;
+  uint32_t* gmax_bits = nullptr;      // device scalar: float bits of max ||g||^2 ever ingested (raw stores)
   int32_t* tags = nullptr;            // [capacity]
   std::mutex mu;                      // guards the fields above and the stream bookkeeping
   cudaEvent_t last_write = nullptr;   // recorded after every mutation
@@ -97,6 +102,11 @@ int store_begin_read(frg_store* s, cudaStream_t stream);
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
                              __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* cand_total, int* n_flagged,
                              cudaStream_t st);
+// queries.cu: Euclidean tensor-core prep: qn = q as given, bf16 image [nq][dim + 64] = [q, 1, 1, 1, 0...],
+// eps[f] = filter error bound of query f from ||q|| and the store's max row norm
+int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_t* gmax_bits, float* qn,
+                                  __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
+                                  int* n_flagged, cudaStream_t st);
 
 // scan_f32.cu: exact scan; writes nq x k best (score desc, row asc) into rows32/scores
 struct ScanArgs {
@@ -125,15 +135,20 @@ int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
-// tc_match.cu: tcgen05 filter + exact rescoring (cosine, dim multiple of 64 and <= 512)
+// tc_match.cu: tcgen05 filter + exact rescoring.  Cosine: dim multiple of 64 and <= 512 (unit rows);
+// Euclidean: dim multiple of 64 and <= 448 over a raw store's augmented plane (plane_dim = dim + 64).
+constexpr int kEuclidPad = 64;      // one more 128-byte swizzle row of k for the three bias columns
+constexpr float kEuclidNone = -3.0e38f;   // "no score yet" of the Euclidean filter (scores are unbounded below)
 int tc_supported(int dim, int metric, const char** why);
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count);
 void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_count, unsigned char* ws,
                                uint32_t** keys, int** cand_total, int** n_flagged);
-int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
-                    bool rescore, float threshold, int64_t row_offset, unsigned char* ws, int sm_count,
-                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,
-                    int** n_flagged_out, cudaStream_t st);
+// metric cosine: qb = [nq][dim] bf16 unit queries, eps == nullptr (constant bound).
+// metric euclidean: qb = [nq][dim + 64] augmented image, eps[nq] per-query bounds.
+int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
+                    int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
+                    unsigned char* ws, int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
+                    int** flagged_out, int** n_flagged_out, cudaStream_t st);
 
 // first_match.cu
 int launch_first_match(const float* master, const int32_t* tags, int64_t rows, int dim, const float* qn, int nq,
@@ -141,13 +156,15 @@ int launch_first_match(const float* master, const int32_t* tags, int64_t rows, i
                        int sm_count, int64_t* out_rows, float* out_scores, cudaStream_t st);
 
 // store_kernels.cu
+// plane_dim > dim: Euclidean scan plane (bias columns written, gmax_bits folded); else plane_dim == dim
 int launch_ingest(const float* vecs, const int64_t* rows, const int32_t* tags, int64_t n, int64_t append_at,
-                  int dim, bool normalise, float* master, __nv_bfloat16* plane, int32_t* tag_out,
-                  cudaStream_t st);
+                  int dim, bool normalise, float* master, __nv_bfloat16* plane, int plane_dim, uint32_t* gmax_bits,
+                  int32_t* tag_out, cudaStream_t st);
 int launch_tombstone(const int64_t* rows, int64_t n, int64_t limit, int32_t* tags, cudaStream_t st);
 int launch_synth(int64_t n, int64_t append_at, int64_t global_row0, uint64_t seed, int32_t tag, int dim,
-                 float* master, __nv_bfloat16* plane, int32_t* tag_out, cudaStream_t st);
-int launch_gather_rows(const int64_t* src_rows, int64_t n, int dim, const float* master_in,
+                 float* master, __nv_bfloat16* plane, int plane_dim, uint32_t* gmax_bits, int32_t* tag_out,
+                 cudaStream_t st);
+int launch_gather_rows(const int64_t* src_rows, int64_t n, int dim, int plane_dim, const float* master_in,
                        const __nv_bfloat16* plane_in, const int32_t* tags_in, float* master_out,
                        __nv_bfloat16* plane_out, int32_t* tags_out, cudaStream_t st);
 

@@ -2,6 +2,8 @@
 // (`face.normed_embedding / np.linalg.norm(face.normed_embedding)`, infrenceServer.py:532,
 // peopleCount.py:863).  One warp per query; writes the fp32 unit query and, for the tensor-core
 // variants, its bf16 image.
+#include <cstring>
+
 #include "frg_internal.cuh"
 
 namespace frg {
@@ -48,6 +50,69 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
       reinterpret_cast<uint2*>(qb + size_t(w) * dim)[v] = p;
     }
   }
+}
+
+// Euclidean tensor-core prep (BASELINE config 3; ours, not in the reference).  The query is used as
+// given; its bf16 image gets kEuclidPad more columns [1, 1, 1, 0 ...] that pick up the three bias terms of
+// the Euclidean scan plane, so that the tensor-core score is S = q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2:
+// largest S <=> smallest distance.  eps[w] bounds |S - exact| for every row of the store:
+//   bf16 rounding of both operands  (2u + u^2) ||q|| ||g||,  u = 2^-9   ->  < 3.92e-3 ||q|| Gmax
+//   fp32 bias / accumulation          O(dim * 2^-24) (||q|| ||g|| + ||g||^2 / 2)
+// taken as 4e-3 * ||q|| * Gmax + 1e-4 * Gmax^2 (the cosine filter's 4e-3 for unit vectors, plus the bias term).
+__global__ void __launch_bounds__(128)
+prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, const uint32_t* __restrict__ gmax_bits,
+                              float* __restrict__ qn, __nv_bfloat16* __restrict__ q_aug, float* __restrict__ eps,
+                              uint32_t* __restrict__ group_keys, uint32_t none_key, int* __restrict__ cand_total,
+                              int* __restrict__ n_flagged) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nq) return;
+  if (group_keys) group_keys[size_t(w) * 32 + lane] = none_key;
+  if (cand_total && lane == 0) cand_total[w] = 0;
+  if (n_flagged && w == 0 && lane < 3) n_flagged[lane] = 0;
+  const float4* src = reinterpret_cast<const float4*>(q + size_t(w) * dim);
+  const int nvec = dim >> 2;
+  const int aug = dim + kEuclidPad;
+  float ss = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    const float4 x = __ldg(src + v);
+    ss = fmaf(x.x, x.x, ss); ss = fmaf(x.y, x.y, ss); ss = fmaf(x.z, x.z, ss); ss = fmaf(x.w, x.w, ss);
+    reinterpret_cast<float4*>(qn + size_t(w) * dim)[v] = x;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(x.z, x.w);
+    uint2 p;
+    p.x = *reinterpret_cast<uint32_t*>(&lo);
+    p.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(q_aug + size_t(w) * aug)[v] = p;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane < kEuclidPad / 4) {
+    // bf16(1.0) = 0x3F80
+    const uint2 ones = lane == 0 ? make_uint2(0x3F803F80u, 0x00003F80u) : make_uint2(0u, 0u);
+    reinterpret_cast<uint2*>(q_aug + size_t(w) * aug + dim)[lane] = ones;
+  }
+  if (lane == 0) {
+    const float g2 = __uint_as_float(*gmax_bits);
+    eps[w] = 4e-3f * __fsqrt_rn(ss) * __fsqrt_rn(g2) + 1e-4f * g2;
+  }
+}
+
+int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_t* gmax_bits, float* qn,
+                                  __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
+                                  int* n_flagged, cudaStream_t st) {
+  if (nq <= 0) return FRG_OK;
+  FRG_CUDA(cudaFuncSetAttribute(prepare_queries_euclid_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  // group maxima start from "nothing seen" = the ordered key of -3e38 (Euclidean scores are unbounded below)
+  uint32_t none_bits;
+  const float none = kEuclidNone;
+  memcpy(&none_bits, &none, sizeof(none_bits));
+  const uint32_t none_key = ~none_bits;        // float_key() of a negative value: all bits complemented
+  prepare_queries_euclid_kernel<<<(nq + 3) / 4, 128, 0, st>>>(q, nq, dim, gmax_bits, qn, q_aug, eps, group_keys,
+                                                               none_key, cand_total, n_flagged);
+  note_launch(nullptr);
+  FRG_CUDA(cudaGetLastError());
+  return FRG_OK;
 }
 
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,

@@ -254,8 +254,8 @@ scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restric
   if (!is_last) return;
   __threadfence();
   for (int slot = threadIdx.x >> 5; slot < nf; slot += kScanWarps)
-    merge_one<int32_t, KMAX>(part_sc, part_ix, int(gridDim.x), nq_total, K, K, METRIC, threshold, row_offset, 0,
-                             slot, flagged[slot], int64_t(nq_total) * K, int64_t(nq_total) * K, out_rows, out_scores,
+    merge_one<int32_t, KMAX>(part_sc, part_ix, int(gridDim.x), nq_total, K, K, METRIC, threshold, row_offset,
+                             /*internal_euclid=*/METRIC == FRG_METRIC_EUCLIDEAN ? 1 : 0, slot, flagged[slot], int64_t(nq_total) * K, int64_t(nq_total) * K, out_rows, out_scores,
                              out_accept);
 }
 
@@ -349,7 +349,12 @@ static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int
                             int64_t row_offset, float* ps, int32_t* pi, int64_t* out_rows, float* out_scores,
                             uint8_t* out_accept, cudaStream_t st) {
   const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
-  if (a.master) {
+  if (a.master && a.metric == FRG_METRIC_EUCLIDEAN) {
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_EUCLIDEAN, KMAX, float>;
+    FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
+                                              threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+  } else if (a.master) {
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float>;
     FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,

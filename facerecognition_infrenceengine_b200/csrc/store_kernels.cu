@@ -20,13 +20,36 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
   *reinterpret_cast<uint2*>(dst) = packed;
 }
 
+// Euclidean scan plane (raw stores): columns dim .. dim+63 of the row = [hi, mid, lo, 0 ...], the exact
+// three-term bf16 split of c = -0.5 * ||g||^2 (24 significand bits = 3 x 8), so that the tensor-core
+// product with a query image [q, 1, 1, 1, 0 ...] accumulates q.g - 0.5*||g||^2.  The largest ||g||^2
+// ever stored is folded into *gmax_bits (non-negative floats order like their bit patterns); it scales
+// the filter's error bound.  Non-finite norms are left out: such rows can never match either way.
+__device__ __forceinline__ void store_bias_columns(__nv_bfloat16* row_aug, float ss, uint32_t* gmax_bits, int lane) {
+  if (lane < 16) {
+    uint2 packed = make_uint2(0u, 0u);
+    if (lane == 0) {
+      const float c = -0.5f * ss;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(c);
+      const float r1 = c - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(mid);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+      packed.x = uint32_t(__bfloat16_as_ushort(hi)) | (uint32_t(__bfloat16_as_ushort(mid)) << 16);
+      packed.y = uint32_t(__bfloat16_as_ushort(lo));
+      if (gmax_bits && ss < INFINITY) atomicMax(gmax_bits, __float_as_uint(ss));
+    }
+    reinterpret_cast<uint2*>(row_aug)[lane] = packed;
+  }
+}
+
 // `embedding / np.linalg.norm(embedding)` at load time: infrenceServer.py:271,324; peopleCount.py:788,806.
 // norm = sqrt(sum x^2) in fp32 (numpy's sdot-based norm; summation order differs by a few ulp).
 __global__ void __launch_bounds__(256)
 ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
               const int32_t* __restrict__ tags, int64_t n, int64_t append_at, int64_t limit, int dim,
-              int normalise, float* __restrict__ master, __nv_bfloat16* __restrict__ plane,
-              int32_t* __restrict__ tag_out) {
+              int normalise, float* __restrict__ master, __nv_bfloat16* __restrict__ plane, int plane_dim,
+              uint32_t* __restrict__ gmax_bits, int32_t* __restrict__ tag_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -45,15 +68,19 @@ ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
       inv_or_norm = __fsqrt_rn(warp_sum(ss));
     }
     float4* m = master ? reinterpret_cast<float4*>(master + dst * dim) : nullptr;   // null: bf16-only store
+    float ss_stored = 0.f;                    // ||stored row||^2, for the Euclidean plane's bias columns
     for (int v = lane; v < nvec; v += 32) {
       float4 x = __ldg(src + v);
       if (normalise) {
         x.x = __fdiv_rn(x.x, inv_or_norm); x.y = __fdiv_rn(x.y, inv_or_norm);
         x.z = __fdiv_rn(x.z, inv_or_norm); x.w = __fdiv_rn(x.w, inv_or_norm);
       }
+      ss_stored = fmaf(x.x, x.x, ss_stored); ss_stored = fmaf(x.y, x.y, ss_stored);
+      ss_stored = fmaf(x.z, x.z, ss_stored); ss_stored = fmaf(x.w, x.w, ss_stored);
       if (m) m[v] = x;
-      if (plane) store_bf16x4(plane + dst * dim + v * 4, x);
+      if (plane) store_bf16x4(plane + dst * plane_dim + v * 4, x);
     }
+    if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), gmax_bits, lane);
     if (lane == 0) tag_out[dst] = tags ? tags[i] : 0;
   }
 }
@@ -68,7 +95,7 @@ __global__ void tombstone_kernel(const int64_t* __restrict__ rows, int64_t n, in
 }
 
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(const int64_t* __restrict__ src_rows, int64_t n, int dim,
+gather_rows_kernel(const int64_t* __restrict__ src_rows, int64_t n, int dim, int plane_dim,
                    const float* __restrict__ master_in, const __nv_bfloat16* __restrict__ plane_in,
                    const int32_t* __restrict__ tags_in, float* __restrict__ master_out,
                    __nv_bfloat16* __restrict__ plane_out, int32_t* __restrict__ tags_out) {
@@ -84,9 +111,9 @@ gather_rows_kernel(const int64_t* __restrict__ src_rows, int64_t n, int dim,
       for (int v = lane; v < nvec; v += 32) mo[v] = mi[v];
     }
     if (plane_in) {
-      const uint2* pi = reinterpret_cast<const uint2*>(plane_in + s * dim);
-      uint2* po = reinterpret_cast<uint2*>(plane_out + i * dim);
-      for (int v = lane; v < nvec; v += 32) po[v] = pi[v];
+      const uint2* pi = reinterpret_cast<const uint2*>(plane_in + s * plane_dim);
+      uint2* po = reinterpret_cast<uint2*>(plane_out + i * plane_dim);
+      for (int v = lane; v < (plane_dim >> 2); v += 32) po[v] = pi[v];
     }
     if (lane == 0) tags_out[i] = tags_in[s];
   }
@@ -114,8 +141,8 @@ __device__ __forceinline__ int nibble_sum(uint32_t h) {
 // for dim <= 1024).  sum(x^2) is an exact integer, so norm and quotients are bit-identical to numpy.
 __global__ void __launch_bounds__(256)
 synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uint32_t k1, int32_t tag,
-             int dim, float* __restrict__ master, __nv_bfloat16* __restrict__ plane,
-             int32_t* __restrict__ tag_out) {
+             int dim, float* __restrict__ master, __nv_bfloat16* __restrict__ plane, int plane_dim,
+             uint32_t* __restrict__ gmax_bits, int32_t* __restrict__ tag_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -142,6 +169,7 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float norm = __fsqrt_rn(float(ss));
+    float ss_stored = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int b = lane + 32 * j;
@@ -156,11 +184,16 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
           m[0] = lo; m[1] = hi;
         }
         if (plane) {
-          store_bf16x4(plane + dst * dim + b * 8, lo);
-          store_bf16x4(plane + dst * dim + b * 8 + 4, hi);
+          store_bf16x4(plane + dst * plane_dim + b * 8, lo);
+          store_bf16x4(plane + dst * plane_dim + b * 8 + 4, hi);
         }
+        ss_stored = fmaf(lo.x, lo.x, ss_stored); ss_stored = fmaf(lo.y, lo.y, ss_stored);
+        ss_stored = fmaf(lo.z, lo.z, ss_stored); ss_stored = fmaf(lo.w, lo.w, ss_stored);
+        ss_stored = fmaf(hi.x, hi.x, ss_stored); ss_stored = fmaf(hi.y, hi.y, ss_stored);
+        ss_stored = fmaf(hi.z, hi.z, ss_stored); ss_stored = fmaf(hi.w, hi.w, ss_stored);
       }
     }
+    if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), gmax_bits, lane);
     if (lane == 0) tag_out[dst] = tag;
   }
 }
@@ -173,13 +206,14 @@ static int grid_for_rows(int64_t n, int warps_per_block) {
 }
 
 int launch_ingest(const float* vecs, const int64_t* rows, const int32_t* tags, int64_t n, int64_t append_at,
-                  int dim, bool normalise, float* master, __nv_bfloat16* plane, int32_t* tag_out,
-                  cudaStream_t st) {
+                  int dim, bool normalise, float* master, __nv_bfloat16* plane, int plane_dim, uint32_t* gmax_bits,
+                  int32_t* tag_out, cudaStream_t st) {
   if (n <= 0) return FRG_OK;
   // limit: appended rows land below append_at + n, in-place rows below append_at
   const int64_t limit = rows ? append_at : append_at + n;
   ingest_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(vecs, rows, tags, n, append_at, limit, dim,
-                                                     normalise ? 1 : 0, master, plane, tag_out);
+                                                     normalise ? 1 : 0, master, plane, plane_dim, gmax_bits,
+                                                     tag_out);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;
@@ -194,20 +228,22 @@ int launch_tombstone(const int64_t* rows, int64_t n, int64_t limit, int32_t* tag
 }
 
 int launch_synth(int64_t n, int64_t append_at, int64_t global_row0, uint64_t seed, int32_t tag, int dim,
-                 float* master, __nv_bfloat16* plane, int32_t* tag_out, cudaStream_t st) {
+                 float* master, __nv_bfloat16* plane, int plane_dim, uint32_t* gmax_bits, int32_t* tag_out,
+                 cudaStream_t st) {
   if (n <= 0) return FRG_OK;
   synth_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(n, append_at, global_row0, uint32_t(seed),
-                                                    uint32_t(seed >> 32), tag, dim, master, plane, tag_out);
+                                                    uint32_t(seed >> 32), tag, dim, master, plane, plane_dim,
+                                                    gmax_bits, tag_out);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;
 }
 
-int launch_gather_rows(const int64_t* src_rows, int64_t n, int dim, const float* master_in,
+int launch_gather_rows(const int64_t* src_rows, int64_t n, int dim, int plane_dim, const float* master_in,
                        const __nv_bfloat16* plane_in, const int32_t* tags_in, float* master_out,
                        __nv_bfloat16* plane_out, int32_t* tags_out, cudaStream_t st) {
   if (n <= 0) return FRG_OK;
-  gather_rows_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(src_rows, n, dim, master_in, plane_in, tags_in,
+  gather_rows_kernel<<<grid_for_rows(n, 8), 256, 0, st>>>(src_rows, n, dim, plane_dim, master_in, plane_in, tags_in,
                                                           master_out, plane_out, tags_out);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());

@@ -242,6 +242,10 @@ struct TcScanParams {
   int* cand_total;         // [nq] candidates of the query over all chunks (atomicAdd at the CTA's end)
   int2* dense;             // [nq][dense_cap]: the segments, packed per query for the select kernel
   int dense_cap;
+  // error bound of the filter: eps == nullptr -> kCoarseEps for every query (unit vectors, cosine);
+  // else eps[q] (Euclidean plane: scales with ||q|| and the store's largest row norm)
+  const float* eps;
+  float none_score;        // "nothing seen": kNoScore (cosine, scores > -1) or kEuclidNone
 };
 
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
@@ -425,7 +429,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         }
         g[j] = key_float(x.x); g[j + 1] = key_float(x.y); g[j + 2] = key_float(x.z); g[j + 3] = key_float(x.w);
       }
-      float floor_v = kNoScore;
+      float floor_v = p.none_score;
       for (int r = 0; r < p.k; ++r) {
         float m = g[0];
 #pragma unroll
@@ -441,11 +445,12 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       }
       // fewer than k usable groups so far: no bound, every valid row is a candidate
       // (finite, so that masked columns, which are set to -inf, still fail the comparison)
-      return (floor_v <= kNoScore) ? -3.0e38f : floor_v - 2.0f * kCoarseEps;
+      const float eps_q = p.eps ? __ldg(p.eps + q) : kCoarseEps;
+      return (floor_v <= p.none_score) ? -3.0e38f : floor_v - 2.0f * eps_q;
     };
     if (MODE != kModeFilter) {
 #pragma unroll
-      for (int j = 0; j < kGroups; ++j) gmax[j] = kNoScore;
+      for (int j = 0; j < kGroups; ++j) gmax[j] = p.none_score;
     }
     if (MODE != kModeGroupMax && q_real) {
       if (MODE == kModeFilter) thr = derive_thr();
@@ -542,7 +547,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
             uint32_t* o = p.group_key + size_t(q) * kGroups + half * 16;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (gmax[j] > kNoScore) atomicMax(o + j, float_key(gmax[j]));
+              if (gmax[j] > p.none_score) atomicMax(o + j, float_key(gmax[j]));
           }
           __threadfence();
           asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // the epilogue warps only
@@ -566,14 +571,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         uint32_t* o = p.group_key + size_t(q) * kGroups;
 #pragma unroll
         for (int j = 0; j < kGroups; ++j)
-          if (gmax[j] > kNoScore) atomicMax(o + j, float_key(gmax[j]));
+          if (gmax[j] > p.none_score) atomicMax(o + j, float_key(gmax[j]));
       } else {
         // pack this thread's few candidates into the query's dense list: one atomicAdd per (query, CTA),
-        // outside the scan loop.  A private-segment overflow poisons the total so that select flags it.
-        const int base = atomicAdd(p.cand_total + q, emitted > p.seg ? (1 << 24) : emitted);
+        // outside the scan loop.  A private-segment overflow poisons the total so that select flags it
+        // (2^20 > any dense_cap; a query has at most 2 * 148 segments, so the sum of poisons cannot wrap).
+        const int base = atomicAdd(p.cand_total + q, emitted > p.seg ? (1 << 20) : emitted);
         const int mine_n = emitted < p.seg ? emitted : p.seg;
         for (int i = 0; i < mine_n; ++i)
-          if (base + i < p.dense_cap) p.dense[size_t(q) * p.dense_cap + base + i] = my_seg[i];
+          if (unsigned(base + i) < unsigned(p.dense_cap)) p.dense[size_t(q) * p.dense_cap + base + i] = my_seg[i];
       }
     }
   }
@@ -631,10 +637,14 @@ constexpr int kSelectWarps = 4;
 // The dense candidate list of a query (a few hundred entries, L2-resident: the filter kernel has just
 // written it) is read twice straight from global memory - no shared-memory staging, so every query's
 // warp is resident at once and the DRAM/L2 latencies of different queries overlap.
-template <int K>
+// EUCLID: the coarse scores are S = q.g - 0.5*||g||^2 (larger = nearer); the kept rows are rescored as the
+// exact direct-difference d^2 = sum (g - q)^2 (the streaming scan's arithmetic and order), ranked by
+// (-d^2 desc, row asc) and reported as distances; accept iff d <= threshold.
+template <int K, bool EUCLID>
 __global__ void __launch_bounds__(kSelectWarps * 32)
 select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ cand_total,
                       int dense_cap, int nq, int k, int dim, const float* __restrict__ qn,
+                      const float* __restrict__ eps,
                       const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
                       uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged) {
@@ -690,7 +700,7 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   }
 
   // (b) compact the rows that can still be in the true top-k
-  const float keep_thr = tau - 2.0f * kCoarseEps;
+  const float keep_thr = tau - 2.0f * (eps ? __ldg(eps + q) : kCoarseEps);
   int m = 0;
   for (int c0 = 0; c0 < n; c0 += 128) {             // 4 independent loads per lane per round
     int2 e[4];
@@ -732,34 +742,47 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
       for (int u = 0; u < kRescoreRows; ++u) x[u] = __ldg(g[u] + v);
 #pragma unroll
       for (int u = 0; u < kRescoreRows; ++u) {
-        a[u] = fmaf(x[u].x, y.x, a[u]); a[u] = fmaf(x[u].y, y.y, a[u]);
-        a[u] = fmaf(x[u].z, y.z, a[u]); a[u] = fmaf(x[u].w, y.w, a[u]);
+        if (EUCLID) {
+          float d;
+          d = x[u].x - y.x; a[u] = fmaf(d, d, a[u]); d = x[u].y - y.y; a[u] = fmaf(d, d, a[u]);
+          d = x[u].z - y.z; a[u] = fmaf(d, d, a[u]); d = x[u].w - y.w; a[u] = fmaf(d, d, a[u]);
+        } else {
+          a[u] = fmaf(x[u].x, y.x, a[u]); a[u] = fmaf(x[u].y, y.y, a[u]);
+          a[u] = fmaf(x[u].z, y.z, a[u]); a[u] = fmaf(x[u].w, y.w, a[u]);
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < kRescoreRows; ++u) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
-      if (lane == 0 && i0 + u < m) keep_sc[w][i0 + u] = a[u];
+      if (lane == 0 && i0 + u < m) keep_sc[w][i0 + u] = EUCLID ? -a[u] : a[u];
     }
   }
   __syncwarp();
 
   // (d) final order (score desc, row asc) over the m exact scores; lane-local lists + warp merge
+  const float sentinel = EUCLID ? -INFINITY : kNoScore;     // the exact scan's initial best
 #pragma unroll
-  for (int j = 0; j < K; ++j) { sc[j] = kNoScore; ix[j] = 0x7fffffff; }
+  for (int j = 0; j < K; ++j) { sc[j] = sentinel; ix[j] = 0x7fffffff; }
   for (int c = lane; c < m; c += 32) {
     const float s = keep_sc[w][c];
-    if (s > kNoScore) lane_insert<K>(sc, ix, s, keep_row[w][c]);   // scores <= -1 and NaN never match
+    if (s > sentinel) lane_insert<K>(sc, ix, s, keep_row[w][c]);   // scores <= -1 (d = inf) and NaN never match
   }
   for (int j = 0; j < k; ++j) {
     float bs; int32_t br;
-    warp_pop_best<K>(sc, ix, lane, kNoScore, &bs, &br);
+    warp_pop_best<K>(sc, ix, lane, sentinel, &bs, &br);
     if (lane == 0) {
       const bool filled = br != 0x7fffffff;
       out_rows[size_t(q) * k + j] = filled ? int64_t(br) + row_offset : int64_t(kNoRow);
-      out_scores[size_t(q) * k + j] = filled ? bs : kNoScore;
-      if (j == 0 && out_accept) out_accept[q] = (filled && bs >= threshold) ? 1 : 0;
+      if (EUCLID) {
+        const float d = filled ? __fsqrt_rn(fmaxf(-bs, 0.f)) : INFINITY;
+        out_scores[size_t(q) * k + j] = d;
+        if (j == 0 && out_accept) out_accept[q] = (filled && d <= threshold) ? 1 : 0;
+      } else {
+        out_scores[size_t(q) * k + j] = filled ? bs : kNoScore;
+        if (j == 0 && out_accept) out_accept[q] = (filled && bs >= threshold) ? 1 : 0;
+      }
     }
   }
   if (overflow && lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
@@ -805,8 +828,13 @@ static size_t tc_smem_bytes(int dim) {
 }
 
 int tc_supported(int dim, int metric, const char** why) {
-  if (metric != FRG_METRIC_COSINE) { *why = "tensor-core variants implement the cosine metric only"; return 0; }
-  if (dim % kBlockK != 0 || dim < kBlockK || dim > 512) { *why = "tensor-core variants need dim in {64..512} and a multiple of 64"; return 0; }
+  // the tiles take any multiple of 64 up to 512 columns; the exact pass behind the filter (rescoring
+  // order, overflow fallback) is the streaming scan's, which is built for 128 / 256 / 512
+  if (dim != 128 && dim != 256 && dim != 512) { *why = "tensor-core variants are built for dim 128, 256 and 512"; return 0; }
+  if (metric == FRG_METRIC_EUCLIDEAN && dim + kEuclidPad > 512) {
+    *why = "the Euclidean tensor-core filter needs dim <= 448 (one more k-block carries the norm terms)";
+    return 0;
+  }
   return 1;
 }
 
@@ -933,10 +961,14 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
 
 // qn / qb: normalised fp32 queries and their bf16 image [nq][dim]; ws: tc_workspace_bytes() of scratch.
 // Leaves the overflowed queries in (flagged, n_flagged) for the caller's exact fallback pass.
-int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb, int nq, int k, int32_t tenant,
-                    bool rescore, float threshold, int64_t row_offset, unsigned char* ws, int sm_count,
-                    int64_t* out_rows, float* out_scores, uint8_t* out_accept, int** flagged_out,
-                    int** n_flagged_out, cudaStream_t st) {
+int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
+                    int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
+                    unsigned char* ws, int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
+                    int** flagged_out, int** n_flagged_out, cudaStream_t st) {
+  const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
+  // contraction length: the plane's row length (dim, or dim + kEuclidPad for the Euclidean plane)
+  const int kdim = s->plane_dim;
+  if (euclid != (kdim != s->dim)) { set_error("tc_match: metric does not fit the store's scan plane"); return FRG_ERR_UNSUPPORTED; }
   TcPlan pl;
   tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
   uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
@@ -950,11 +982,12 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   const bool masked = tenant >= 0 || s->maybe_dead;
 
   CUtensorMap qm, gm_full;
-  FRG_CHECK(make_map(&qm, qb, s->dim, nq, size_t(s->dim) * 2, kTileQ));
-  FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, size_t(s->dim) * 2, kTileR));   // box = one CTA's half
+  FRG_CHECK(make_map(&qm, qb, kdim, nq, size_t(kdim) * 2, kTileQ));
+  FRG_CHECK(make_map(&gm_full, s->plane, kdim, s->rows, size_t(kdim) * 2, kTileR));   // box = one CTA's half
 
   TcScanParams p{};
-  p.dim = s->dim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
+  p.eps = eps; p.none_score = euclid ? kEuclidNone : kNoScore;
+  p.dim = kdim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   p.n_rows = int(s->rows); p.group_key = keys; p.k = k;
   p.seg = pl.seg; p.cand = cand; p.cand_total = cnt; p.dense = dense; p.dense_cap = pl.stage_entries;
   int rc;
@@ -989,10 +1022,12 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
   profile_begin(st, kStageSelect);
   const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
   const int rs = rescore ? 1 : 0;
+#define FRG_SELECT_M(KK, EU)                                                                                    \
+  FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+  select_rescore_kernel<KK, EU><<<grid, kSelectWarps * 32, 0, st>>>(dense, cnt, pl.stage_entries, nq, k,        \
+      s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
 #define FRG_SELECT(KK)                                                                                          \
-  FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-  select_rescore_kernel<KK><<<grid, kSelectWarps * 32, 0, st>>>(dense, cnt, pl.stage_entries, nq, k,            \
-      s->dim, qn, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
+  if (euclid) { FRG_SELECT_M(KK, true); } else { FRG_SELECT_M(KK, false); }
   switch (pl.kreg) {
     case 1: FRG_SELECT(1); break;
     case 4: FRG_SELECT(4); break;
@@ -1000,6 +1035,7 @@ int launch_tc_match(const frg_store* s, const float* qn, const __nv_bfloat16* qb
     default: FRG_SELECT(16); break;
   }
 #undef FRG_SELECT
+#undef FRG_SELECT_M
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   profile_end(st, 1);

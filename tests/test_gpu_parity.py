@@ -360,6 +360,28 @@ def test_candidate_overflow_falls_back_to_exact_scan(frg):
     store.close()
 
 
+def test_every_row_is_a_candidate(frg):
+    """Degenerate gallery - the same template enrolled 50 000 times: every row ties with every other,
+    every private candidate segment of every CTA overflows at once (their poisoned totals must not
+    wrap).  The exact fallback answers: ties go to the earliest rows, in order."""
+    d, n = 512, 50_000
+    g = synth.gallery(1, d, 5)[0]
+    G = np.repeat(g[None], n, axis=0)
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.append_rows(G, prenormalised=True)
+    other = synth.gallery(1, d, 6)[0]
+    Q = np.concatenate([np.stack([g, other]), np.repeat(g[None], 140, axis=0)])   # F > 128: CTA-pair kernels too
+    for k in (1, 16):
+        r = frg.Matcher(store).match(Q, k, 0.4, variant="tc_exact")
+        e = frg.Matcher(store).match(Q, k, 0.4, variant="scan_f32")
+        assert np.array_equal(r.rows, e.rows) and np.array_equal(r.scores, e.scores) and np.array_equal(r.accept, e.accept)
+        assert (r.rows == np.arange(k)[None]).all(), r.rows[:3]
+        ref = np.float32(np.dot(Q[1].astype(np.float64), g.astype(np.float64)))
+        assert np.abs(r.scores[0] - 1).max() <= TOL and np.abs(r.scores[1] - ref).max() <= TOL
+        assert r.accept[0] and r.accept[2:].all() and not r.accept[1]
+    store.close()
+
+
 @pytest.mark.parametrize("k", [1, 3])
 def test_euclidean_128d(frg, k):
     """BASELINE config 3 (ours; parity unpinned by the reference): d = ||g - q||_2, smallest wins."""
