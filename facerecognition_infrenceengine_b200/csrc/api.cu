@@ -544,7 +544,7 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
     return FRG_ERR_UNSUPPORTED;
   }
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
-  const size_t qb_bytes = (size_t(nq) * s->plane_dim * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
+  const size_t qb_bytes = (size_t(nq) * (s->dim + (euclid ? kEuclidQPad : 0)) * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
   const size_t eps_bytes = euclid ? ((size_t(nq) * sizeof(float) + 255) & ~size_t(255)) : 0;
   const size_t tc_bytes = tc_workspace_bytes(s->rows, s->dim, nq, k, sm_count);
   unsigned char* ws = nullptr;

@@ -74,8 +74,8 @@ struct frg_store {
   float* master = nullptr;            // [capacity][dim] fp32, unit rows
   __nv_bfloat16* plane = nullptr;     // [capacity][plane_dim] bf16 image (scan plane) or null
   // plane_dim == dim for unit-row stores.  A FRG_STORE_RAW store's plane is the EUCLIDEAN scan plane:
-  // plane_dim = dim + 64, columns dim..dim+2 hold -0.5*||g||^2 split exactly into three bf16 terms
-  // (the rest 0), so that Qaug . Gaug = q.g - 0.5*||g||^2 with Qaug = [q, 1, 1, 1, 0...] (tc_match.cu)
+  // plane_dim = dim + kEuclidPad (16), columns dim..dim+2 hold -0.5*||g||^2 split exactly into three bf16
+  // terms (the rest 0), so that Qaug . Gaug = q.g - 0.5*||g||^2 with Qaug = [q, 1, 1, 1, 0...] (tc_match.cu)
   int plane_dim = 0;
   uint32_t* gmax_bits = nullptr;      // device scalar: float bits of max ||g||^2 ever ingested (raw stores)
   int32_t* tags = nullptr;            // [capacity]
@@ -102,7 +102,7 @@ int store_begin_read(frg_store* s, cudaStream_t stream);
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
                              __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* cand_total, int* n_flagged,
                              cudaStream_t st);
-// queries.cu: Euclidean tensor-core prep: qn = q as given, bf16 image [nq][dim + 64] = [q, 1, 1, 1, 0...],
+// queries.cu: Euclidean tensor-core prep: qn = q as given, bf16 image [nq][dim + kEuclidQPad] = [q, 1, 1, 1, 0...],
 // eps[f] = filter error bound of query f from ||q|| and the store's max row norm
 int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_t* gmax_bits, float* qn,
                                   __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
@@ -136,15 +136,16 @@ int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
 // tc_match.cu: tcgen05 filter + exact rescoring.  Cosine: dim multiple of 64 and <= 512 (unit rows);
-// Euclidean: dim multiple of 64 and <= 448 over a raw store's augmented plane (plane_dim = dim + 64).
-constexpr int kEuclidPad = 64;      // one more 128-byte swizzle row of k for the three bias columns
+// Euclidean: dim 128 / 256 over a raw store's augmented plane (plane_dim = dim + kEuclidPad).
+constexpr int kEuclidPad = 16;      // plane: one more 32-byte group of k (one UMMA K step) for the three bias columns
+constexpr int kEuclidQPad = 64;     // query image: padded to a whole 128-byte swizzle row (the tile's k-block)
 constexpr float kEuclidNone = -3.0e38f;   // "no score yet" of the Euclidean filter (scores are unbounded below)
 int tc_supported(int dim, int metric, const char** why);
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count);
 void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_count, unsigned char* ws,
                                uint32_t** keys, int** cand_total, int** n_flagged);
 // metric cosine: qb = [nq][dim] bf16 unit queries, eps == nullptr (constant bound).
-// metric euclidean: qb = [nq][dim + 64] augmented image, eps[nq] per-query bounds.
+// metric euclidean: qb = [nq][dim + kEuclidQPad] augmented image, eps[nq] per-query bounds.
 int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept,

@@ -53,7 +53,7 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
 }
 
 // Euclidean tensor-core prep (BASELINE config 3; ours, not in the reference).  The query is used as
-// given; its bf16 image gets kEuclidPad more columns [1, 1, 1, 0 ...] that pick up the three bias terms of
+// given; its bf16 image gets kEuclidQPad more columns [1, 1, 1, 0 ...] that pick up the three bias terms of
 // the Euclidean scan plane, so that the tensor-core score is S = q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2:
 // largest S <=> smallest distance.  eps[w] bounds |S - exact| for every row of the store:
 //   bf16 rounding of both operands  (2u + u^2) ||q|| ||g||,  u = 2^-9   ->  < 3.92e-3 ||q|| Gmax
@@ -72,7 +72,7 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
   if (n_flagged && w == 0 && lane < 3) n_flagged[lane] = 0;
   const float4* src = reinterpret_cast<const float4*>(q + size_t(w) * dim);
   const int nvec = dim >> 2;
-  const int aug = dim + kEuclidPad;
+  const int aug = dim + kEuclidQPad;
   float ss = 0.f;
   for (int v = lane; v < nvec; v += 32) {
     const float4 x = __ldg(src + v);
@@ -87,7 +87,7 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane < kEuclidPad / 4) {
+  if (lane < kEuclidQPad / 4) {
     // bf16(1.0) = 0x3F80
     const uint2 ones = lane == 0 ? make_uint2(0x3F803F80u, 0x00003F80u) : make_uint2(0u, 0u);
     reinterpret_cast<uint2*>(q_aug + size_t(w) * aug + dim)[lane] = ones;

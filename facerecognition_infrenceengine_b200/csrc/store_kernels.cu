@@ -20,13 +20,13 @@ __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
   *reinterpret_cast<uint2*>(dst) = packed;
 }
 
-// Euclidean scan plane (raw stores): columns dim .. dim+63 of the row = [hi, mid, lo, 0 ...], the exact
+// Euclidean scan plane (raw stores): columns dim .. dim+15 of the row = [hi, mid, lo, 0 ...], the exact
 // three-term bf16 split of c = -0.5 * ||g||^2 (24 significand bits = 3 x 8), so that the tensor-core
 // product with a query image [q, 1, 1, 1, 0 ...] accumulates q.g - 0.5*||g||^2.  The largest ||g||^2
 // ever stored is folded into *gmax_bits (non-negative floats order like their bit patterns); it scales
 // the filter's error bound.  Non-finite norms are left out: such rows can never match either way.
 __device__ __forceinline__ void store_bias_columns(__nv_bfloat16* row_aug, float ss, uint32_t* gmax_bits, int lane) {
-  if (lane < 16) {
+  if (lane < kEuclidPad / 4) {
     uint2 packed = make_uint2(0u, 0u);
     if (lane == 0) {
       const float c = -0.5f * ss;

@@ -194,12 +194,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
          (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
 
+// K-major, 32B-swizzled operand tile of ONE UMMA K step: rows of 16 bf16 (32 B), 8-row groups 256 B apart
+// (layout type 6).  The Euclidean plane's pad block: only 16 columns per gallery row are staged and multiplied.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(6) << 61);
+}
+
 // ------------------------------------------------------------------------------------------ shapes
 constexpr int kTileQ = 128;          // queries per CTA tile (TMEM lanes); UMMA M = 128, or 256 across a CTA pair
 constexpr int kTileR = 128;          // gallery rows staged per CTA and k-block (TMA box rows)
 constexpr int kBlockK = 64;          // one 128-byte swizzle row of bf16
-constexpr int kStages = 6;
+constexpr int kMaxStages = 12;       // ring depth: 6 by default (all a 512-column query tile leaves room for)
 constexpr int kStageBytes = kTileR * kBlockK * 2;          // 16 KB
+constexpr int kPadStageBytes = kTileR * kEuclidPad * 2;    // 4 KB of a stage: the Euclidean plane's pad block
 constexpr int kEpiWarps = 8;          // two per TMEM lane quarter: they split a tile's columns
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 // accumulator: double-buffered, N columns each (N = 128 single CTA, 256 for a CTA pair)
@@ -246,6 +254,10 @@ struct TcScanParams {
   // else eps[q] (Euclidean plane: scales with ||q|| and the store's largest row norm)
   const float* eps;
   float none_score;        // "nothing seen": kNoScore (cosine, scores > -1) or kEuclidNone
+  // Euclidean plane: the LAST k-block of the query tile meets a 16-column pad block of the plane (pad_map:
+  // box 16 x 128 rows, 32B swizzle, 4 KB per stage) with ONE K = 16 MMA instead of four
+  int pad;
+  int stages;              // depth of the TMA ring (tc_stages)
 };
 
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
@@ -259,7 +271,7 @@ struct TcScanParams {
 template <int MODE, bool MASKED, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap g_map,
-               const TcScanParams p) {
+               const __grid_constant__ CUtensorMap pad_map, const TcScanParams p) {
   constexpr int kAccN = PAIR ? 2 * kTileR : kTileR;        // accumulator columns = gallery rows per tile
   constexpr int kTmemCols = 2 * kAccN;
   constexpr uint32_t kIdesc = make_idesc(PAIR ? 2 * kTileQ : kTileQ, kAccN);
@@ -274,14 +286,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   const uint32_t q_bytes = uint32_t(kTileQ) * p.dim * 2;            // resident query tile
   const uint32_t q_smem = base;
   const uint32_t stage_smem = base + q_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + q_bytes + kStages * kStageBytes);
+  const int nstages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + q_bytes + nstages * kStageBytes);
   const uint32_t bar0 = smem_u32(bars);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
-  auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
-  const uint32_t bar_q = bar0 + 8u * (2 * kStages + 4);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+  auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * kMaxStages + b); };
+  auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 2 + b); };
+  const uint32_t bar_q = bar0 + 8u * (2 * kMaxStages + 4);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -302,7 +315,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   auto tile_of = [&](int it) { return it < n_tiles ? tile_begin + it : tile_begin + (it - n_tiles); };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), PAIR ? 2 * kEpiWarps : kEpiWarps); }
     mbar_init(bar_q, 1);
     fence_barrier_init();
@@ -322,6 +335,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     if (lane == 0) {
       tma_prefetch_desc(&q_map);
       tma_prefetch_desc(&g_map);
+      if (p.pad) tma_prefetch_desc(&pad_map);
       const uint64_t g_hint = gridDim.x > (PAIR ? 2 : 1) ? kEvictLast : kEvictFirst;
       if (PAIR) {
         if (leader) mbar_expect_tx(bar_q, 2 * q_bytes);
@@ -338,14 +352,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         const int row0 = t * p.tile_scale * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(bar_empty(stage), phase ^ 1);
+          const bool padkb = p.pad && kb == kblocks - 1;
+          const CUtensorMap* map = padkb ? &pad_map : &g_map;
+          const uint32_t bytes = padkb ? kPadStageBytes : kStageBytes;
+          const int c0 = padkb ? 0 : kb * kBlockK;
           if (PAIR) {
-            if (leader) mbar_expect_tx(bar_full(stage), 2 * kStageBytes);
-            tma_load_2d_pair(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK, row0, g_hint);
+            if (leader) mbar_expect_tx(bar_full(stage), 2 * bytes);
+            tma_load_2d_pair(stage_smem + stage * kStageBytes, map, bar_full(stage), c0, row0, g_hint);
           } else {
-            mbar_expect_tx(bar_full(stage), kStageBytes);
-            tma_load_2d(stage_smem + stage * kStageBytes, &g_map, bar_full(stage), kb * kBlockK, row0, g_hint);
+            mbar_expect_tx(bar_full(stage), bytes);
+            tma_load_2d(stage_smem + stage * kStageBytes, map, bar_full(stage), c0, row0, g_hint);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -362,6 +380,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       int buf = 0; uint32_t tphase = 0;
       const uint64_t a_base = umma_desc_sw128(q_smem);
       const uint64_t b_base = umma_desc_sw128(stage_smem);
+      const uint64_t pad_base = umma_desc_sw32(stage_smem);
       for (int it = 0; it < n_iter; ++it) {
         mbar_wait(bar_tempty(buf), tphase ^ 1);
         tc_fence_after();
@@ -372,13 +391,21 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
           // descriptor start-address field is (addr >> 4): a k-block of A is 16 KB, a stage of B 16 KB
           const uint64_t a0 = a_base + uint64_t(kb * ((kTileQ * kBlockK * 2) >> 4));
           const uint64_t b0 = b_base + uint64_t(stage * (kStageBytes >> 4));
+          const bool padkb = p.pad && kb == kblocks - 1;
           if (elect_one()) {
+            if (padkb) {
+              // the query tile's last k-block (128B swizzle, columns 0..15) x the staged 16-column pad block
+              const uint64_t bp = pad_base + uint64_t(stage * (kStageBytes >> 4));
+              if (PAIR) umma_bf16_pair(d_tmem, a0, bp, kIdesc, 1u);
+              else umma_bf16(d_tmem, a0, bp, kIdesc, 1u);
+            } else {
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 16; ++kk) {
-              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-              const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-              if (PAIR) umma_bf16_pair(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, acc);
-              else umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, acc);
+              for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+                const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+                if (PAIR) umma_bf16_pair(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, acc);
+                else umma_bf16(d_tmem, a0 + uint64_t(kk * 2), b0 + uint64_t(kk * 2), kIdesc, acc);
+              }
             }
             // smem slot reusable / accumulator readable once these MMAs retire (both CTAs in pair mode)
             if (PAIR) {
@@ -390,7 +417,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
             }
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (++buf == 2) { buf = 0; tphase ^= 1; }
       }
@@ -806,32 +833,48 @@ static int get_encode(EncodeTiledFn* out) {
   return FRG_OK;
 }
 
-// 2-D bf16 row-major [rows][dim] view with a row pitch (bytes), box = 64 k x box_rows, 128B swizzle
-static int make_map(CUtensorMap* map, const void* ptr, int dim, int64_t rows, size_t pitch_bytes, int box_rows) {
+// 2-D bf16 row-major [rows][dim] view with a row pitch (bytes), box = box_k x box_rows; box_k = 64 with the
+// 128B swizzle (a k-block) or 16 with the 32B swizzle (the Euclidean pad block)
+static int make_map(CUtensorMap* map, const void* ptr, int dim, int64_t rows, size_t pitch_bytes, int box_rows,
+                    int box_k = kBlockK) {
   EncodeTiledFn enc = nullptr;
   FRG_CHECK(get_encode(&enc));
   cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(rows)};
   cuuint64_t gstride[1] = {cuuint64_t(pitch_bytes)};
-  cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+  cuuint32_t box[2] = {cuuint32_t(box_k), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_k == kBlockK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld pitch=%zu", int(r), (long long)rows, pitch_bytes); return FRG_ERR_CUDA; }
   return FRG_OK;
 }
 
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
-static size_t tc_smem_bytes(int dim) {
-  return size_t(kTileQ) * dim * 2 + size_t(kStages) * kStageBytes + 256 + 1024;
+// dynamic shared memory: [alignment slack 1 KB][query tile][ring][barriers 256 B].  Six 16 KB stages
+// (96 KB in flight per SM) already reach the HBM peak; a deeper ring beside shorter query tiles
+// (FRG_TC_STAGES up to 12) measured no faster at dim 128 / 256 - those shapes are bound by the TMEM read
+// rate of the epilogue, not by bytes in flight.
+constexpr size_t kSmemLimit = 227 * 1024;
+static int tc_stages(int qdim) {
+  const size_t fixed = size_t(kTileQ) * qdim * 2 + 256 + 1024;
+  int st = int((kSmemLimit - fixed) / kStageBytes);
+  static const int cap = []() { const char* e = getenv("FRG_TC_STAGES"); return e ? atoi(e) : 6; }();
+  if (st > cap) st = cap;
+  if (st > kMaxStages) st = kMaxStages;
+  return st < 2 ? 2 : st;
+}
+static size_t tc_smem_bytes(int qdim) {
+  return size_t(kTileQ) * qdim * 2 + size_t(tc_stages(qdim)) * kStageBytes + 256 + 1024;
 }
 
 int tc_supported(int dim, int metric, const char** why) {
   // the tiles take any multiple of 64 up to 512 columns; the exact pass behind the filter (rescoring
   // order, overflow fallback) is the streaming scan's, which is built for 128 / 256 / 512
   if (dim != 128 && dim != 256 && dim != 512) { *why = "tensor-core variants are built for dim 128, 256 and 512"; return 0; }
-  if (metric == FRG_METRIC_EUCLIDEAN && dim + kEuclidPad > 512) {
+  if (metric == FRG_METRIC_EUCLIDEAN && dim + kEuclidQPad > 512) {
     *why = "the Euclidean tensor-core filter needs dim <= 448 (one more k-block carries the norm terms)";
     return 0;
   }
@@ -911,11 +954,11 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
 }
 
 template <int MODE, bool MASKED, bool PAIR>
-static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const TcScanParams& p, int qtiles, int chunks,
-                          cudaStream_t st) {
+static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const CUtensorMap& pm, const TcScanParams& p,
+                          int qtiles, int chunks, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p.dim);
   auto kern = tc_scan_kernel<MODE, MASKED, PAIR>;
-  FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes(512))));
+  FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(qtiles, chunks);
   cfg.blockDim = dim3(kTcThreads);
@@ -928,19 +971,19 @@ static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const Tc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FRG_CUDA(cudaLaunchKernelEx(&cfg, kern, qm, gm, p));
+  FRG_CUDA(cudaLaunchKernelEx(&cfg, kern, qm, gm, pm, p));
   note_launch(nullptr);
   return FRG_OK;
 }
 
 template <int MODE>
 static int launch_tc_scan_m(bool masked, bool pair, const CUtensorMap& qm, const CUtensorMap& gm,
-                            const TcScanParams& p, int qtiles, int chunks, cudaStream_t st) {
+                            const CUtensorMap& pm, const TcScanParams& p, int qtiles, int chunks, cudaStream_t st) {
   if (pair)
-    return masked ? launch_tc_scan<MODE, true, true>(qm, gm, p, qtiles, chunks, st)
-                  : launch_tc_scan<MODE, false, true>(qm, gm, p, qtiles, chunks, st);
-  return masked ? launch_tc_scan<MODE, true, false>(qm, gm, p, qtiles, chunks, st)
-                : launch_tc_scan<MODE, false, false>(qm, gm, p, qtiles, chunks, st);
+    return masked ? launch_tc_scan<MODE, true, true>(qm, gm, pm, p, qtiles, chunks, st)
+                  : launch_tc_scan<MODE, false, true>(qm, gm, pm, p, qtiles, chunks, st);
+  return masked ? launch_tc_scan<MODE, true, false>(qm, gm, pm, p, qtiles, chunks, st)
+                : launch_tc_scan<MODE, false, false>(qm, gm, pm, p, qtiles, chunks, st);
 }
 
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
@@ -966,9 +1009,10 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
                     unsigned char* ws, int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
                     int** flagged_out, int** n_flagged_out, cudaStream_t st) {
   const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
-  // contraction length: the plane's row length (dim, or dim + kEuclidPad for the Euclidean plane)
-  const int kdim = s->plane_dim;
-  if (euclid != (kdim != s->dim)) { set_error("tc_match: metric does not fit the store's scan plane"); return FRG_ERR_UNSUPPORTED; }
+  if (euclid != (s->plane_dim != s->dim)) { set_error("tc_match: metric does not fit the store's scan plane"); return FRG_ERR_UNSUPPORTED; }
+  // columns of the query tile: dim, or dim + kEuclidQPad (its last k-block meets the plane's 16-column pad block)
+  const int kdim = euclid ? s->dim + kEuclidQPad : s->dim;
+  const size_t pitch = size_t(s->plane_dim) * 2;
   TcPlan pl;
   tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
   uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
@@ -981,12 +1025,14 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
   *n_flagged_out = n_flagged;
   const bool masked = tenant >= 0 || s->maybe_dead;
 
-  CUtensorMap qm, gm_full;
+  CUtensorMap qm, gm_full, pm;
   FRG_CHECK(make_map(&qm, qb, kdim, nq, size_t(kdim) * 2, kTileQ));
-  FRG_CHECK(make_map(&gm_full, s->plane, kdim, s->rows, size_t(kdim) * 2, kTileR));   // box = one CTA's half
+  FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, pitch, kTileR));   // box = one CTA's half
+  if (euclid) FRG_CHECK(make_map(&pm, s->plane + s->dim, kEuclidPad, s->rows, pitch, kTileR, kEuclidPad));
+  else pm = gm_full;                                                          // never dereferenced (p.pad == 0)
 
   TcScanParams p{};
-  p.eps = eps; p.none_score = euclid ? kEuclidNone : kNoScore;
+  p.eps = eps; p.none_score = euclid ? kEuclidNone : kNoScore; p.pad = euclid ? 1 : 0; p.stages = tc_stages(kdim);
   p.dim = kdim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   p.n_rows = int(s->rows); p.group_key = keys; p.k = k;
   p.seg = pl.seg; p.cand = cand; p.cand_total = cnt; p.dense = dense; p.dense_cap = pl.stage_entries;
@@ -1002,19 +1048,19 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
       p.arrive_target = ctas < sm_count ? ctas : sm_count;
     }
     profile_begin(st, kStageDominant);
-    rc = launch_tc_scan_m<kModeFused>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
+    rc = launch_tc_scan_m<kModeFused>(masked, pl.pair, qm, gm_full, pm, p, pl.qtiles, pl.chunks_main, st);
     FRG_CHECK(rc);
     profile_end(st, 1);
   } else {
     // 1. pre-pass over the sampled tiles
     p.tile_scale = pl.stride;
     profile_begin(st, kStagePrepass);
-    FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_pre, st));
+    FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm, gm_full, pm, p, pl.qtiles, pl.chunks_pre, st));
     profile_end(st, 1);
     // 2. filter over the whole plane
     p.tile_scale = 1;
     profile_begin(st, kStageDominant);
-    rc = launch_tc_scan_m<kModeFilter>(masked, pl.pair, qm, gm_full, p, pl.qtiles, pl.chunks_main, st);
+    rc = launch_tc_scan_m<kModeFilter>(masked, pl.pair, qm, gm_full, pm, p, pl.qtiles, pl.chunks_main, st);
     FRG_CHECK(rc);
     profile_end(st, 1);
   }

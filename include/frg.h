@@ -52,12 +52,16 @@ extern "C" {
 /* kernel variant */
 #define FRG_VARIANT_AUTO      0  /* dispatch table by batch size */
 #define FRG_VARIANT_SCAN_F32  1  /* exact fp32 streaming scan on CUDA cores, reads the fp32 master */
-#define FRG_VARIANT_TC_EXACT  2  /* tcgen05 bf16 filter over the scan plane + exact fp32 rescoring */
+#define FRG_VARIANT_TC_EXACT  2  /* tcgen05 bf16 filter over the scan plane + exact fp32 rescoring (cosine: unit-row
+                                    stores; euclidean: FRG_STORE_RAW stores with a scan plane, dim 128 / 256) */
 #define FRG_VARIANT_TC_BF16   3  /* tcgen05 bf16 scores returned as-is ("bf16 gallery mode", own tolerance) */
 
 /* frg_store_create flags */
 #define FRG_STORE_BF16_PLANE  1u /* keep the bf16 scan plane next to the fp32 master (needed by TC variants) */
-#define FRG_STORE_RAW         2u /* never normalise on ingest (Euclidean galleries) */
+#define FRG_STORE_RAW         2u /* never normalise on ingest (Euclidean galleries, cluster means).  Together with
+                                   FRG_STORE_BF16_PLANE the plane is the EUCLIDEAN scan plane: each row carries
+                                   -0.5*||g||^2 in 64 more bf16 columns, so that the tensor-core product with
+                                   [q, 1, 1, 1, 0..] is q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2 */
 #define FRG_STORE_BF16_ONLY   4u /* keep ONLY the bf16 scan plane (1 KB / 512-d row instead of 3 KB): "bf16 gallery
                                    mode".  Matches run as FRG_VARIANT_TC_BF16 (scores within 4e-3 of fp32);
                                    the exact variants, first_match and the Euclidean metric are not available. */
