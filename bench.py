@@ -290,7 +290,10 @@ def ours_arm(args, rank, world):
                 if i % 64 == 0:
                     torch.cuda.synchronize()
             torch.cuda.synchronize()
-        N.profile_enable(True)
+        # Inside the timed region only the DOMINANT kernel is bracketed by events (2 records per step:
+        # measured +6 us per step).  Bracketing every stage costs ~30 us per step (12 % at batch 64,
+        # tools/event_tax_probe.py), so the per-stage split comes from a separate short pass below.
+        N.check(N.lib.frg_profile_enable(2))
         N.profile_collect()
         if world > 1:
             torch.distributed.barrier()
@@ -305,9 +308,26 @@ def ours_arm(args, rank, world):
             torch.distributed.barrier()
         total_ms = ev0.elapsed_time(ev1)
         dom_ms, dom_launches = N.profile_collect()
-        stages = {k_: v / steps for k_, v in N.profile_stages().items()}
-        N.profile_enable(False)
         ck = sampler.stop() if sampler else None
+        # per-stage split (untimed for `value`): every stage bracketed, a few steps
+        N.check(N.lib.frg_profile_enable(1))
+        nsplit = max(5, min(steps, 30))
+        for i in range(nsplit):
+            step(i)
+        torch.cuda.synchronize()
+        N.profile_collect()
+        stages = {k_: v / nsplit for k_, v in N.profile_stages().items()}
+        N.profile_enable(False)
+        # spread of single steps (median, p10, p90): one event per step boundary
+        nsp = max(10, min(steps, 100))
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nsp + 1)]
+        evs[0].record(stream)
+        for i in range(nsp):
+            step(i)
+            evs[i + 1].record(stream)
+        torch.cuda.synchronize()
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(nsp))
+        spread = {"p10": per[nsp // 10], "p50": per[nsp // 2], "p90": per[(nsp * 9) // 10], "steps": nsp}
         if world > 1:
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -315,7 +335,7 @@ def ours_arm(args, rank, world):
         ms = total_ms / steps
         return {"batch": F, "value": F * scale / (ms * 1e-3), "ms_per_step": ms, "variant": variant,
                 "launches_per_step": launches_per_step, "dom_ms": dom_ms, "dom_launches": dom_launches,
-                "total_ms": total_ms, "clocks": ck, "stage_ms": stages}
+                "total_ms": total_ms, "clocks": ck, "stage_ms": stages, "step_ms_spread": spread}
 
     # ---- headline batch: device-timed region
     F = args.batch
@@ -412,6 +432,7 @@ def ours_arm(args, rank, world):
             sweep.append({"batch": Fs, "value": r["value"], "ms_per_step": r["ms_per_step"], "variant": r["variant"],
                           "bound": rf["bound"], "kernel_frac": rf["frac"], "kernel_ms": rf["launch_ms"],
                           "stage_ms": {k_: round(v, 4) for k_, v in r["stage_ms"].items()},
+                          "step_ms_spread": {k_: round(v, 4) for k_, v in r["step_ms_spread"].items()},
                           "step_frac_of_roofline": step_roofline_ms(n, dim, Fs, peaks) / r["ms_per_step"]})
 
     if rank != 0:
@@ -456,7 +477,10 @@ def ours_arm(args, rank, world):
             "queries_per_s_raw": value / scale if sharded else value,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": main["launches_per_step"] * args.steps,
-            "clocks": clocks, "parity": parity, "sweep": sweep, "peaks": peaks}
+            "clocks": clocks, "parity": parity, "sweep": sweep, "peaks": peaks,
+            "step_ms_spread": main["step_ms_spread"],
+            "timing": "CUDA events on the launching stream around the K steps; only the dominant kernel is "
+                      "bracketed inside the timed region, per-stage and per-step figures come from separate passes"}
     print(json.dumps(line), flush=True)
 
 
@@ -519,7 +543,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=512)

@@ -31,14 +31,14 @@ void note_launch(const char* variant) {
 void reset_launches() { g_launches = 0; g_variant = "none"; }
 
 struct ProfileSpan { cudaEvent_t a, b; int launches; int stage; };
-static thread_local bool g_profile = false;
+static thread_local int g_profile = 0;      // 0 off, 1 every stage, 2 the dominant kernel only
 static thread_local std::vector<ProfileSpan> g_spans;
 static thread_local cudaEvent_t g_open = nullptr;
 static thread_local int g_open_stage = 0;
 static thread_local float g_stage_ms[FRG_PROFILE_STAGES] = {0};
 
 void profile_begin(cudaStream_t st, int stage) {
-  if (!g_profile) return;
+  if (!g_profile || (g_profile == 2 && stage != kStageDominant)) return;
   if (cudaEventCreate(&g_open) != cudaSuccess) { g_open = nullptr; return; }
   g_open_stage = stage;
   cudaEventRecord(g_open, st);
@@ -174,7 +174,7 @@ int frg_last_launch_count(void) { return g_launches; }
 const char* frg_last_variant(void) { return g_variant; }
 
 int frg_profile_enable(int32_t on) {
-  g_profile = on != 0;
+  g_profile = on < 0 ? 0 : (on > 2 ? 1 : on);
   return FRG_OK;
 }
 

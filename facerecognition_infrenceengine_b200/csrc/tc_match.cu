@@ -661,9 +661,12 @@ __device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], 
 
 constexpr int kSelectWarps = 4;
 
-// The dense candidate list of a query (a few hundred entries, L2-resident: the filter kernel has just
-// written it) is read twice straight from global memory - no shared-memory staging, so every query's
-// warp is resident at once and the DRAM/L2 latencies of different queries overlap.
+// ONE CTA (4 warps) per query.  The dense candidate list of a query (a few hundred entries, L2-resident:
+// the filter kernel has just written it) is read twice straight from global memory, each warp taking every
+// fourth 32-entry slice; the warps meet in shared memory three times (their k best coarse scores -> tau,
+// the compacted survivors, the exact scores).  With one WARP per query the kernel ran ~3900 dependent
+// instructions per query at 5 warps per SM (40 us at 1024 queries, ncu: 83 % of cycles no eligible warp);
+// four warps per query cut the chain and quadruple the warps in flight.
 // EUCLID: the coarse scores are S = q.g - 0.5*||g||^2 (larger = nearer); the kept rows are rescored as the
 // exact direct-difference d^2 = sum (g - q)^2 (the streaming scan's arithmetic and order), ranked by
 // (-d^2 desc, row asc) and reported as distances; accept iff d <= threshold.
@@ -675,35 +678,54 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
                       const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
                       uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged) {
-  __shared__ int keep_row[kSelectWarps][kMaxKeep];
-  __shared__ float keep_sc[kSelectWarps][kMaxKeep];
+  __shared__ int keep_row[kMaxKeep];
+  __shared__ float keep_sc[kMaxKeep];
+  __shared__ float top_s[kSelectWarps][FRG_MAX_K];
+  __shared__ int32_t top_r[kSelectWarps][FRG_MAX_K];
+  __shared__ int s_m;
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  const int q = blockIdx.x * kSelectWarps + w;
-  if (q >= nq) return;
+  const int q = blockIdx.x;
 
   const int total = cand_total[q];
-  bool overflow = total > dense_cap;                 // also set by a poisoned total (segment overflow)
-  if (overflow) {
+  if (total > dense_cap) {                           // also set by a poisoned total (segment overflow)
     // the dense list is incomplete (and partly unwritten): leave the query to the exact fallback
-    if (lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
+    if (threadIdx.x == 0) flagged[atomicAdd(n_flagged, 1)] = q;
     return;
   }
   const int n = total;
   const int2* mine = dense + size_t(q) * dense_cap;
+  if (threadIdx.x == 0) s_m = 0;
 
-  // (a) tau = k-th best coarse score: lane-local top-K, then k rounds of warp arg-max
+  // (a) this warp's k best coarse scores: lane-local top-K over its slices, then k rounds of warp arg-max
   float sc[K];
   int32_t ix[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) { sc[j] = -INFINITY; ix[j] = 0x7fffffff; }
-  for (int c0 = lane; c0 < n; c0 += 128) {
+  for (int c0 = w * 32 + lane; c0 < n; c0 += 4 * kSelectWarps * 32) {
     int2 e[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) e[u] = c0 + 32 * u < n ? mine[c0 + 32 * u] : make_int2(0x7fffffff, __float_as_int(-INFINITY));
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * kSelectWarps * 32;
+      e[u] = c < n ? mine[c] : make_int2(0x7fffffff, __float_as_int(-INFINITY));
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (c0 + 32 * u < n) lane_insert<K>(sc, ix, __int_as_float(e[u].y), e[u].x);
+      if (c0 + u * kSelectWarps * 32 < n) lane_insert<K>(sc, ix, __int_as_float(e[u].y), e[u].x);
+  }
+  for (int j = 0; j < k; ++j) {
+    float bs; int32_t br;
+    warp_pop_best<K>(sc, ix, lane, -INFINITY, &bs, &br);
+    if (lane == 0) { top_s[w][j] = bs; top_r[w][j] = br; }
+  }
+  __syncthreads();
+
+  // tau = k-th best of the 4 x k warp winners (every warp folds them: no second barrier for a broadcast)
+#pragma unroll
+  for (int j = 0; j < K; ++j) { sc[j] = -INFINITY; ix[j] = 0x7fffffff; }
+  for (int c = lane; c < kSelectWarps * k; c += 32) {
+    const int ww = c / k, j = c - ww * k;
+    lane_insert<K>(sc, ix, top_s[ww][j], top_r[ww][j]);
   }
   float tau = -INFINITY;
   float top_sc = 0.f; int32_t top_ix = -1;     // lane j keeps the j-th coarse winner (TC_BF16 output)
@@ -716,51 +738,56 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
 
   if (!rescore) {
     // bf16 gallery mode: report the coarse scores themselves (own tolerance)
-    if (lane < k) {
+    if (w == 0 && lane < k) {
       const bool filled = top_ix >= 0 && top_sc > kNoScore;
       out_rows[size_t(q) * k + lane] = filled ? int64_t(top_ix) + row_offset : int64_t(kNoRow);
       out_scores[size_t(q) * k + lane] = filled ? top_sc : kNoScore;
       if (lane == 0 && out_accept) out_accept[q] = (filled && top_sc >= threshold) ? 1 : 0;
     }
-    if (overflow && lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
     return;
   }
 
-  // (b) compact the rows that can still be in the true top-k
+  // (b) compact the rows that can still be in the true top-k (their order is irrelevant: the final
+  //     order below is total)
   const float keep_thr = tau - 2.0f * (eps ? __ldg(eps + q) : kCoarseEps);
-  int m = 0;
-  for (int c0 = 0; c0 < n; c0 += 128) {             // 4 independent loads per lane per round
+  for (int c0 = w * 32; c0 < n; c0 += 4 * kSelectWarps * 32) {     // 4 independent loads per lane per round
     int2 e[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int c = c0 + 32 * u + lane;
+      const int c = c0 + u * kSelectWarps * 32 + lane;
       e[u] = c < n ? mine[c] : make_int2(-1, __float_as_int(-INFINITY));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const bool kp = (c0 + 32 * u + lane < n) && __int_as_float(e[u].y) >= keep_thr;
+      const bool kp = (c0 + u * kSelectWarps * 32 + lane < n) && __int_as_float(e[u].y) >= keep_thr;
       const unsigned bal = __ballot_sync(0xffffffffu, kp);
-      const int pos = m + __popc(bal & ((1u << lane) - 1));
-      if (kp && pos < kMaxKeep) keep_row[w][pos] = e[u].x;
-      m += __popc(bal);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(bal & ((1u << lane) - 1));
+        if (kp && pos < kMaxKeep) keep_row[pos] = e[u].x;
+      }
     }
   }
-  if (m > kMaxKeep) { overflow = true; m = kMaxKeep; }
-  __syncwarp();
+  __syncthreads();
+  int m = s_m;
+  const bool overflow = m > kMaxKeep;            // too many survivors: rescored in part, then redone by the fallback
+  if (overflow) m = kMaxKeep;
 
-  // (c) exact fp32 rescoring, 8 rows in flight per warp (coalesced 16-byte loads, same element ->
+  // (c) exact fp32 rescoring, 4 rows in flight per warp (coalesced 16-byte loads, same element ->
   //     lane mapping and summation order as the streaming scan)
-  constexpr int kRescoreRows = 8;
+  constexpr int kRescoreRows = 4;
   const int nvec = dim >> 2;
   const float4* qq = reinterpret_cast<const float4*>(qn + size_t(q) * dim);
-  for (int i0 = 0; i0 < m; i0 += kRescoreRows) {
+  for (int i0 = w * kRescoreRows; i0 < m; i0 += kSelectWarps * kRescoreRows) {
     float a[kRescoreRows];
     const float4* g[kRescoreRows];
 #pragma unroll
     for (int u = 0; u < kRescoreRows; ++u) {
       a[u] = 0.f;
       const int i = i0 + u < m ? i0 + u : i0;
-      g[u] = reinterpret_cast<const float4*>(master + size_t(keep_row[w][i]) * dim);
+      g[u] = reinterpret_cast<const float4*>(master + size_t(keep_row[i]) * dim);
     }
     for (int v = lane; v < nvec; v += 32) {
       const float4 y = __ldg(qq + v);
@@ -783,18 +810,19 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
     for (int u = 0; u < kRescoreRows; ++u) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
-      if (lane == 0 && i0 + u < m) keep_sc[w][i0 + u] = EUCLID ? -a[u] : a[u];
+      if (lane == 0 && i0 + u < m) keep_sc[i0 + u] = EUCLID ? -a[u] : a[u];
     }
   }
-  __syncwarp();
+  __syncthreads();
+  if (w != 0) return;
 
   // (d) final order (score desc, row asc) over the m exact scores; lane-local lists + warp merge
   const float sentinel = EUCLID ? -INFINITY : kNoScore;     // the exact scan's initial best
 #pragma unroll
   for (int j = 0; j < K; ++j) { sc[j] = sentinel; ix[j] = 0x7fffffff; }
   for (int c = lane; c < m; c += 32) {
-    const float s = keep_sc[w][c];
-    if (s > sentinel) lane_insert<K>(sc, ix, s, keep_row[w][c]);   // scores <= -1 (d = inf) and NaN never match
+    const float s = keep_sc[c];
+    if (s > sentinel) lane_insert<K>(sc, ix, s, keep_row[c]);   // scores <= -1 (d = inf) and NaN never match
   }
   for (int j = 0; j < k; ++j) {
     float bs; int32_t br;
@@ -1066,7 +1094,7 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
   }
   // 3. select + exact rescoring
   profile_begin(st, kStageSelect);
-  const int grid = (nq + kSelectWarps - 1) / kSelectWarps;
+  const int grid = nq;                                   // one CTA per query
   const int rs = rescore ? 1 : 0;
 #define FRG_SELECT_M(KK, EU)                                                                                    \
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
