@@ -205,7 +205,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
 constexpr int kTileQ = 128;          // queries per CTA tile (TMEM lanes); UMMA M = 128, or 256 across a CTA pair
 constexpr int kTileR = 128;          // gallery rows staged per CTA and k-block (TMA box rows)
 constexpr int kBlockK = 64;          // one 128-byte swizzle row of bf16
-constexpr int kMaxStages = 12;       // ring depth: 6 by default (all a 512-column query tile leaves room for)
+constexpr int kMaxStages = 8;        // ring depth: 6 by default (all a 512-column query tile leaves room for)
+constexpr int kMaxKBlocks = 8;       // 512 columns / 64
 constexpr int kStageBytes = kTileR * kBlockK * 2;          // 16 KB
 constexpr int kPadStageBytes = kTileR * kEuclidPad * 2;    // 4 KB of a stage: the Euclidean plane's pad block
 constexpr int kEpiWarps = 8;          // two per TMEM lane quarter: they split a tile's columns
@@ -293,8 +294,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   auto bar_empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * kMaxStages + b); };
   auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * kMaxStages + 2 + b); };
-  const uint32_t bar_q = bar0 + 8u * (2 * kMaxStages + 4);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  // one barrier per k-block of the resident query tile: the first MMAs start when 16 KB of it have
+  // landed, not all 128 KB
+  auto bar_q = [&](int kb) { return bar0 + 8u * (2 * kMaxStages + 4 + kb); };
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kMaxKBlocks);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -317,7 +320,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), PAIR ? 2 * kEpiWarps : kEpiWarps); }
-    mbar_init(bar_q, 1);
+    for (int kb = 0; kb < kblocks; ++kb) mbar_init(bar_q(kb), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -337,20 +340,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       tma_prefetch_desc(&g_map);
       if (p.pad) tma_prefetch_desc(&pad_map);
       const uint64_t g_hint = gridDim.x > (PAIR ? 2 : 1) ? kEvictLast : kEvictFirst;
-      if (PAIR) {
-        if (leader) mbar_expect_tx(bar_q, 2 * q_bytes);
-        for (int kb = 0; kb < kblocks; ++kb)
-          tma_load_2d_pair(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
-      } else {
-        mbar_expect_tx(bar_q, q_bytes);
-        for (int kb = 0; kb < kblocks; ++kb)
-          tma_load_2d(q_smem + kb * (kTileQ * kBlockK * 2), &q_map, bar_q, kb * kBlockK, qtile * kTileQ, kEvictLast);
-      }
+      constexpr uint32_t kQBlockBytes = kTileQ * kBlockK * 2;
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iter; ++it) {
         const int t = tile_of(it);
         const int row0 = t * p.tile_scale * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
         for (int kb = 0; kb < kblocks; ++kb) {
+          if (it == 0) {
+            // the query tile's k-block kb, issued just ahead of the first gallery block that meets it
+            if (PAIR) {
+              if (leader) mbar_expect_tx(bar_q(kb), 2 * kQBlockBytes);
+              tma_load_2d_pair(q_smem + kb * kQBlockBytes, &q_map, bar_q(kb), kb * kBlockK, qtile * kTileQ, kEvictLast);
+            } else {
+              mbar_expect_tx(bar_q(kb), kQBlockBytes);
+              tma_load_2d(q_smem + kb * kQBlockBytes, &q_map, bar_q(kb), kb * kBlockK, qtile * kTileQ, kEvictLast);
+            }
+          }
           mbar_wait(bar_empty(stage), phase ^ 1);
           const bool padkb = p.pad && kb == kblocks - 1;
           const CUtensorMap* map = padkb ? &pad_map : &g_map;
@@ -374,8 +379,6 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     // themselves are issued by one elected lane.  (Running the loop under `lane == 0` costs an
     // ELECT + R2UR chain per MMA operand and makes the issue path, not the tensor pipe, the limit.)
     if (leader) {
-      mbar_wait(bar_q, 0);
-      tc_fence_after();
       int stage = 0; uint32_t phase = 0;
       int buf = 0; uint32_t tphase = 0;
       const uint64_t a_base = umma_desc_sw128(q_smem);
@@ -386,6 +389,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(buf * kAccN);
         for (int kb = 0; kb < kblocks; ++kb) {
+          if (it == 0) mbar_wait(bar_q(kb), 0);          // first tile: the query k-block must have landed
           mbar_wait(bar_full(stage), phase);
           tc_fence_after();
           // descriptor start-address field is (addr >> 4): a k-block of A is 16 KB, a stage of B 16 KB
@@ -945,10 +949,19 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
     if (c > tiles) c = tiles;
     return c < 1 ? 1 : c;
   };
-  pl->chunks_pre = chunks_for((tiles_all + stride - 1) / stride);
-  // fewer, longer pre-pass CTAs: the floor fold costs O(parts) per query
-  static const int pre_cap = []() { const char* e = getenv("FRG_TC_PRE_CHUNKS"); return e ? atoi(e) : 148; }();
-  if (pre_cap > 0 && pl->chunks_pre > pre_cap) pl->chunks_pre = pre_cap;
+  // pre-pass: a few tiles per CTA, so the fixed cost of a CTA (query-tile load, TMEM allocation, the
+  // group-max atomics at its end) matters - never more than ONE wave (1024 queries: 72 CTA pairs with
+  // 7 tiles each instead of 148 pairs in two waves of 3-4)
+  {
+    const int units = pl->pair ? sm_count / 2 : sm_count;
+    const int cols = pl->pair ? pl->qtiles / 2 : pl->qtiles;
+    const int tiles_pre = (tiles_all + stride - 1) / stride;
+    int c = cols <= units ? units / cols : 1;
+    if (c > tiles_pre) c = tiles_pre;
+    static const int pre_cap = []() { const char* e = getenv("FRG_TC_PRE_CHUNKS"); return e ? atoi(e) : 0; }();
+    if (pre_cap > 0) c = pre_cap < tiles_pre ? pre_cap : tiles_pre;
+    pl->chunks_pre = c < 1 ? 1 : c;
+  }
   pl->chunks_main = chunks_for(tiles_all);
   pl->kreg = reg_k(k);
   // Expected candidates per query ~ 2 * stride * Gamma(k): the k-th best of a 1/stride sample sits
