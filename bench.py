@@ -290,10 +290,10 @@ def ours_arm(args, rank, world):
                 if i % 64 == 0:
                     torch.cuda.synchronize()
             torch.cuda.synchronize()
-        # Inside the timed region only the DOMINANT kernel is bracketed by events (2 records per step:
-        # measured +6 us per step).  Bracketing every stage costs ~30 us per step (12 % at batch 64,
+        # Inside the timed region only the DOMINANT kernel is bracketed by events, on every 4th step (an
+        # event pair costs ~6 us of stream time; bracketing every stage ~30 us per step = 12 % at batch 64,
         # tools/event_tax_probe.py), so the per-stage split comes from a separate short pass below.
-        N.check(N.lib.frg_profile_enable(2))
+        N.check(N.lib.frg_profile_enable(3))
         N.profile_collect()
         if world > 1:
             torch.distributed.barrier()
@@ -335,6 +335,7 @@ def ours_arm(args, rank, world):
         ms = total_ms / steps
         return {"batch": F, "value": F * scale / (ms * 1e-3), "ms_per_step": ms, "variant": variant,
                 "launches_per_step": launches_per_step, "dom_ms": dom_ms, "dom_launches": dom_launches,
+                "dom_steps": (steps + 3) // 4,          # steps whose dominant kernel was bracketed
                 "total_ms": total_ms, "clocks": ck, "stage_ms": stages, "step_ms_spread": spread}
 
     # ---- headline batch: device-timed region
@@ -414,9 +415,59 @@ def ours_arm(args, rank, world):
         e2e_s = float(t.item())
     e2e = {"value": F * scale * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
            "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / args.steps * 1e3,
+           "callers": 1,
            "api": ("ShardedMatcher.match: pinned host batch -> H2D -> frg_match per shard -> all-gather -> "
                    "frg_merge_topk_strided -> D2H" if sharded else
                    "frg_match_host via Matcher.match (pinned host buffers)")}
+
+    # The reference runs one matcher thread per camera against one shared gallery (peopleCount.py:918-924):
+    # the same public call from TWO host threads, each with its own batches and result buffers.  Every
+    # step still copies its batch in and its results out inside the timed region; the copies and the
+    # launch latency of one caller overlap the kernels of the other (frg_match_host is re-entrant: one
+    # stream per host thread).  Reported beside the single-caller figure, never instead of it.
+    if not sharded and args.e2e_callers > 1:
+        import threading
+        T = args.e2e_callers
+        per = max(1, args.steps // T)
+        start = threading.Barrier(T + 1)
+        spans, errs = [None] * T, []
+
+        def caller(ti):
+            try:
+                torch.cuda.set_device(local)
+                Qt = [torch.from_numpy(q).pin_memory() for q in Qh]
+                rt = frg.MatchResult(torch.empty((F, k), dtype=torch.int64).pin_memory().numpy(),
+                                     torch.empty((F, k), dtype=torch.float32).pin_memory().numpy(),
+                                     torch.empty((F,), dtype=torch.uint8).pin_memory().numpy())
+                mt = frg.Matcher(store)
+                for i in range(3):
+                    mt.match(Qt[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=rt)
+                start.wait()
+                a = time.perf_counter()
+                for i in range(per):
+                    mt.match(Qt[(i + ti) % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=rt)
+                spans[ti] = (a, time.perf_counter())
+            except Exception as ex:          # noqa: BLE001
+                errs.append(repr(ex))
+                try:
+                    start.abort()
+                except Exception:            # noqa: BLE001
+                    pass
+
+        th = [threading.Thread(target=caller, args=(ti,)) for ti in range(T)]
+        [t_.start() for t_ in th]
+        try:
+            start.wait()
+        except threading.BrokenBarrierError:
+            pass
+        [t_.join() for t_ in th]
+        if not errs and all(spans):
+            wall = max(b for _, b in spans) - min(a for a, _ in spans)
+            e2e["concurrent"] = {"callers": T, "value": F * per * T / wall, "unit": UNIT,
+                                 "ms_per_step": wall / (per * T) * 1e3, "steps": per * T,
+                                 "h2d_bytes_per_step": F * dim * 4, "d2h_bytes_per_step": F * k * 12 + F}
+        else:
+            e2e["concurrent"] = {"callers": T, "error": errs[:2]}
 
     # ---- other batch sizes of configs[1] ("batch 1-1024"): device-timed, same method
     sweep = []
@@ -440,8 +491,9 @@ def ours_arm(args, rank, world):
 
     roof = roofline_for(variant, n, dim, F, main["dom_ms"] / max(main["dom_launches"], 1), peaks)
     roof["traffic"], roof["traffic_source"] = ncu_traffic(variant, n, dim, F, world)
-    roof["launches_per_step"] = main["dom_launches"] / args.steps
-    roof["kernel_share_of_step"] = main["dom_ms"] / main["total_ms"]
+    roof["launches_per_step"] = main["dom_launches"] / main["dom_steps"]
+    roof["timed_launches"] = main["dom_launches"]
+    roof["kernel_share_of_step"] = (main["dom_ms"] / main["dom_steps"]) / ms_per_step
     roof["step_frac_of_roofline"] = step_roofline_ms(n, dim, F, peaks) / ms_per_step
 
     # ---- CPU baseline (bounded sample of the same workload, on this box's host cores)
@@ -489,7 +541,7 @@ def ncu_traffic(variant, n, dim, F, world):
     capture committed under profiles/ (only when it was taken on this very workload), else None."""
     if world != 1 or variant != "tc_exact" or (n, dim) != (1_000_000, 512):
         return None, None
-    name = {1024: "r01_ncu_full_tc_scan_b1024_v3.txt", 64: "r01_ncu_full_tc_scan_b64_v1.txt"}.get(F)
+    name = {1024: "r01_ncu_full_tc_scan_b1024_v4.txt", 64: "r01_ncu_full_tc_scan_b64_v1.txt"}.get(F)
     path = os.path.join(ROOT, "profiles", name) if name else None
     if not path or not os.path.exists(path):
         return None, None
@@ -561,6 +613,8 @@ def main():
                          "--batch 4096 --k 10); default: --rows per GPU")
     ap.add_argument("--shard", default="gallery", choices=["gallery", "queries"],
                     help="N>1: row-shard the gallery (all-gather + merge) or replicate it and shard the query stream")
+    ap.add_argument("--e2e-callers", type=int, default=2,
+                    help="host threads of the extra concurrent end-to-end measurement (1 = skip it)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)

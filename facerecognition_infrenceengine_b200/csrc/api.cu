@@ -31,14 +31,17 @@ void note_launch(const char* variant) {
 void reset_launches() { g_launches = 0; g_variant = "none"; }
 
 struct ProfileSpan { cudaEvent_t a, b; int launches; int stage; };
-static thread_local int g_profile = 0;      // 0 off, 1 every stage, 2 the dominant kernel only
+static thread_local int g_profile = 0;      // 0 off, 1 every stage, 2 the dominant kernel only, 3 = 2 on every 4th match
+static thread_local unsigned g_match_seq = 0;
+constexpr unsigned kProfileSampleEvery = 4;
 static thread_local std::vector<ProfileSpan> g_spans;
 static thread_local cudaEvent_t g_open = nullptr;
 static thread_local int g_open_stage = 0;
 static thread_local float g_stage_ms[FRG_PROFILE_STAGES] = {0};
 
 void profile_begin(cudaStream_t st, int stage) {
-  if (!g_profile || (g_profile == 2 && stage != kStageDominant)) return;
+  if (!g_profile || (g_profile >= 2 && stage != kStageDominant)) return;
+  if (g_profile == 3 && (g_match_seq % kProfileSampleEvery) != 0) return;
   if (cudaEventCreate(&g_open) != cudaSuccess) { g_open = nullptr; return; }
   g_open_stage = stage;
   cudaEventRecord(g_open, st);
@@ -174,7 +177,8 @@ int frg_last_launch_count(void) { return g_launches; }
 const char* frg_last_variant(void) { return g_variant; }
 
 int frg_profile_enable(int32_t on) {
-  g_profile = on < 0 ? 0 : (on > 2 ? 1 : on);
+  g_profile = on < 0 ? 0 : (on > 3 ? 1 : on);
+  g_match_seq = 0;
   return FRG_OK;
 }
 
@@ -596,6 +600,7 @@ int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_mat
   std::lock_guard<std::mutex> lk(s->mu);   // enqueue under the lock: the snapshot a match sees is the
                                            // store as of this call (peopleCount.py:816-819 semantics)
   FRG_CHECK(store_begin_read(s, st));
+  struct SeqBump { ~SeqBump() { ++g_match_seq; } } bump;      // sampled profiling: every 4th match is bracketed
   switch (pick_variant(s, p, nq)) {
     case FRG_VARIANT_SCAN_F32:
       return match_scan(s, q, nq, k, p, di.sm_count, out_rows, out_scores, out_accept, st);
@@ -608,6 +613,25 @@ int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_mat
       return FRG_ERR_INVALID;
   }
 }
+
+// Per-thread pinned bounce buffer for results: ONE device->host copy per match instead of three, at full
+// PCIe rate whether or not the caller's arrays are pinned.  Grow-only; released with the thread.
+struct PinnedScratch {
+  unsigned char* p = nullptr;
+  size_t cap = 0;
+  ~PinnedScratch() { if (p) cudaFreeHost(p); }
+  unsigned char* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      const size_t want = (bytes + 65535) & ~size_t(65535);
+      if (cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return nullptr; }
+      cap = want;
+    }
+    return p;
+  }
+};
+static thread_local PinnedScratch g_result_bounce;
 
 int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
                    int64_t* out_rows, float* out_scores, uint8_t* out_accept) {
@@ -628,10 +652,24 @@ int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const fr
     rc = frg_match(s, reinterpret_cast<float*>(d), nq, k, p, reinterpret_cast<int64_t*>(d + o_r),
                    reinterpret_cast<float*>(d + o_s), d + o_a, st);
   if (rc == FRG_OK) {
-    e = cudaMemcpyAsync(out_rows, d + o_r, rb, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d + o_s, sb, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && out_accept) e = cudaMemcpyAsync(out_accept, d + o_a, ab, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    // rows | scores | accept sit in one device range [o_r, o_a + ab): one copy into the pinned bounce
+    const size_t span = o_a + ab - o_r;
+    unsigned char* h = g_result_bounce.get(span);
+    if (h) {
+      e = cudaMemcpyAsync(h, d + o_r, span, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) {
+        memcpy(out_rows, h, rb);
+        memcpy(out_scores, h + (o_s - o_r), sb);
+        if (out_accept) memcpy(out_accept, h + (o_a - o_r), ab);
+      }
+    } else {
+      (void)cudaGetLastError();        // no pinned memory to be had: three direct copies
+      e = cudaMemcpyAsync(out_rows, d + o_r, rb, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d + o_s, sb, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && out_accept) e = cudaMemcpyAsync(out_accept, d + o_a, ab, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
     if (e != cudaSuccess) rc = cuda_fail(e, "D2H results", __FILE__, __LINE__);
   }
   cudaFreeAsync(d, st);

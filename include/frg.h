@@ -184,7 +184,8 @@ FRG_API const char* frg_last_variant(void);
  * events on the caller's stream.  frg_profile_collect waits for those events, returns the summed
  * device time and launch count since the last collect, and clears them.  Thread-local. */
 /* on: 0 = off, 1 = every stage of the pipeline (frg_profile_stage_ms), 2 = the dominant kernel only
- * (two event records per match: what bench.py keeps inside its timed region) */
+ * (two event records per match), 3 = as 2 but only every 4th match of this thread, starting with the
+ * next one (what bench.py keeps inside its timed region: an event pair costs ~6 us of stream time) */
 FRG_API int frg_profile_enable(int32_t on);
 FRG_API int frg_profile_collect(float* dominant_ms, int32_t* dominant_launches);
 /* Per-stage device time of the matches since the last frg_profile_collect (filled by that call):
