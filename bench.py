@@ -175,7 +175,7 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": qps, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "setup_s": gen_s}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def workload_config(args, batch, world=1):
@@ -533,7 +533,29 @@ def ours_arm(args, rank, world):
             "step_ms_spread": main["step_ms_spread"],
             "timing": "CUDA events on the launching stream around the K steps; only the dominant kernel is "
                       "bracketed inside the timed region, per-stage and per-step figures come from separate passes"}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries write banners to stdout (NCCL: "NCCL version ..." at communicator creation).  The contract is
+    ONE JSON line on stdout: point fd 1 at stderr for the whole run and keep the real stdout for emit_json()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def ncu_traffic(variant, n, dim, F, world):
@@ -623,6 +645,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    quiet_stdout()
     if args.impl == "reference":
         reference_arm(args, rank, world)
     else:
