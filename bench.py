@@ -186,12 +186,12 @@ def workload_config(args, batch, world=1):
         cfg["storage"] = "bf16-only gallery (FRG_STORE_BF16_ONLY): scores are the bf16 filter's, |dscore| <= 4e-3"
     if args.rows_total:
         cfg.update({"workload": "configs[3]: 512-d cosine, %d-template gallery row-sharded over %d B200 (%d rows each), "
-                                "batch %d, top-%d, NCCL all-gather + k-way merge" % (
+                                "batch %d, top-%d, per-rank top-k exchanged and merged (config.exchange)" % (
                                     args.rows_total, world, args.rows, batch, args.k),
                     "sharding": "gallery rows", "gallery_rows_total": args.rows_total})
     elif world > 1 and args.shard == "gallery":
         cfg.update({"workload": "configs[1] per GPU, gallery row-sharded over %d GPUs (%d rows each, %d total), "
-                                "queries replicated, NCCL all-gather of per-rank top-k + k-way merge" % (
+                                "queries replicated, per-rank top-k exchanged and merged (config.exchange)" % (
                                     world, args.rows, args.rows * world),
                     "sharding": "gallery rows", "gallery_rows_total": args.rows * world,
                     "value_definition": "1M-row-gallery-equivalent queries/s = batch * (total_rows / gallery_rows) / "
@@ -243,7 +243,7 @@ def ours_arm(args, rank, world):
         from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
         sg = ShardedGallery(dim=dim, device=local, store=store)
         sg.fill_synthetic(n * world, args.seed)          # this rank: rows [rank*n, (rank+1)*n)
-        smatcher = ShardedMatcher(sg)
+        smatcher = ShardedMatcher(sg, exchange=args.exchange)
     else:
         store.fill_synthetic(n, 0, args.seed)
     torch.cuda.synchronize()
@@ -416,8 +416,8 @@ def ours_arm(args, rank, world):
     e2e = {"value": F * scale * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
            "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / args.steps * 1e3,
            "callers": 1,
-           "api": ("ShardedMatcher.match: pinned host batch -> H2D -> frg_match per shard -> all-gather -> "
-                   "frg_merge_topk_strided -> D2H" if sharded else
+           "api": ("ShardedMatcher.match: pinned host batch -> H2D -> frg_match per shard -> exchange + merge "
+                   "(config.exchange) -> D2H" if sharded else
                    "frg_match_host via Matcher.match (pinned host buffers)")}
 
     # The reference runs one matcher thread per camera against one shared gallery (peopleCount.py:918-924):
@@ -525,7 +525,12 @@ def ours_arm(args, rank, world):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.rows_total else "weak",
             "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
-            "data": "synthetic", "config": workload_config(args, F, world), "variant": variant,
+            "data": "synthetic", "config": dict(workload_config(args, F, world), **(
+                {"exchange": {"p2p": "frg_exchange_merge_topk: one kernel, NVLink peer-memory push + epoch flags + "
+                                     "merge (no collective call on the data path)",
+                              "nccl": "NCCL all_gather_into_tensor + frg_merge_topk_strided"}.get(
+                                  smatcher.exchange, str(smatcher.exchange)),
+                 "exchange_fallback_reason": smatcher.p2p_error} if sharded else {})), "variant": variant,
             "queries_per_s_raw": value / scale if sharded else value,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": main["launches_per_step"] * args.steps,
@@ -635,6 +640,9 @@ def main():
                          "--batch 4096 --k 10); default: --rows per GPU")
     ap.add_argument("--shard", default="gallery", choices=["gallery", "queries"],
                     help="N>1: row-shard the gallery (all-gather + merge) or replicate it and shard the query stream")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1, row-sharded: fused push+flag+merge kernel over NVLink peer memory, or NCCL "
+                         "all-gather + merge kernel; auto = p2p when the peer mapping can be set up")
     ap.add_argument("--e2e-callers", type=int, default=2,
                     help="host threads of the extra concurrent end-to-end measurement (1 = skip it)")
     ap.add_argument("--no-cpu", action="store_true")

@@ -68,6 +68,9 @@ SIGNATURES = {
                                  C.c_float, _P, _P, _P, _P]),
     "frg_merge_topk_strided": (C.c_int, [C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_float, _P, _P, _P, _P]),
+    "frg_exchange_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "frg_exchange_merge_topk": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, C.c_uint32, _P, _P,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
     "frg_last_launch_count": (C.c_int, []),
     "frg_last_variant": (C.c_char_p, []),
     "frg_profile_enable": (C.c_int, [C.c_int32]),

@@ -760,4 +760,37 @@ int frg_merge_topk_strided(int32_t device, const float* scores, int64_t score_pa
                                   out_rows, out_scores, out_accept, static_cast<cudaStream_t>(stream));
 }
 
+int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap, int64_t* total) {
+  if (world < 1 || world > 64 || nq < 0 || k < 1 || k > FRG_MAX_K || !block_cap || !total) {
+    set_error("exchange_bytes: bad argument");
+    return FRG_ERR_INVALID;
+  }
+  const int64_t cap = ((int64_t(nq) * k * 12 + 255) / 256) * 256;
+  *block_cap = cap;
+  *total = 512 + 2 * int64_t(world) * cap;
+  return FRG_OK;
+}
+
+int frg_exchange_merge_topk(int32_t device, int32_t rank, int32_t world, void* const* peer_bufs,
+                            int64_t block_cap, uint32_t epoch, const int64_t* local_rows,
+                            const float* local_scores, int32_t nq, int32_t k, int32_t metric, float threshold,
+                            int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
+  reset_launches();
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || !peer_bufs || nq < 0 || k < 1 || k > FRG_MAX_K ||
+      (nq > 0 && (!local_rows || !local_scores || !out_rows || !out_scores))) {
+    set_error("exchange_merge_topk: bad argument");
+    return FRG_ERR_INVALID;
+  }
+  if ((int64_t(nq) * k) % 2) { set_error("exchange_merge_topk: nq*k must be even (pad the batch)"); return FRG_ERR_INVALID; }
+  if (block_cap < int64_t(nq) * k * 12 || block_cap % 8) { set_error("exchange_merge_topk: block_cap too small / unaligned"); return FRG_ERR_INVALID; }
+  if (epoch == 0) { set_error("exchange_merge_topk: epochs start at 1 (the flags are zero-initialised)"); return FRG_ERR_INVALID; }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
+  DeviceInfo di;
+  FRG_CHECK(device_info(device, &di));
+  return launch_exchange_merge(reinterpret_cast<unsigned char* const*>(peer_bufs), rank, world, block_cap, epoch,
+                               local_rows, local_scores, nq, k, metric, threshold, di.sm_count, out_rows,
+                               out_scores, out_accept, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -135,6 +135,12 @@ int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
+// exchange.cu: push-to-all-peers + flag + merge in one kernel (multi-GPU tail over NVLink peer memory)
+int launch_exchange_merge(unsigned char* const* peer_bufs, int rank, int world, int64_t block_cap, uint32_t epoch,
+                          const int64_t* local_rows, const float* local_scores, int nq, int k, int metric,
+                          float threshold, int sm_count, int64_t* out_rows, float* out_scores,
+                          uint8_t* out_accept, cudaStream_t st);
+
 // tc_match.cu: tcgen05 filter + exact rescoring.  Cosine: dim multiple of 64 and <= 512 (unit rows);
 // Euclidean: dim 128 / 256 over a raw store's augmented plane (plane_dim = dim + kEuclidPad).
 constexpr int kEuclidPad = 16;      // plane: one more 32-byte group of k (one UMMA K step) for the three bias columns

@@ -4,8 +4,12 @@ One process per GPU (``torch.distributed``; NCCL on GPUs, gloo in the CPU tests)
 contiguous block of gallery rows ``[offset_r, offset_r + n_r)``; a match is
 
     local fused match on every rank           (frg_match, rows returned as GLOBAL rows)
-    -> ONE all-gather of the packed [rows | scores] block, F*k*12 bytes per rank, latency-sized
-    -> k-way merge on every rank               (frg_merge_topk_strided)
+    -> exchange "p2p" (default on GPUs): ONE kernel, frg_exchange_merge_topk - every rank pushes its packed
+       [rows | scores] block (F*k*12 bytes, latency-sized) into every rank's exchange buffer over NVLink
+       peer memory (torch symmetric memory supplies the peer pointers), publishes an epoch flag, waits for
+       the others' flags and merges: no collective-library call on the data path
+    -> exchange "nccl" (fallback; gloo in the CPU tests): ONE all-gather of the block, then the k-way merge
+       kernel on every rank (frg_merge_topk_strided)
 
 Contiguous blocks keep global row order = enrolment order, so the merge's (score desc, row asc)
 order reproduces the reference's strict-'>' tie rule (infrenceServer.py:538-542) across shards.
@@ -89,12 +93,74 @@ class ShardedGallery:
 
 class ShardedMatcher:
     def __init__(self, gallery: ShardedGallery,
-                 local_match: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_match: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 exchange: str = "auto"):
+        """exchange: "p2p" (fused push + flag + merge kernel over NVLink peer memory), "nccl" (all-gather +
+        merge kernel) or "auto" (p2p when the peer mapping can be set up, else nccl; `self.exchange` tells
+        which one runs, `self.p2p_error` why not)."""
         self.g = gallery
         self._local = local_match or self._local_cuda
         self._merge = merge or self._merge_cuda
         self._matcher = Matcher(gallery.store) if gallery.store is not None else None
         self._buf = None
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be auto, p2p or nccl")
+        injected = local_match is not None or merge is not None      # host-logic tests: no device pieces
+        self._want = "nccl" if (injected or gallery.world == 1) else exchange
+        self.exchange = "nccl" if self._want == "nccl" else None      # decided at the first match
+        self.p2p_error: Optional[str] = None
+        self._x = None            # (tensor, handle, block_cap, slots)
+        self._epoch = 0
+
+    # ---- peer-memory exchange ---------------------------------------------------------------------
+    def _p2p_setup(self, Q, F, k):
+        """Collective: (re)allocates the symmetric exchange buffer for F*k slots per rank."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        cap, total = C.c_int64(), C.c_int64()
+        N.check(N.lib.frg_exchange_bytes(self.g.world, F, k, C.byref(cap), C.byref(total)))
+        group = self.g.group if self.g.group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:            # noqa: BLE001  (newer torch: enabled implicitly)
+            pass
+        t = symm.empty(int(total.value), dtype=torch.uint8, device=Q.device)
+        t.zero_()                                    # flags and ticket start at 0; epochs start at 1
+        hdl = symm.rendezvous(t, group)
+        torch.cuda.synchronize(Q.device)
+        dist.barrier(group=self.g.group)             # every buffer is zeroed before anyone pushes into it
+        self._x = (t, hdl, int(cap.value), F * k)
+        self._epoch = 0
+
+    def _p2p_ready(self, Q, F, k) -> bool:
+        if self._want == "nccl" or not getattr(Q, "is_cuda", False):
+            return False
+        if self.exchange == "nccl":
+            return False
+        if self._x is None or self._x[3] < F * k:
+            try:
+                self._p2p_setup(Q, F, k)
+            except Exception as e:                   # noqa: BLE001
+                self.p2p_error = repr(e)
+                if self._want == "p2p":
+                    raise
+                self.exchange = "nccl"
+                return False
+        self.exchange = "p2p"
+        return True
+
+    def _exchange_merge_p2p(self, rows_l, scores_l, F, k, threshold, out):
+        import torch
+        t, hdl, cap, _ = self._x
+        rows, scores, accept = out
+        self._epoch += 1
+        stream = torch.cuda.current_stream(rows_l.device).cuda_stream
+        N.check(N.lib.frg_exchange_merge_topk(
+            rows_l.device.index, self.g.rank, self.g.world, C.c_void_p(int(hdl.buffer_ptrs_dev)), cap,
+            self._epoch & 0xFFFFFFFF, C.c_void_p(rows_l.data_ptr()), C.c_void_p(scores_l.data_ptr()), F, k,
+            N.METRIC_COSINE, float(np.float32(threshold)), C.c_void_p(rows.data_ptr()),
+            C.c_void_p(scores.data_ptr()), C.c_void_p(accept.data_ptr()), C.c_void_p(stream)))
 
     # ---- CUDA pieces ------------------------------------------------------------------------------
     def _local_cuda(self, Q, k, threshold, variant, rows_out, scores_out):
@@ -139,14 +205,17 @@ class ShardedMatcher:
         rows_l = local[:F * k * 8].view(torch.int64).view(F, k)
         scores_l = local[F * k * 8:].view(torch.float32).view(F, k)
         self._local(Q, k, threshold, variant, rows_l, scores_l)
+        if out is None:
+            out = (torch.empty((F, k), dtype=torch.int64, device=Q.device),
+                   torch.empty((F, k), dtype=torch.float32, device=Q.device),
+                   torch.empty((F,), dtype=torch.uint8, device=Q.device))
+        if self.g.world > 1 and self._p2p_ready(Q, F, k):
+            self._exchange_merge_p2p(rows_l, scores_l, F, k, threshold, out)
+            return out
         if self.g.world > 1:
             gathered = torch.empty((self.g.world * block,), dtype=torch.uint8, device=Q.device)
             dist.all_gather_into_tensor(gathered, local, group=self.g.group)
         else:
             gathered = local
-        if out is None:
-            out = (torch.empty((F, k), dtype=torch.int64, device=Q.device),
-                   torch.empty((F, k), dtype=torch.float32, device=Q.device),
-                   torch.empty((F,), dtype=torch.uint8, device=Q.device))
         self._merge(gathered, self.g.world, F, k, threshold, out)
         return out

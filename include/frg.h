@@ -174,6 +174,19 @@ FRG_API int frg_merge_topk_strided(int32_t device, const float* scores, int64_t 
                            int32_t metric, float threshold, int64_t* out_rows, float* out_scores,
                            uint8_t* out_accept, void* stream);
 
+/* ---- the same tail as ONE kernel over NVLink peer memory, no collective library call: every rank
+ * pushes its local [rows | scores] block into slot `rank` of every rank's exchange buffer, publishes the
+ * call's epoch, waits for all ranks' epochs and merges.  peer_bufs: DEVICE array of `world` pointers to
+ * the ranks' exchange buffers, peer-mapped into this process (e.g. torch symmetric memory:
+ * rendezvous(...).buffer_ptrs_dev), each frg_exchange_bytes() large and zero-initialised once.  Collective:
+ * every rank calls it with the same nq, k and epoch = 1, 2, 3, ... (one more per call).  nq*k must be
+ * even.  local_rows / local_scores: this rank's frg_match output (global rows). */
+FRG_API int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap, int64_t* total);
+FRG_API int frg_exchange_merge_topk(int32_t device, int32_t rank, int32_t world, void* const* peer_bufs,
+                            int64_t block_cap, uint32_t epoch, const int64_t* local_rows,
+                            const float* local_scores, int32_t nq, int32_t k, int32_t metric, float threshold,
+                            int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
+
 /* ---- introspection for tests / bench: name and launch count of the kernels the LAST frg_match /
  * frg_match_host on this thread enqueued (bench.py reports it as gpu_launches). */
 FRG_API int frg_last_launch_count(void);

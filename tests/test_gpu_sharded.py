@@ -45,8 +45,11 @@ store = frg.GalleryStore(dim=d, capacity=n, device=local)
 g = ShardedGallery(dim=d, device=local, store=store)
 g.fill_synthetic(n, 1234)
 Q, target = synth.queries(f, n, d)
-rows, scores, acc = ShardedMatcher(g).match(torch.from_numpy(Q).cuda(), k, 0.45)
+Qd = torch.from_numpy(Q).cuda()
+m_nccl = ShardedMatcher(g, exchange="nccl")
+rows, scores, acc = m_nccl.match(Qd, k, 0.45)
 torch.cuda.synchronize()
+assert m_nccl.exchange == "nccl"
 if dist.get_rank() == 0:
     G = synth.gallery(n, d)
     rr, rs, ra = mo.match_topk(Q, G, k + 1, 0.45)
@@ -54,6 +57,26 @@ if dist.get_rank() == 0:
     assert np.abs(scores.cpu().numpy() - rs[:, :k]).max() <= 1e-4
     assert (acc.cpu().numpy().astype(bool) == ra).all()
     print("SHARDED_OK world=%%d" %% dist.get_world_size())
+# the fused peer-memory exchange (push + flag + merge in one kernel, no collective call) gives the same
+# answer bit for bit, call after call (epoch parity reuse), for changing batch sizes (buffer regrowth), and
+# when one rank runs late
+m_p2p = ShardedMatcher(g, exchange="p2p")
+for it, (ff, kk) in enumerate([(64, 10), (64, 10), (64, 10), (8, 1), (200, 5), (64, 10), (2, 16)] * 3):
+    Qi = Qd[:ff] if ff <= f else torch.from_numpy(synth.queries(ff, n, d, seed=77 + it)[0]).cuda()
+    if it %% 4 == dist.get_rank():
+        torch.cuda._sleep(200_000_000)              # ~0.1 s of GPU time: this rank arrives late
+    a = m_p2p.match(Qi, kk, 0.45)
+    b = m_nccl.match(Qi, kk, 0.45)
+    torch.cuda.synchronize()
+    assert m_p2p.exchange == "p2p", m_p2p.p2p_error
+    for x, y in zip(a, b):
+        assert torch.equal(x, y), (it, ff, kk)
+# every rank holds the same merged result
+chk = a[0].clone()
+dist.broadcast(chk, src=0)
+assert torch.equal(chk, a[0])
+if dist.get_rank() == 0:
+    print("P2P_OK world=%%d epochs=%%d" %% (dist.get_world_size(), m_p2p._epoch))
 dist.destroy_process_group()
 '''
 
@@ -69,3 +92,4 @@ def test_sharded_two_ranks_nccl(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK world=2" in r.stdout
+    assert "P2P_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
