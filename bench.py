@@ -526,8 +526,9 @@ def ours_arm(args, rank, world):
             "scaling": "strong" if args.rows_total else "weak",
             "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
             "data": "synthetic", "config": dict(workload_config(args, F, world), **(
-                {"exchange": {"p2p": "frg_exchange_merge_topk: one kernel, NVLink peer-memory push + epoch flags + "
-                                     "merge (no collective call on the data path)",
+                {"exchange": {"p2p": "frg_match_exchange: the select stage pushes each query's top-k to all ranks over "
+                                     "NVLink peer memory as {payload, epoch} packets, one kernel polls + merges "
+                                     "(no collective call on the data path)",
                               "nccl": "NCCL all_gather_into_tensor + frg_merge_topk_strided"}.get(
                                   smatcher.exchange, str(smatcher.exchange)),
                  "exchange_fallback_reason": smatcher.p2p_error} if sharded else {})), "variant": variant,

@@ -43,6 +43,11 @@ class MatchParams(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class Exchange(C.Structure):          # frg_exchange_t
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("peer_bufs", C.c_void_p),
+                ("block_cap", C.c_int64), ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 # every symbol include/frg.h declares: (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -69,8 +74,10 @@ SIGNATURES = {
     "frg_merge_topk_strided": (C.c_int, [C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_float, _P, _P, _P, _P]),
     "frg_exchange_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "frg_exchange_merge_topk": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, C.c_uint32, _P, _P,
-                                          C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
+    "frg_match_exchange": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(MatchParams), C.POINTER(Exchange),
+                                     _P, _P, _P, _P, _P, _P]),
+    "frg_exchange_merge_topk": (C.c_int, [C.c_int32, C.POINTER(Exchange), _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_float, _P, _P, _P, _P]),
     "frg_last_launch_count": (C.c_int, []),
     "frg_last_variant": (C.c_char_p, []),
     "frg_profile_enable": (C.c_int, [C.c_int32]),

@@ -497,8 +497,19 @@ static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq)
   return tc_ok ? FRG_VARIANT_TC_EXACT : FRG_VARIANT_SCAN_F32;
 }
 
+// Row-sharded gallery: where the local result goes next.  active: out_rows / out_scores of the match are the
+// caller's LOCAL scratch, the merged result of all ranks goes to fin_*.
+struct ExchangeTail {
+  bool active = false;
+  XPush x;
+  int64_t* fin_rows = nullptr;
+  float* fin_scores = nullptr;
+  uint8_t* fin_accept = nullptr;
+};
+
 static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, int sm_count,
-                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st,
+                      const ExchangeTail& tail = ExchangeTail()) {
   if (!s->master && s->rows > 0) {
     set_error("match: a bf16-only store has no fp32 master for the exact scan (use FRG_VARIANT_TC_BF16 / AUTO)");
     return FRG_ERR_UNSUPPORTED;
@@ -516,6 +527,9 @@ static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_mat
   int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE && !(p->flags & FRG_QUERY_PRENORMALISED), qn, nullptr, nullptr, nullptr, nullptr, st);
   if (rc == FRG_OK)
     rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
+  if (rc == FRG_OK && tail.active)       // no select stage here: the exchange kernel pushes every query itself
+    rc = launch_exchange_merge(tail.x, out_rows, out_scores, nullptr, nullptr, true, nq, k, p->metric, p->threshold,
+                               sm_count, tail.fin_rows, tail.fin_scores, tail.fin_accept, st);
   g_variant = "scan_f32";
   cudaError_t e = cudaFreeAsync(ws, st);
   if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
@@ -523,7 +537,8 @@ static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_mat
 }
 
 static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, bool rescore,
-                    int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+                    int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st,
+                    const ExchangeTail& tail = ExchangeTail()) {
   const char* why = "";
   const bool euclid = p->metric == FRG_METRIC_EUCLIDEAN;
   if (!s->plane) { set_error("match: the store was created without FRG_STORE_BF16_PLANE"); return FRG_ERR_UNSUPPORTED; }
@@ -542,7 +557,7 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
     return FRG_ERR_UNSUPPORTED;
   }
   if (s->rows > 0x7fffffff) { set_error("match: more than 2^31-1 rows in one shard"); return FRG_ERR_UNSUPPORTED; }
-  if (s->rows == 0) return match_scan(s, q, nq, k, p, sm_count, out_rows, out_scores, out_accept, st);
+  if (s->rows == 0) return match_scan(s, q, nq, k, p, sm_count, out_rows, out_scores, out_accept, st, tail);
   if (rescore && !s->master) {
     set_error("match: FRG_VARIANT_TC_EXACT needs the fp32 master; this store is bf16-only");
     return FRG_ERR_UNSUPPORTED;
@@ -567,7 +582,8 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
   profile_end(st, 1);
   if (rc == FRG_OK)
     rc = launch_tc_match(s, p->metric, qn, qb, eps, nq, k, p->tenant, rescore, p->threshold, p->row_offset, tc_ws,
-                         sm_count, out_rows, out_scores, out_accept, &flagged, &n_flagged, st);
+                         sm_count, tail.active ? tail.x : XPush(), out_rows, out_scores, out_accept, &flagged,
+                         &n_flagged, st);
   if (rc == FRG_OK) {
     // queries whose candidate lists overflowed are redone exactly, inside the same enqueue
     ScanArgs a;
@@ -578,14 +594,20 @@ static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match
                                  out_accept, st);
     profile_end(st, 1);
   }
+  if (rc == FRG_OK && tail.active)
+    // select has pushed every query it settled; the flagged ones (just redone above) are pushed here,
+    // then every query's `world` lists are merged as their packets arrive
+    rc = launch_exchange_merge(tail.x, out_rows, out_scores, flagged, n_flagged, false, nq, k, p->metric,
+                               p->threshold, sm_count, tail.fin_rows, tail.fin_scores, tail.fin_accept, st);
   g_variant = rescore ? "tc_exact" : "tc_bf16";
   cudaError_t e = cudaFreeAsync(ws, st);
   if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
   return rc;
 }
 
-int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
-              int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
+static int match_impl(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream,
+                      const ExchangeTail& tail) {
   reset_launches();
   if (!s || !p || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("match: bad argument"); return FRG_ERR_INVALID; }
   if (k < 1 || k > FRG_MAX_K) { set_error("match: k=%d out of range 1..%d", k, FRG_MAX_K); return FRG_ERR_INVALID; }
@@ -603,15 +625,47 @@ int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_mat
   struct SeqBump { ~SeqBump() { ++g_match_seq; } } bump;      // sampled profiling: every 4th match is bracketed
   switch (pick_variant(s, p, nq)) {
     case FRG_VARIANT_SCAN_F32:
-      return match_scan(s, q, nq, k, p, di.sm_count, out_rows, out_scores, out_accept, st);
+      return match_scan(s, q, nq, k, p, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     case FRG_VARIANT_TC_EXACT:
-      return match_tc(s, q, nq, k, p, true, di.sm_count, out_rows, out_scores, out_accept, st);
+      return match_tc(s, q, nq, k, p, true, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     case FRG_VARIANT_TC_BF16:
-      return match_tc(s, q, nq, k, p, false, di.sm_count, out_rows, out_scores, out_accept, st);
+      return match_tc(s, q, nq, k, p, false, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     default:
       set_error("match: unknown variant %d", p->variant);
       return FRG_ERR_INVALID;
   }
+}
+
+int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+              int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
+  return match_impl(s, q, nq, k, p, out_rows, out_scores, out_accept, stream, ExchangeTail());
+}
+
+static int check_exchange(const frg_exchange_t* x, int32_t nq, int32_t k, XPush* out) {
+  if (!x || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || !x->peer_bufs) {
+    set_error("exchange: bad descriptor");
+    return FRG_ERR_INVALID;
+  }
+  if (x->epoch == 0) { set_error("exchange: epochs start at 1 (the buffers are zero-initialised)"); return FRG_ERR_INVALID; }
+  if (x->block_cap < int64_t(nq) * k * 24 || x->block_cap % 8) { set_error("exchange: block_cap too small / unaligned"); return FRG_ERR_INVALID; }
+  out->peer_bufs = reinterpret_cast<unsigned char* const*>(x->peer_bufs);
+  out->rank = x->rank; out->world = x->world; out->epoch = x->epoch;
+  out->block_cap = x->block_cap; out->nslots = int64_t(nq) * k;
+  return FRG_OK;
+}
+
+int frg_match_exchange(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+                       const frg_exchange_t* x, int64_t* local_rows, float* local_scores,
+                       int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
+  if (nq > 0 && (!local_rows || !local_scores)) { set_error("match_exchange: local scratch is NULL"); return FRG_ERR_INVALID; }
+  if (nq < 0 || k < 1 || k > FRG_MAX_K) { set_error("match_exchange: bad nq / k"); return FRG_ERR_INVALID; }
+  ExchangeTail tail;
+  FRG_CHECK(check_exchange(x, nq, k, &tail.x));
+  tail.active = true;
+  tail.fin_rows = out_rows; tail.fin_scores = out_scores; tail.fin_accept = out_accept;
+  if (nq > 0 && (!out_rows || !out_scores)) { set_error("match_exchange: bad argument"); return FRG_ERR_INVALID; }
+  // the local stage writes this shard's own top-k (global rows) into the scratch; no local decision is kept
+  return match_impl(s, q, nq, k, p, local_rows, local_scores, nullptr, stream, tail);
 }
 
 // Per-thread pinned bounce buffer for results: ONE device->host copy per match instead of three, at full
@@ -765,32 +819,28 @@ int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap,
     set_error("exchange_bytes: bad argument");
     return FRG_ERR_INVALID;
   }
-  const int64_t cap = ((int64_t(nq) * k * 12 + 255) / 256) * 256;
+  const int64_t cap = ((int64_t(nq) * k * 24 + 255) / 256) * 256;      // three 8-byte packets per slot
   *block_cap = cap;
-  *total = 512 + 2 * int64_t(world) * cap;
+  *total = kExchangeHeader + 2 * int64_t(world) * cap;
   return FRG_OK;
 }
 
-int frg_exchange_merge_topk(int32_t device, int32_t rank, int32_t world, void* const* peer_bufs,
-                            int64_t block_cap, uint32_t epoch, const int64_t* local_rows,
+int frg_exchange_merge_topk(int32_t device, const frg_exchange_t* x, const int64_t* local_rows,
                             const float* local_scores, int32_t nq, int32_t k, int32_t metric, float threshold,
                             int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream) {
   reset_launches();
-  if (world < 1 || world > 64 || rank < 0 || rank >= world || !peer_bufs || nq < 0 || k < 1 || k > FRG_MAX_K ||
-      (nq > 0 && (!local_rows || !local_scores || !out_rows || !out_scores))) {
+  if (nq < 0 || k < 1 || k > FRG_MAX_K || (nq > 0 && (!local_rows || !local_scores || !out_rows || !out_scores))) {
     set_error("exchange_merge_topk: bad argument");
     return FRG_ERR_INVALID;
   }
-  if ((int64_t(nq) * k) % 2) { set_error("exchange_merge_topk: nq*k must be even (pad the batch)"); return FRG_ERR_INVALID; }
-  if (block_cap < int64_t(nq) * k * 12 || block_cap % 8) { set_error("exchange_merge_topk: block_cap too small / unaligned"); return FRG_ERR_INVALID; }
-  if (epoch == 0) { set_error("exchange_merge_topk: epochs start at 1 (the flags are zero-initialised)"); return FRG_ERR_INVALID; }
+  XPush xp;
+  FRG_CHECK(check_exchange(x, nq, k, &xp));
   DeviceGuard g(device);
   if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
   DeviceInfo di;
   FRG_CHECK(device_info(device, &di));
-  return launch_exchange_merge(reinterpret_cast<unsigned char* const*>(peer_bufs), rank, world, block_cap, epoch,
-                               local_rows, local_scores, nq, k, metric, threshold, di.sm_count, out_rows,
-                               out_scores, out_accept, static_cast<cudaStream_t>(stream));
+  return launch_exchange_merge(xp, local_rows, local_scores, nullptr, nullptr, true, nq, k, metric, threshold,
+                               di.sm_count, out_rows, out_scores, out_accept, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,112 +1,92 @@
-// Multi-GPU tail as ONE kernel over NVLink peer memory: instead of an NCCL
-// all-gather of every rank's local top-k followed by a merge launch, each rank
-//   1. PUSHES its packed [rows | scores] block into slot `rank` of every rank's exchange buffer
-//      (plain 8-byte stores to peer-mapped pointers: NVLink P2P writes, full NVSwitch bandwidth to all peers),
-//   2. publishes the call's epoch in every rank's flag word (release at system scope, after a
-//      last-CTA-done ticket so that all of its pushes are ordered before the flag),
-//   3. waits until all ranks' flags carry the epoch (acquire at system scope), and
-//   4. merges the `world` lists of each query from its OWN buffer (local HBM reads).
-// The exchange is latency-sized (F*k*12 bytes per rank: 61 KB at F = 1024, k = 5), so what this saves is
-// launches and NCCL's proxy/handshake latency, not bytes.  Buffers are double-buffered by epoch parity:
-// a rank can be at most one call ahead of a peer (call e+1 cannot finish before the peer has published
-// e+1, which it does only after its call e has completed in stream order), so slot parity e&1 is never
-// overwritten while a slower peer still merges call e.
+// Multi-GPU tail over NVLink peer memory, no collective-library call on the data path.
 //
-// Exchange buffer of every rank (identical layout, allocated symmetrically by the host side):
-//   [0, 256)            uint32 flags[world]   flags[r] = last epoch rank r has fully pushed here
-//   [256, 512)          uint32 ticket         local: CTAs of the running call that finished pushing
-//   [512 + (parity*world + r) * block_cap ...)  rank r's block: int64 rows[nq*k], float scores[nq*k]
+// Every rank's exchange buffer (peer-mapped into all ranks, e.g. a torch symmetric-memory allocation) holds,
+// per call parity and source rank, the source's local top-k block as PACKETS: 8-byte words {payload, epoch},
+// stored with single 8-byte writes, so a packet is valid exactly when its epoch word matches - the data is
+// its own flag (the low-latency protocol of collective libraries): no fence, no separate flag, no grid-wide
+// rendezvous.  Three packet planes per block: row low word, row high word, score bits.
+//
+//   * select_rescore_kernel (tc_match.cu) pushes each query's final local top-k to every rank THE MOMENT it
+//     is final - the exchange overlaps the rest of the select kernel and the fallback launch;
+//   * exchange_merge_kernel then pushes what select could not (queries redone by the exact fallback; every
+//     query for variants without a select stage) and merges: one warp per query polls the `world` lists of
+//     that query in its OWN buffer until their packets carry the call's epoch, and folds them.
+//
+// Double buffering by epoch parity: a rank can be at most one call ahead of a peer (it cannot finish call
+// e+1 before the peer has pushed e+1, which the peer does only after its call e completed in stream order),
+// so the packets of parity e&1 are never overwritten while a slower peer still reads call e.
 #include "merge_device.cuh"
 
 namespace frg {
 
-constexpr int kExchangeHeader = 512;
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_packet(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 
+// the packet planes this rank RECEIVES from `src` for the call's parity
+struct PacketLists {
+  const unsigned char* mine;       // this rank's exchange buffer
+  int world;
+  int64_t block_cap, nslots;
+  uint32_t epoch;
+  __device__ __forceinline__ void load(int part, size_t in_part, int64_t* r, float* s) const {
+    const uint2* b = reinterpret_cast<const uint2*>(
+        mine + kExchangeHeader + (size_t(epoch & 1u) * world + part) * size_t(block_cap));
+    uint2 lo, hi, sc;
+    const long long t0 = clock64();
+    // bounded: a dead peer must not hang the GPU for ever (~30 s at 2 GHz, then the kernel traps)
+    while ((lo = ld_packet(b + in_part)).y != epoch) { __nanosleep(100); if (clock64() - t0 > 60000000000ll) __trap(); }
+    while ((hi = ld_packet(b + nslots + in_part)).y != epoch) { __nanosleep(100); if (clock64() - t0 > 60000000000ll) __trap(); }
+    while ((sc = ld_packet(b + 2 * nslots + in_part)).y != epoch) { __nanosleep(100); if (clock64() - t0 > 60000000000ll) __trap(); }
+    *r = int64_t((uint64_t(hi.x) << 32) | uint64_t(lo.x));
+    *s = __uint_as_float(sc.x);
+  }
+};
+
+// push_list / n_push: the queries select did not push (device-resident list, may be null = none);
+// push_all: nothing was pushed yet (variants without a select stage, or results computed elsewhere)
 template <int KMAX>
 __global__ void __launch_bounds__(128)
-exchange_merge_kernel(unsigned char* const* __restrict__ peer_bufs, int rank, int world, int64_t block_cap,
-                      uint32_t epoch, const int64_t* __restrict__ local_rows,
-                      const float* __restrict__ local_scores, int nq, int k, int metric, float threshold,
+exchange_merge_kernel(const XPush x, const int64_t* __restrict__ local_rows,
+                      const float* __restrict__ local_scores, const int* __restrict__ push_list,
+                      const int* __restrict__ n_push, int push_all, int nq, int k, int metric, float threshold,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
                       uint8_t* __restrict__ out_accept) {
-  const int parity = int(epoch & 1u);
-  const size_t slot_off = size_t(kExchangeHeader) + (size_t(parity) * world + rank) * size_t(block_cap);
-  const int64_t nslots = int64_t(nq) * k;
-  const int64_t tid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t nthreads = int64_t(gridDim.x) * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
 
-  // 1. push: rows (8 B each), then scores two at a time (nq*k is even: the host side checks)
-  const uint2* src_r = reinterpret_cast<const uint2*>(local_rows);
-  const uint2* src_s = reinterpret_cast<const uint2*>(local_scores);
-  const int64_t n_r = nslots, n_s = nslots / 2;
-  for (int i = 0; i < world; ++i) {
-    const int peer = (rank + 1 + i) % world;              // start with the neighbour: spreads the first stores
-    uint2* dst_r = reinterpret_cast<uint2*>(peer_bufs[peer] + slot_off);
-    uint2* dst_s = dst_r + n_r;
-    for (int64_t j = tid; j < n_r; j += nthreads) dst_r[j] = src_r[j];
-    for (int64_t j = tid; j < n_s; j += nthreads) dst_s[j] = src_s[j];
-  }
-
-  // 2. all pushes of this rank ordered before its flags: fence per thread, ticket per CTA, last CTA publishes
-  __threadfence_system();
-  __syncthreads();
-  unsigned char* mine = peer_bufs[rank];
-  uint32_t* ticket = reinterpret_cast<uint32_t*>(mine + 256);
-  if (threadIdx.x == 0) {
-    const uint32_t t = atomicAdd(ticket, 1u);
-    if (t == gridDim.x - 1) {
-      *ticket = 0;                                        // for the next call (stream-ordered after this one)
-      __threadfence_system();
-      for (int i = 0; i < world; ++i) {
-        const int peer = (rank + 1 + i) % world;
-        st_release_sys(reinterpret_cast<uint32_t*>(peer_bufs[peer]) + rank, epoch);
-      }
-    }
-    // 3. wait for every rank's block of this call (bounded: a dead peer must not hang the GPU for ever)
-    const uint32_t* flags = reinterpret_cast<const uint32_t*>(mine);
-    const long long t0 = clock64();
-    for (int r = 0; r < world; ++r) {
-      // ">= epoch", wrap-safe: a faster peer may already have published the NEXT call's epoch here
-      while (int32_t(ld_acquire_sys(flags + r) - epoch) < 0) {
-        __nanosleep(200);
-        if (clock64() - t0 > 60000000000ll) __trap();     // ~30 s at 2 GHz
-      }
+  // 1. late pushes: one warp per query, lanes over (peer, slot)
+  const int np = push_all ? nq : (n_push ? *n_push : 0);
+  for (int i = warp; i < np; i += nwarps) {
+    const int q = push_all ? i : push_list[i];
+    for (int c = lane; c < x.world * k; c += 32) {
+      const int peer = c / k, j = c - peer * k;
+      const int64_t slot = int64_t(q) * k + j;
+      xpush_slot(x, (x.rank + 1 + peer) % x.world, slot, local_rows[slot], local_scores[slot]);
     }
   }
-  __syncthreads();
 
-  // 4. merge the `world` best-first lists of each query from the local buffer: one warp per query
-  const unsigned char* base = mine + size_t(kExchangeHeader) + size_t(parity) * world * size_t(block_cap);
-  const int64_t* rows = reinterpret_cast<const int64_t*>(base);
-  const float* scores = reinterpret_cast<const float*>(base + size_t(nslots) * 8);
-  const int warps_per_cta = blockDim.x >> 5;
-  for (int q = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); q < nq; q += gridDim.x * warps_per_cta)
-    merge_one<int64_t, KMAX>(scores, rows, world, nq, k, k, metric, threshold, 0, 0, q, q, block_cap / 4,
-                             block_cap / 8, out_rows, out_scores, out_accept);
+  // 2. merge: one warp per query polls and folds the `world` lists of that query
+  const PacketLists lists{x.peer_bufs[x.rank], x.world, x.block_cap, x.nslots, x.epoch};
+  for (int q = warp; q < nq; q += nwarps)
+    merge_lists<int64_t, KMAX>(lists, x.world, k, k, metric, threshold, 0, 0, q, q, out_rows, out_scores, out_accept);
 }
 
-int launch_exchange_merge(unsigned char* const* peer_bufs, int rank, int world, int64_t block_cap, uint32_t epoch,
-                          const int64_t* local_rows, const float* local_scores, int nq, int k, int metric,
+int launch_exchange_merge(const XPush& x, const int64_t* local_rows, const float* local_scores,
+                          const int* push_list, const int* n_push, bool push_all, int nq, int k, int metric,
                           float threshold, int sm_count, int64_t* out_rows, float* out_scores,
                           uint8_t* out_accept, cudaStream_t st) {
   if (nq <= 0) return FRG_OK;
-  // every CTA spins on the flags: the whole grid must be resident at once
   int grid = (nq + 3) / 4;
-  if (grid > sm_count) grid = sm_count;
+  if (grid > 4 * sm_count) grid = 4 * sm_count;
   if (grid < 1) grid = 1;
-#define FRG_XM(K)                                                                                              \
-  exchange_merge_kernel<K><<<grid, 128, 0, st>>>(peer_bufs, rank, world, block_cap, epoch, local_rows,         \
-                                                 local_scores, nq, k, metric, threshold, out_rows, out_scores, \
-                                                 out_accept)
+  const int pa = push_all ? 1 : 0;
+#define FRG_XM(K)                                                                                                 \
+  exchange_merge_kernel<K><<<grid, 128, 0, st>>>(x, local_rows, local_scores, push_list, n_push, pa, nq, k, metric, \
+                                                 threshold, out_rows, out_scores, out_accept)
   if (k == 1) FRG_XM(1);
   else if (k <= 4) FRG_XM(4);
   else if (k <= 8) FRG_XM(8);

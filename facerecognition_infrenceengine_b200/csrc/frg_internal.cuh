@@ -135,9 +135,29 @@ int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq
                      int metric, float threshold, int64_t row_offset, bool finalize_euclid,
                      int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
-// exchange.cu: push-to-all-peers + flag + merge in one kernel (multi-GPU tail over NVLink peer memory)
-int launch_exchange_merge(unsigned char* const* peer_bufs, int rank, int world, int64_t block_cap, uint32_t epoch,
-                          const int64_t* local_rows, const float* local_scores, int nq, int k, int metric,
+// exchange.cu: multi-GPU tail over NVLink peer memory.  XPush describes where this rank's results go:
+// into slot `rank` of every rank's exchange buffer, as 8-byte {payload, epoch} packets.
+constexpr int kExchangeHeader = 512;
+struct XPush {
+  unsigned char* const* peer_bufs = nullptr;   // DEVICE array of `world` peer-mapped buffer pointers; null = no exchange
+  int rank = 0, world = 1;
+  uint32_t epoch = 0;                          // 1, 2, 3, ... one more per collective call; never 0
+  int64_t block_cap = 0;                       // bytes per (parity, source rank) block >= nslots * 24
+  int64_t nslots = 0;                          // nq * k
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void xpush_slot(const XPush& x, int peer, int64_t slot, int64_t row, float score) {
+  uint2* b = reinterpret_cast<uint2*>(x.peer_bufs[peer] + kExchangeHeader +
+                                      (size_t(x.epoch & 1u) * x.world + x.rank) * size_t(x.block_cap));
+  const uint64_t r = uint64_t(row);
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(b + slot), "r"(uint32_t(r)), "r"(x.epoch) : "memory");
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(b + x.nslots + slot), "r"(uint32_t(r >> 32)), "r"(x.epoch) : "memory");
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(b + 2 * x.nslots + slot), "r"(__float_as_uint(score)), "r"(x.epoch) : "memory");
+}
+#endif
+// push_list / n_push: device-resident list of the queries still to be pushed (null = none); push_all: all
+int launch_exchange_merge(const XPush& x, const int64_t* local_rows, const float* local_scores,
+                          const int* push_list, const int* n_push, bool push_all, int nq, int k, int metric,
                           float threshold, int sm_count, int64_t* out_rows, float* out_scores,
                           uint8_t* out_accept, cudaStream_t st);
 
@@ -152,10 +172,11 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
                                uint32_t** keys, int** cand_total, int** n_flagged);
 // metric cosine: qb = [nq][dim] bf16 unit queries, eps == nullptr (constant bound).
 // metric euclidean: qb = [nq][dim + kEuclidQPad] augmented image, eps[nq] per-query bounds.
+// push: the select stage sends every query's final top-k straight to all ranks (XPush::peer_bufs != null)
 int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
-                    unsigned char* ws, int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
-                    int** flagged_out, int** n_flagged_out, cudaStream_t st);
+                    unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
+                    uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st);
 
 // first_match.cu
 int launch_first_match(const float* master, const int32_t* tags, int64_t rows, int dim, const float* qn, int nq,

@@ -15,18 +15,29 @@ template <typename RowT> struct RowLimits;
 template <> struct RowLimits<int32_t> { static __device__ __forceinline__ int32_t none() { return 0x7fffffff; } };
 template <> struct RowLimits<int64_t> { static __device__ __forceinline__ int64_t none() { return 0x7fffffffffffffffLL; } };
 
+// where the partial lists of a merge come from: plain arrays [part][slot] ...
+template <typename RowT>
+struct ArrayLists {
+  const float* scores;
+  const RowT* rows;
+  int64_t score_stride, row_stride;          // elements between consecutive parts
+  __device__ __forceinline__ void load(int part, size_t in_part, RowT* r, float* s) const {
+    *r = rows[size_t(part) * row_stride + in_part];
+    *s = scores[size_t(part) * score_stride + in_part];
+  }
+};
+
 // Internal score convention: larger is better.  Euclidean lists arrive either as distances
 // (external, frg_merge_topk) or as -d^2 (internal partials, finalize_euclid): both are mapped to
 // "larger is better" on load and mapped back on store.
 // One warp folds the `parts` best-first lists of one query.  `slot` addresses the partial lists; with
 // an index list (flagged queries) it differs from `q`, the query the result belongs to.
-template <typename RowT, int KMAX>
-__device__ __forceinline__ void merge_one(const float* __restrict__ scores, const RowT* __restrict__ rows,
-                                          int parts, int nq, int k_in, int k_out, int metric, float threshold,
-                                          int64_t row_offset, int internal_euclid, int slot, int q,
-                                          int64_t score_stride, int64_t row_stride,
-                                          int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
-                                          uint8_t* __restrict__ out_accept) {
+// Lists: ArrayLists, or exchange.cu's packet reader (entries that arrive over NVLink while the warp waits).
+template <typename RowT, int KMAX, typename Lists>
+__device__ __forceinline__ void merge_lists(const Lists& lists, int parts, int k_in, int k_out, int metric,
+                                            float threshold, int64_t row_offset, int internal_euclid, int slot,
+                                            int q, int64_t* __restrict__ out_rows,
+                                            float* __restrict__ out_scores, uint8_t* __restrict__ out_accept) {
   const int lane = threadIdx.x & 31;
   const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
   const float sentinel = euclid ? -INFINITY : kNoScore;
@@ -48,9 +59,7 @@ __device__ __forceinline__ void merge_one(const float* __restrict__ scores, cons
       s[u] = sentinel;
       if (c < total) {
         const int part = c / k_in, j = c - part * k_in;
-        const size_t in_part = size_t(slot) * k_in + j;
-        r[u] = rows[size_t(part) * row_stride + in_part];
-        s[u] = scores[size_t(part) * score_stride + in_part];
+        lists.load(part, size_t(slot) * k_in + j, &r[u], &s[u]);
       }
     }
 #pragma unroll
@@ -104,6 +113,19 @@ __device__ __forceinline__ void merge_one(const float* __restrict__ scores, cons
       }
     }
   }
+}
+
+template <typename RowT, int KMAX>
+__device__ __forceinline__ void merge_one(const float* __restrict__ scores, const RowT* __restrict__ rows,
+                                          int parts, int nq, int k_in, int k_out, int metric, float threshold,
+                                          int64_t row_offset, int internal_euclid, int slot, int q,
+                                          int64_t score_stride, int64_t row_stride,
+                                          int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
+                                          uint8_t* __restrict__ out_accept) {
+  (void)nq;
+  const ArrayLists<RowT> lists{scores, rows, score_stride, row_stride};
+  merge_lists<RowT, KMAX>(lists, parts, k_in, k_out, metric, threshold, row_offset, internal_euclid, slot, q,
+                          out_rows, out_scores, out_accept);
 }
 
 }  // namespace frg

@@ -681,7 +681,8 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
                       const float* __restrict__ eps,
                       const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
-                      uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged) {
+                      uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged,
+                      const XPush x) {
   __shared__ int keep_row[kMaxKeep];
   __shared__ float keep_sc[kMaxKeep];
   __shared__ float top_s[kSelectWarps][FRG_MAX_K];
@@ -744,9 +745,13 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
     // bf16 gallery mode: report the coarse scores themselves (own tolerance)
     if (w == 0 && lane < k) {
       const bool filled = top_ix >= 0 && top_sc > kNoScore;
-      out_rows[size_t(q) * k + lane] = filled ? int64_t(top_ix) + row_offset : int64_t(kNoRow);
-      out_scores[size_t(q) * k + lane] = filled ? top_sc : kNoScore;
+      const int64_t r_out = filled ? int64_t(top_ix) + row_offset : int64_t(kNoRow);
+      const float s_out = filled ? top_sc : kNoScore;
+      out_rows[size_t(q) * k + lane] = r_out;
+      out_scores[size_t(q) * k + lane] = s_out;
       if (lane == 0 && out_accept) out_accept[q] = (filled && top_sc >= threshold) ? 1 : 0;
+      if (x.peer_bufs)
+        for (int i = 0; i < x.world; ++i) xpush_slot(x, (x.rank + 1 + i) % x.world, int64_t(q) * k + lane, r_out, s_out);
     }
     return;
   }
@@ -831,18 +836,18 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   for (int j = 0; j < k; ++j) {
     float bs; int32_t br;
     warp_pop_best<K>(sc, ix, lane, sentinel, &bs, &br);
+    const bool filled = br != 0x7fffffff;
+    const int64_t r_out = filled ? int64_t(br) + row_offset : int64_t(kNoRow);
+    const float s_out = EUCLID ? (filled ? __fsqrt_rn(fmaxf(-bs, 0.f)) : INFINITY) : (filled ? bs : kNoScore);
     if (lane == 0) {
-      const bool filled = br != 0x7fffffff;
-      out_rows[size_t(q) * k + j] = filled ? int64_t(br) + row_offset : int64_t(kNoRow);
-      if (EUCLID) {
-        const float d = filled ? __fsqrt_rn(fmaxf(-bs, 0.f)) : INFINITY;
-        out_scores[size_t(q) * k + j] = d;
-        if (j == 0 && out_accept) out_accept[q] = (filled && d <= threshold) ? 1 : 0;
-      } else {
-        out_scores[size_t(q) * k + j] = filled ? bs : kNoScore;
-        if (j == 0 && out_accept) out_accept[q] = (filled && bs >= threshold) ? 1 : 0;
-      }
+      out_rows[size_t(q) * k + j] = r_out;
+      out_scores[size_t(q) * k + j] = s_out;
+      if (j == 0 && out_accept) out_accept[q] = (filled && (EUCLID ? s_out <= threshold : bs >= threshold)) ? 1 : 0;
     }
+    // row-sharded gallery: this slot is final - send it to every rank now (lane p -> rank p), unless the
+    // query goes to the exact fallback, whose result the exchange kernel pushes
+    if (x.peer_bufs && !overflow)
+      for (int pr = lane; pr < x.world; pr += 32) xpush_slot(x, pr, int64_t(q) * k + j, r_out, s_out);
   }
   if (overflow && lane == 0) flagged[atomicAdd(n_flagged, 1)] = q;
 }
@@ -1047,8 +1052,8 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
 // Leaves the overflowed queries in (flagged, n_flagged) for the caller's exact fallback pass.
 int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
-                    unsigned char* ws, int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
-                    int** flagged_out, int** n_flagged_out, cudaStream_t st) {
+                    unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
+                    uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st) {
   const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
   if (euclid != (s->plane_dim != s->dim)) { set_error("tc_match: metric does not fit the store's scan plane"); return FRG_ERR_UNSUPPORTED; }
   // columns of the query tile: dim, or dim + kEuclidQPad (its last k-block meets the plane's 16-column pad block)
@@ -1112,7 +1117,8 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
 #define FRG_SELECT_M(KK, EU)                                                                                    \
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
   select_rescore_kernel<KK, EU><<<grid, kSelectWarps * 32, 0, st>>>(dense, cnt, pl.stage_entries, nq, k,        \
-      s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged)
+      s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged, \
+      push)
 #define FRG_SELECT(KK)                                                                                          \
   if (euclid) { FRG_SELECT_M(KK, true); } else { FRG_SELECT_M(KK, false); }
   switch (pl.kreg) {

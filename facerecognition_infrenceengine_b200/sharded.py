@@ -4,10 +4,11 @@ One process per GPU (``torch.distributed``; NCCL on GPUs, gloo in the CPU tests)
 contiguous block of gallery rows ``[offset_r, offset_r + n_r)``; a match is
 
     local fused match on every rank           (frg_match, rows returned as GLOBAL rows)
-    -> exchange "p2p" (default on GPUs): ONE kernel, frg_exchange_merge_topk - every rank pushes its packed
-       [rows | scores] block (F*k*12 bytes, latency-sized) into every rank's exchange buffer over NVLink
-       peer memory (torch symmetric memory supplies the peer pointers), publishes an epoch flag, waits for
-       the others' flags and merges: no collective-library call on the data path
+    -> exchange "p2p" (default on GPUs): frg_match_exchange - the select stage of the local match pushes each
+       query's top-k into every rank's exchange buffer over NVLink peer memory the moment it is final
+       (8-byte {payload, epoch} packets: the data is its own flag; torch symmetric memory supplies the peer
+       pointers), and one last kernel merges every query's `world` lists as their packets arrive:
+       no collective-library call on the data path
     -> exchange "nccl" (fallback; gloo in the CPU tests): ONE all-gather of the block, then the k-way merge
        kernel on every rank (frg_merge_topk_strided)
 
@@ -150,16 +151,21 @@ class ShardedMatcher:
         self.exchange = "p2p"
         return True
 
-    def _exchange_merge_p2p(self, rows_l, scores_l, F, k, threshold, out):
+    def _match_exchange_p2p(self, Q, rows_l, scores_l, F, k, threshold, variant, out):
+        """frg_match_exchange: local match whose select stage pushes each query's top-k to all ranks as it
+        becomes final, then the push-stragglers + poll + merge kernel - one enqueue, no collective call."""
         import torch
         t, hdl, cap, _ = self._x
         rows, scores, accept = out
         self._epoch += 1
-        stream = torch.cuda.current_stream(rows_l.device).cuda_stream
-        N.check(N.lib.frg_exchange_merge_topk(
-            rows_l.device.index, self.g.rank, self.g.world, C.c_void_p(int(hdl.buffer_ptrs_dev)), cap,
-            self._epoch & 0xFFFFFFFF, C.c_void_p(rows_l.data_ptr()), C.c_void_p(scores_l.data_ptr()), F, k,
-            N.METRIC_COSINE, float(np.float32(threshold)), C.c_void_p(rows.data_ptr()),
+        x = N.Exchange(rank=self.g.rank, world=self.g.world, peer_bufs=int(hdl.buffer_ptrs_dev), block_cap=cap,
+                       epoch=((self._epoch - 1) % 0xFFFFFFFF) + 1, reserved=0)
+        p = N.MatchParams(metric=N.METRIC_COSINE, variant=N.VARIANTS[variant], threshold=float(np.float32(threshold)),
+                          tenant=-1, row_offset=int(self.g.offset), flags=0, reserved=0)
+        stream = torch.cuda.current_stream(Q.device).cuda_stream
+        N.check(N.lib.frg_match_exchange(
+            self.g.store.handle, C.c_void_p(Q.data_ptr()), F, k, C.byref(p), C.byref(x),
+            C.c_void_p(rows_l.data_ptr()), C.c_void_p(scores_l.data_ptr()), C.c_void_p(rows.data_ptr()),
             C.c_void_p(scores.data_ptr()), C.c_void_p(accept.data_ptr()), C.c_void_p(stream)))
 
     # ---- CUDA pieces ------------------------------------------------------------------------------
@@ -204,14 +210,14 @@ class ShardedMatcher:
         local = torch.empty((block,), dtype=torch.uint8, device=Q.device)
         rows_l = local[:F * k * 8].view(torch.int64).view(F, k)
         scores_l = local[F * k * 8:].view(torch.float32).view(F, k)
-        self._local(Q, k, threshold, variant, rows_l, scores_l)
         if out is None:
             out = (torch.empty((F, k), dtype=torch.int64, device=Q.device),
                    torch.empty((F, k), dtype=torch.float32, device=Q.device),
                    torch.empty((F,), dtype=torch.uint8, device=Q.device))
         if self.g.world > 1 and self._p2p_ready(Q, F, k):
-            self._exchange_merge_p2p(rows_l, scores_l, F, k, threshold, out)
+            self._match_exchange_p2p(Q, rows_l, scores_l, F, k, threshold, variant, out)
             return out
+        self._local(Q, k, threshold, variant, rows_l, scores_l)
         if self.g.world > 1:
             gathered = torch.empty((self.g.world * block,), dtype=torch.uint8, device=Q.device)
             dist.all_gather_into_tensor(gathered, local, group=self.g.group)

@@ -174,16 +174,30 @@ FRG_API int frg_merge_topk_strided(int32_t device, const float* scores, int64_t 
                            int32_t metric, float threshold, int64_t* out_rows, float* out_scores,
                            uint8_t* out_accept, void* stream);
 
-/* ---- the same tail as ONE kernel over NVLink peer memory, no collective library call: every rank
- * pushes its local [rows | scores] block into slot `rank` of every rank's exchange buffer, publishes the
- * call's epoch, waits for all ranks' epochs and merges.  peer_bufs: DEVICE array of `world` pointers to
- * the ranks' exchange buffers, peer-mapped into this process (e.g. torch symmetric memory:
- * rendezvous(...).buffer_ptrs_dev), each frg_exchange_bytes() large and zero-initialised once.  Collective:
- * every rank calls it with the same nq, k and epoch = 1, 2, 3, ... (one more per call).  nq*k must be
- * even.  local_rows / local_scores: this rank's frg_match output (global rows). */
+/* ---- the same tail over NVLink peer memory, no collective-library call on the data path.
+ * Every rank owns an exchange buffer of frg_exchange_bytes() bytes, zero-initialised once and peer-mapped
+ * into all ranks (e.g. torch symmetric memory: rendezvous(...).buffer_ptrs_dev is `peer_bufs`).  A rank's
+ * local top-k travels as 8-byte {payload, epoch} packets written straight into slot `rank` of every rank's
+ * buffer; a packet is valid when its epoch word matches, so there is no fence, flag or rendezvous.
+ * Collective: every rank makes the same call with the same nq, k and epoch = 1, 2, 3, ... */
+typedef struct frg_exchange_t {
+  int32_t rank, world;
+  void* const* peer_bufs;  /* DEVICE array of `world` device pointers */
+  int64_t block_cap;       /* from frg_exchange_bytes() */
+  uint32_t epoch;          /* one more per call, never 0 */
+  uint32_t reserved;
+} frg_exchange_t;
 FRG_API int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap, int64_t* total);
-FRG_API int frg_exchange_merge_topk(int32_t device, int32_t rank, int32_t world, void* const* peer_bufs,
-                            int64_t block_cap, uint32_t epoch, const int64_t* local_rows,
+/* frg_match on this rank's shard + exchange + merge in one enqueue: the select stage pushes every query's
+ * top-k to all ranks the moment it is final; a last kernel pushes the stragglers (queries redone by the
+ * exact fallback) and merges each query's `world` lists as their packets arrive.  local_rows / local_scores:
+ * [nq][k] device scratch for this shard's own result (global rows: params->row_offset).  out_*: the merged
+ * result, identical on every rank. */
+FRG_API int frg_match_exchange(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
+                       const frg_exchange_t* x, int64_t* local_rows, float* local_scores,
+                       int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
+/* Exchange + merge of results computed elsewhere ([nq][k] local lists, global rows). */
+FRG_API int frg_exchange_merge_topk(int32_t device, const frg_exchange_t* x, const int64_t* local_rows,
                             const float* local_scores, int32_t nq, int32_t k, int32_t metric, float threshold,
                             int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
 

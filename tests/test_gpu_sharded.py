@@ -71,6 +71,22 @@ for it, (ff, kk) in enumerate([(64, 10), (64, 10), (64, 10), (8, 1), (200, 5), (
     assert m_p2p.exchange == "p2p", m_p2p.p2p_error
     for x, y in zip(a, b):
         assert torch.equal(x, y), (it, ff, kk)
+# variants without a select stage: the exchange kernel pushes every query itself
+a = m_p2p.match(Qd, 5, 0.45, variant="scan_f32"); b = m_nccl.match(Qd, 5, 0.45, variant="scan_f32")
+torch.cuda.synchronize()
+for x, y in zip(a, b):
+    assert torch.equal(x, y)
+# adversarial shard: 3000 copies of one template land on the LAST rank; the queries near it overflow that
+# rank's candidate lists, are redone by its exact fallback, and reach the other ranks through the late push
+dupe = synth.unit_rows(np.arange(1), d, 4242, synth.STREAM_IMPOSTOR)
+g.append_local(np.repeat(dupe, 3000, axis=0), prenormalised=True)
+Qx = torch.from_numpy(np.concatenate([dupe, dupe + np.float32(1e-3), Q[:14]])).cuda()
+for kk in (1, 16):
+    a = m_p2p.match(Qx, kk, 0.45); b = m_nccl.match(Qx, kk, 0.45)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y), kk
+    assert a[0][0].tolist() == list(range(n, n + kk)), a[0][0].tolist()      # ties -> earliest rows, global numbering
 # every rank holds the same merged result
 chk = a[0].clone()
 dist.broadcast(chk, src=0)

@@ -104,3 +104,16 @@ def test_shard_bounds_cover_everything():
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
     b = shard_bounds(10, 4)
     assert [owner_of(r, b) for r in range(10)] == [0, 0, 1, 1, 1, 2, 2, 3, 3, 3]
+
+
+def test_matcher_wiring_without_injected_pieces():
+    """The CUDA pieces are bound methods of the matcher itself; world = 1 never sets up an exchange."""
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+    g = ShardedGallery(dim=512, device=0, store=None, rank=0, world=1)
+    m = ShardedMatcher(g)
+    assert m.exchange == "nccl" and callable(m._local) and callable(m._merge)
+    for name in ("_local_cuda", "_merge_cuda", "_accept_scratch", "_p2p_setup", "_p2p_ready", "_match_exchange_p2p"):
+        assert callable(getattr(m, name))
+    import pytest
+    with pytest.raises(ValueError):
+        ShardedMatcher(g, exchange="smoke-signals")
