@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import threading
 import time
-from datetime import datetime
+from datetime import datetime, timezone
 from typing import Dict, Iterable, List, Optional
 
 import numpy as np
@@ -24,6 +24,11 @@ from .gallery import GalleryStore
 
 
 # ---- eligibility filters: the Mongo queries of the loaders, restated on dict records ----------
+def _utcnow() -> datetime:
+    """Naive UTC timestamp, what the reference's `datetime.utcnow()` returns (infrenceServer.py:112,226)."""
+    return datetime.now(timezone.utc).replace(tzinfo=None)
+
+
 def eligible_employee(doc: Dict) -> bool:
     """infrenceServer.py:95-99 == peopleCount.py:738-742."""
     return (doc.get("status") == "active" and doc.get("blacklisted") is False
@@ -98,7 +103,7 @@ class EmbeddingManager:
     def _initial_load(self):
         """infrenceServer.py:62-91 / peopleCount.py:716-734."""
         self._load_updated_embeddings(self.source.employee_docs(), self.source.visitor_docs())
-        self.last_sync_time = datetime.utcnow()
+        self.last_sync_time = _utcnow()
         self.is_initial_load = False
 
     def _load_updated_embeddings(self, employees: Iterable[Dict], visitors: Iterable[Dict]):
@@ -137,10 +142,10 @@ class EmbeddingManager:
             self._remove_inactive_employees()
             if employees or visitors:
                 self._load_updated_embeddings(employees, visitors)
-            self.last_sync_time = datetime.utcnow()
+            self.last_sync_time = _utcnow()
         else:
             self._load_updated_embeddings(self.source.employee_docs(), self.source.visitor_docs())
-            self.last_sync_time = datetime.utcnow()
+            self.last_sync_time = _utcnow()
 
     def force_sync(self):
         """infrenceServer.py:382-384."""

@@ -69,3 +69,47 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "/root/reference" not in src, f
+
+
+C_CONSUMER = r'''
+#include <stdio.h>
+#include <string.h>
+#include "frg.h"
+
+int main(void) {
+  frg_match_params_t p;
+  frg_exchange_t x;
+  frg_store* s = NULL;
+  int32_t n = -1;
+  int rc;
+  memset(&p, 0, sizeof p);
+  memset(&x, 0, sizeof x);
+  printf("abi=%d params=%u stats=%u exchange=%u\n", frg_abi_version(), (unsigned)sizeof p,
+         (unsigned)sizeof(frg_store_stats_t), (unsigned)sizeof x);
+  rc = frg_device_count(&n);                 /* no GPU here: an error code and a message, not a crash */
+  printf("device_count rc=%d n=%d err=%s\n", rc, (int)n, frg_last_error());
+  rc = frg_store_create(0, 512, 16, FRG_STORE_BF16_PLANE, &s);
+  printf("store_create rc=%d\n", rc);
+  if (rc == FRG_OK) frg_store_destroy(s);
+  return 0;
+}
+'''
+
+
+def test_header_is_plain_c_and_links_from_c(native, tmp_path):
+    """include/frg.h is the boundary a non-Python host would bind: it must compile as strict C99 and a
+    C program must link against libfrg.so alone (no Python, no torch, no libcuda at link time)."""
+    src = tmp_path / "consumer.c"
+    src.write_text(C_CONSUMER)
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(native.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-lfrg", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "abi=1 params=32 stats=56 exchange=32" in out.stdout
+    import torch
+    if not torch.cuda.is_available():
+        assert "device_count rc=2" in out.stdout and "store_create rc=0" not in out.stdout

@@ -240,7 +240,7 @@ def test_store_semantics_follow_the_dict(frg, variant):
 
 def test_embedding_manager_replays_reference_scenario(frg, golden):
     """tests/golden/managers.npz: ids order and loaded matrices of BOTH reference managers."""
-    from datetime import datetime, timedelta
+    from datetime import datetime, timedelta, timezone
     g = golden("managers.npz")
     st = g["stored"]
     A, B = "a" * 24, "b" * 24
@@ -275,7 +275,7 @@ def test_embedding_manager_replays_reference_scenario(frg, golden):
     s = m.get_stats()
     assert [s["total_embeddings"], s["employees"], s["visitors"]] == list(g["ref_live_load_stats"])
     assert s["initial_load_complete"] and s["last_sync"]
-    later = datetime.utcnow() + timedelta(seconds=5)
+    later = datetime.now(timezone.utc).replace(tzinfo=None) + timedelta(seconds=5)
     E[1]["embedding"] = st[30]; E[1]["lastUpdated"] = later
     E[0]["status"] = "inactive"
     E.append(dict(emp(12), lastUpdated=later))
@@ -283,7 +283,7 @@ def test_embedding_manager_replays_reference_scenario(frg, golden):
     E[3]["status"] = "active"; E[3]["lastUpdated"] = later
     m.force_sync()
     same(m, "ref_live_sync1")
-    E[0]["status"] = "active"; E[0]["lastUpdated"] = datetime.utcnow() + timedelta(seconds=10)
+    E[0]["status"] = "active"; E[0]["lastUpdated"] = datetime.now(timezone.utc).replace(tzinfo=None) + timedelta(seconds=10)
     m.force_sync()
     same(m, "ref_live_sync2")
     ids, _, tags = m.store.snapshot_arrays()
