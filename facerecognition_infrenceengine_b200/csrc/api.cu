@@ -1,6 +1,7 @@
 // C ABI of libfrg.so (include/frg.h): store life-cycle, ingest, match dispatch, merge.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -22,6 +23,11 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d: %s", int(e), cudaGetErrorString(e), file, line, what);
   return e == cudaErrorMemoryAllocation ? FRG_ERR_NOMEM : FRG_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("FRG_PDL"); return !e || atoi(e) != 0; }();
+  return on;
 }
 
 void note_launch(const char* variant) {

@@ -57,6 +57,7 @@ exchange_merge_kernel(const XPush x, const int64_t* __restrict__ local_rows,
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
+  pdl_wait();             // the local match's results and its list of late queries
 
   // 1. late pushes: one warp per query, lanes over (peer, slot)
   const int np = push_all ? nq : (n_push ? *n_push : 0);
@@ -85,8 +86,8 @@ int launch_exchange_merge(const XPush& x, const int64_t* local_rows, const float
   if (grid < 1) grid = 1;
   const int pa = push_all ? 1 : 0;
 #define FRG_XM(K)                                                                                                 \
-  exchange_merge_kernel<K><<<grid, 128, 0, st>>>(x, local_rows, local_scores, push_list, n_push, pa, nq, k, metric, \
-                                                 threshold, out_rows, out_scores, out_accept)
+  FRG_CUDA(launch_kernel(exchange_merge_kernel<K>, dim3(grid), dim3(128), 0, st, true, x, local_rows, local_scores,  \
+                         push_list, n_push, pa, nq, k, metric, threshold, out_rows, out_scores, out_accept))
   if (k == 1) FRG_XM(1);
   else if (k <= 4) FRG_XM(4);
   else if (k <= 8) FRG_XM(8);

@@ -41,6 +41,32 @@ enum ProfileStage { kStagePrep = 0, kStagePrepass = 1, kStageFloor = 2, kStageDo
 void profile_begin(cudaStream_t st, int stage = kStageDominant);
 void profile_end(cudaStream_t st, int launches);
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The kernels of one match run back to back on one stream.  A kernel launched with the programmatic-
+// serialization attribute may be SCHEDULED while its predecessor is still running (once every CTA of the
+// predecessor has called pdl_trigger() or exited): its launch latency and prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the predecessor's tail.  pdl_wait() then blocks until the
+// predecessor has completed and its writes are visible - it precedes every read of earlier results.
+// Without the attribute both calls are no-ops.  FRG_PDL=0 turns the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 struct DeviceInfo {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;

@@ -13,6 +13,7 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
                          float* __restrict__ qn, __nv_bfloat16* __restrict__ qb,
                          uint32_t* __restrict__ group_keys, int* __restrict__ cand_total,
                          int* __restrict__ n_flagged) {
+  pdl_trigger();          // the next kernel of the match may be scheduled now (it waits before reading)
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= nq) return;
@@ -64,6 +65,7 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
                               float* __restrict__ qn, __nv_bfloat16* __restrict__ q_aug, float* __restrict__ eps,
                               uint32_t* __restrict__ group_keys, uint32_t none_key, int* __restrict__ cand_total,
                               int* __restrict__ n_flagged) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= nq) return;

@@ -236,6 +236,8 @@ scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restric
   float* l_sc = reinterpret_cast<float*>(smem_raw);
   int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
   __shared__ int is_last;
+  pdl_wait();             // the select kernel's list of flagged queries
+  pdl_trigger();
   const int nf = ctl[0];
   for (int q0 = 0; q0 < nf; q0 += QB) {
     const int nq_pass = nf - q0 < QB ? nf - q0 : QB;
@@ -352,19 +354,22 @@ static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int
   if (a.master && a.metric == FRG_METRIC_EUCLIDEAN) {
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_EUCLIDEAN, KMAX, float>;
     FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
-                                              threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+    FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
+                           a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
+                           out_accept));
   } else if (a.master) {
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float>;
     FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    kern<<<grid, kScanWarps * 32, smem, st>>>(a.master, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
-                                              threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+    FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
+                           a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
+                           out_accept));
   } else {
     // bf16-only store: the exact re-do reads the scan plane (fp32 query x bf16 row, fp32 accumulation)
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, __nv_bfloat16>;
     FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    kern<<<grid, kScanWarps * 32, smem, st>>>(a.plane, a.tags, a.rows, a.qn, a.nq, flagged, ctl, a.k, a.tenant,
-                                              threshold, row_offset, ps, pi, out_rows, out_scores, out_accept);
+    FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.plane, a.tags, a.rows, a.qn,
+                           a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
+                           out_accept));
   }
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());

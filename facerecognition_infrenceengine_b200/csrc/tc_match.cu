@@ -332,6 +332,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // everything above ran while the previous kernel of the match was still finishing (PDL); from here on
+  // its results are read (query image, group maxima, counters)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -691,6 +695,8 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const int q = blockIdx.x;
+  pdl_wait();             // the filter kernel's candidate lists
+  pdl_trigger();
 
   const int total = cand_total[q];
   if (total > dense_cap) {                           // also set by a poisoned total (segment overflow)
@@ -784,9 +790,10 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   const bool overflow = m > kMaxKeep;            // too many survivors: rescored in part, then redone by the fallback
   if (overflow) m = kMaxKeep;
 
-  // (c) exact fp32 rescoring, 4 rows in flight per warp (coalesced 16-byte loads, same element ->
-  //     lane mapping and summation order as the streaming scan)
-  constexpr int kRescoreRows = 4;
+  // (c) exact fp32 rescoring, 2 rows per warp and round - the typical k + 3 survivors occupy all four
+  //     warps - with the row's 16-byte loads unrolled four deep (a 512-d row = 4 loads per lane: one DRAM
+  //     round trip, not four); same element -> lane mapping and summation order as the streaming scan
+  constexpr int kRescoreRows = 2;
   const int nvec = dim >> 2;
   const float4* qq = reinterpret_cast<const float4*>(qn + size_t(q) * dim);
   for (int i0 = w * kRescoreRows; i0 < m; i0 += kSelectWarps * kRescoreRows) {
@@ -798,6 +805,7 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
       const int i = i0 + u < m ? i0 + u : i0;
       g[u] = reinterpret_cast<const float4*>(master + size_t(keep_row[i]) * dim);
     }
+#pragma unroll 4
     for (int v = lane; v < nvec; v += 32) {
       const float4 y = __ldg(qq + v);
       float4 x[kRescoreRows];
@@ -1010,13 +1018,15 @@ static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const CU
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   FRG_CUDA(cudaLaunchKernelEx(&cfg, kern, qm, gm, pm, p));
   note_launch(nullptr);
   return FRG_OK;
@@ -1116,9 +1126,9 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
   const int rs = rescore ? 1 : 0;
 #define FRG_SELECT_M(KK, EU)                                                                                    \
   FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-  select_rescore_kernel<KK, EU><<<grid, kSelectWarps * 32, 0, st>>>(dense, cnt, pl.stage_entries, nq, k,        \
-      s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores, out_accept, flagged, n_flagged, \
-      push)
+  FRG_CUDA(launch_kernel(select_rescore_kernel<KK, EU>, dim3(grid), dim3(kSelectWarps * 32), 0, st, true, dense, \
+      cnt, pl.stage_entries, nq, k, s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores,   \
+      out_accept, flagged, n_flagged, push))
 #define FRG_SELECT(KK)                                                                                          \
   if (euclid) { FRG_SELECT_M(KK, true); } else { FRG_SELECT_M(KK, false); }
   switch (pl.kreg) {
