@@ -326,6 +326,47 @@ int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const
 
 
 
+// Small host batches (online enrolment: a few templates between query batches, BASELINE config 5) are
+// staged through a per-thread ring of pinned bounce buffers: the caller's arrays are copied out at once, the
+// H2D copy + ingest are enqueued and the call returns WITHOUT waiting for the device - a match enqueued next
+// is ordered after the mutation on the device (store_begin_read).  A slot is reused only after the copy
+// that read it has completed (event).  Large batches (bulk loads) keep the direct, synchronous path.
+struct PinnedRing {
+  static constexpr int kSlots = 4;
+  static constexpr size_t kMaxBytes = 4u << 20;
+  unsigned char* p[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0, 0};
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool pending[kSlots] = {false, false, false, false};
+  int next = 0;
+  ~PinnedRing() {
+    for (int i = 0; i < kSlots; ++i) {
+      if (pending[i]) cudaEventSynchronize(done[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+      if (p[i]) cudaFreeHost(p[i]);
+    }
+  }
+  unsigned char* acquire(size_t bytes, int* slot) {
+    const int i = next;
+    next = (next + 1) % kSlots;
+    if (pending[i]) { cudaEventSynchronize(done[i]); pending[i] = false; }
+    if (!done[i] && cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) { done[i] = nullptr; return nullptr; }
+    if (bytes > cap[i]) {
+      if (p[i]) cudaFreeHost(p[i]);
+      p[i] = nullptr; cap[i] = 0;
+      const size_t want = (bytes + 65535) & ~size_t(65535);
+      if (cudaHostAlloc(reinterpret_cast<void**>(&p[i]), want, cudaHostAllocDefault) != cudaSuccess) { p[i] = nullptr; return nullptr; }
+      cap[i] = want;
+    }
+    *slot = i;
+    return p[i];
+  }
+  void release(int slot, cudaStream_t st) {
+    if (cudaEventRecord(done[slot], st) == cudaSuccess) pending[slot] = true;
+  }
+};
+static thread_local PinnedRing g_upload_ring;
+
 int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
                           int64_t n, uint32_t flags) {
   if (!s || (n > 0 && !vecs) || n < 0) { set_error("upsert_host: bad argument"); return FRG_ERR_INVALID; }
@@ -341,26 +382,42 @@ int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, 
         }
   }
   // stream-ordered staging (no cudaMalloc / cudaFree: those synchronise the whole device and would
-  // stall every match in flight): one allocation [vecs | rows | tags], async copies, ingest, one
-  // stream synchronize so that the caller's host buffers may be reused on return
+  // stall every match in flight): one allocation [vecs | rows | tags], ingest
   cudaStream_t st = cudaStreamPerThread;
-  const size_t vb = (size_t(n) * s->dim * sizeof(float) + 255) & ~size_t(255);
+  const size_t vbytes = size_t(n) * s->dim * sizeof(float);
+  const size_t vb = (vbytes + 255) & ~size_t(255);
   const size_t rb = rows ? ((size_t(n) * sizeof(int64_t) + 255) & ~size_t(255)) : 0;
   const size_t tb = tags ? size_t(n) * sizeof(int32_t) : 0;
+  bool negative = false;
+  if (tags) for (int64_t i = 0; i < n; ++i) negative |= tags[i] < 0;
   unsigned char* d = nullptr;
   FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d), vb + rb + tb + 16, st));
   float* dv = reinterpret_cast<float*>(d);
   int64_t* dr = rows ? reinterpret_cast<int64_t*>(d + vb) : nullptr;
   int32_t* dt = tags ? reinterpret_cast<int32_t*>(d + vb + rb) : nullptr;
-  cudaError_t e = cudaMemcpyAsync(dv, vecs, size_t(n) * s->dim * sizeof(float), cudaMemcpyHostToDevice, st);
+
+  int slot = -1;
+  unsigned char* h = vb + rb + tb <= PinnedRing::kMaxBytes ? g_upload_ring.acquire(vb + rb + tb, &slot) : nullptr;
+  if (h) {
+    // asynchronous: the caller's arrays are consumed here, the device is not waited for
+    memcpy(h, vecs, vbytes);
+    if (rows) memcpy(h + vb, rows, size_t(n) * sizeof(int64_t));
+    if (tags) memcpy(h + vb + rb, tags, tb);
+    cudaError_t e = cudaMemcpyAsync(d, h, vb + rb + tb, cudaMemcpyHostToDevice, st);
+    g_upload_ring.release(slot, st);
+    int rc = e == cudaSuccess ? upsert_impl(s, dr, dv, dt, n, flags, st, negative)
+                              : cuda_fail(e, "upsert_host staging", __FILE__, __LINE__);
+    cudaError_t ef = cudaFreeAsync(d, st);
+    if (rc == FRG_OK && ef != cudaSuccess) rc = cuda_fail(ef, "cudaFreeAsync", __FILE__, __LINE__);
+    return rc;
+  }
+  (void)cudaGetLastError();
+  // bulk load: copy straight from the caller's arrays, one stream synchronize so that they may be reused
+  cudaError_t e = cudaMemcpyAsync(dv, vecs, vbytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && rows) e = cudaMemcpyAsync(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && tags) e = cudaMemcpyAsync(dt, tags, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, st);
   int rc = e == cudaSuccess ? FRG_OK : cuda_fail(e, "upsert_host staging", __FILE__, __LINE__);
-  if (rc == FRG_OK) {
-    bool negative = false;
-    if (tags) for (int64_t i = 0; i < n; ++i) negative |= tags[i] < 0;
-    rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative);
-  }
+  if (rc == FRG_OK) rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative);
   cudaError_t ef = cudaFreeAsync(d, st);
   if (rc == FRG_OK) {
     e = cudaStreamSynchronize(st);
@@ -388,9 +445,21 @@ int frg_store_remove_host(frg_store* s, const int64_t* rows, int64_t n) {
   if (n == 0) return FRG_OK;
   DeviceGuard g(s->device);
   cudaStream_t st = cudaStreamPerThread;
+  const size_t bytes = size_t(n) * sizeof(int64_t);
   int64_t* dr = nullptr;
-  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(int64_t), st));
-  cudaError_t e = cudaMemcpyAsync(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dr), bytes, st));
+  int slot = -1;
+  unsigned char* h = bytes <= PinnedRing::kMaxBytes ? g_upload_ring.acquire(bytes, &slot) : nullptr;
+  if (h) {
+    memcpy(h, rows, bytes);                       // asynchronous, as frg_store_upsert_host
+    cudaError_t e = cudaMemcpyAsync(dr, h, bytes, cudaMemcpyHostToDevice, st);
+    g_upload_ring.release(slot, st);
+    int rc = e == cudaSuccess ? frg_store_remove(s, dr, n, st) : cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+    cudaFreeAsync(dr, st);
+    return rc;
+  }
+  (void)cudaGetLastError();
+  cudaError_t e = cudaMemcpyAsync(dr, rows, bytes, cudaMemcpyHostToDevice, st);
   int rc = e == cudaSuccess ? frg_store_remove(s, dr, n, st) : cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
   cudaFreeAsync(dr, st);
   if (rc == FRG_OK) {

@@ -117,6 +117,10 @@ FRG_API int frg_store_stats(frg_store* s, frg_store_stats_t* out);       /* get_
  * (a zero vector becomes a NaN row that never matches).  tags == NULL: tag 0. */
 FRG_API int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
                      int64_t n, uint32_t flags, void* stream);
+/* Host arrays.  Returns once the caller's arrays have been consumed (they may be reused at once); batches up to
+ * 4 MB are staged through pinned memory and the call does NOT wait for the device - every match enqueued
+ * afterwards, on any stream, is ordered after the mutation on the device.  Larger (bulk) batches are copied
+ * straight from the caller's arrays and waited for. */
 FRG_API int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
                           int64_t n, uint32_t flags);
 /* Tombstone rows (tag := -1): `del self.embeddings[id]`, infrenceServer.py:234-258. */
