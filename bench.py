@@ -163,11 +163,16 @@ def reference_arm(args, rank, world):
     t0 = time.perf_counter()
     G = cpu_gallery(n, dim, args.seed, procs)
     from oracle import synth
-    q_per_step = args.cpu_queries or procs            # one query per worker per step: ~n * 1 us each
+    # bounded sample: the per-face loop costs ~0.65 us per gallery row; 1..8 queries per worker per step so
+    # that the whole --steps/--warmup run stays around 1.5 minutes
+    per_query_s = max(n * 0.65e-6, 1e-4)
+    per_worker = max(1, min(8, int(90.0 / ((args.steps + args.warmup) * per_query_s))))
+    q_per_step = args.cpu_queries or procs * per_worker
     Q, _ = synth.queries(q_per_step, n, dim)
     gen_s = time.perf_counter() - t0
     qps, per_step, _ = run_cpu_loop(G, Q, 0.45, procs, args.steps, args.warmup)
-    sample = "%d queries/step (1 per worker) x %d rows, top-1 + threshold (the reference has no top-k)" % (q_per_step, n)
+    sample = "%d queries/step (%d worker processes) x %d rows, top-1 + threshold (the reference has no top-k)" % (
+        q_per_step, procs, n)
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -503,7 +508,8 @@ def ours_arm(args, rank, world):
         if n > 4_000_000:
             raise SystemExit("cpu_baseline copies the gallery to the host: use --no-cpu above 4 M rows")
         G, _ = store.read_rows()                        # bit-identical to the CPU generator (tested)
-        q_cpu = args.cpu_queries or procs
+        # ~10-15 s of wall clock on every core: 16 queries per worker at 1 M rows (~0.65 us per row and query)
+        q_cpu = args.cpu_queries or procs * max(1, min(16, int(12.0 / max(n * 0.65e-6, 1e-4))))
         Qc, _ = synth.queries(q_cpu, n, dim)
         qps, per_step, results = run_cpu_loop(G, Qc, 0.45, procs, 1, 0)
         # the same queries through the GPU (rank 0's rows): identical ids and decisions
@@ -516,8 +522,8 @@ def ours_arm(args, rank, world):
         qps1, _, _ = run_cpu_loop(G1, Q1, 0.45, 1, 1, 0)
         cpu = {"value": qps, "unit": UNIT, "cores": procs, "kind": "port",
                "config1_10k_x_64_one_core_queries_per_s": qps1,
-               "sample": "%d queries (1 per worker process) x %d rows, top-1 + threshold 0.45, "
-                         "per-face Python loop of peopleCount.py:860-887" % (q_cpu, n),
+               "sample": "%d queries over %d worker processes x %d rows, top-1 + threshold 0.45, "
+                         "per-face Python loop of peopleCount.py:860-887" % (q_cpu, procs, n),
                "seconds": per_step, "gpu_agrees": bool(same)}
         del G
 

@@ -66,7 +66,9 @@ class Matcher:
 
     # ---- device tensors in/out, enqueued on the caller's stream (torch is only the allocator here)
     def match_device(self, Q, k: int = 1, threshold: float = LIVE_THRESHOLD, company_id: Optional[str] = None,
-                     variant: str = "auto", row_offset: int = 0, out=None, stream: Optional[int] = None):
+                     variant: str = "auto", row_offset: int = 0, out=None, stream: Optional[int] = None,
+                     tenant: Optional[int] = None):
+        """tenant: a tag code given directly (sharded galleries keep their own id / tenant tables)."""
         import torch
         assert Q.is_cuda and Q.dtype == torch.float32 and Q.is_contiguous()
         F = Q.shape[0]
@@ -77,13 +79,13 @@ class Matcher:
         rows, scores, accept = out
         if stream is None:
             stream = torch.cuda.current_stream(Q.device).cuda_stream
-        tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
+        if tenant is None:
+            tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
         p = _params(self.metric, variant, threshold, tenant, row_offset)
         N.check(N.lib.frg_match(self.store.handle, C.c_void_p(Q.data_ptr()), F, int(k), C.byref(p),
                                 C.c_void_p(rows.data_ptr()), C.c_void_p(scores.data_ptr()),
                                 C.c_void_p(accept.data_ptr()), C.c_void_p(stream)))
         return rows, scores, accept
-
 
     # ---- first row, in gallery order, whose score reaches the threshold (exact fp32)
     def first_above(self, Q: np.ndarray, threshold: float, strict: bool = False, company_id: Optional[str] = None,

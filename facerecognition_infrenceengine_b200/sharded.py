@@ -21,13 +21,21 @@ The reference has no distributed code at all; this file is new capability, not a
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, List, Optional, Tuple
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from . import _native as N
 from .gallery import GalleryStore
 from .matcher import LIVE_THRESHOLD, Matcher
+
+
+def block_layout(F: int, k: int) -> Tuple[int, int]:
+    """(bytes of the row part, bytes of one rank's packed [rows int64 | scores fp32] block).  The block is
+    padded to a multiple of 8 so that every rank's row part stays int64-aligned inside the gathered buffer
+    for any F*k (odd ones too)."""
+    rows_bytes = F * k * 8
+    return rows_bytes, rows_bytes + ((F * k * 4 + 7) & ~7)
 
 
 def shard_bounds(n_rows: int, world: int) -> List[Tuple[int, int]]:
@@ -55,6 +63,12 @@ class ShardedGallery:
         self.device = device
         self.store = store           # None in host-logic tests that inject their own local matcher
         self.bounds: List[Tuple[int, int]] = [(0, 0)] * self.world
+        # the dict keys of the reference (infrenceServer.py:48-51), replicated on every rank: id <-> GLOBAL row
+        self._row_of: Dict[str, int] = {}
+        self._id_of: Dict[int, str] = {}
+        self._meta: Dict[str, Dict] = {}
+        self._tenants: Dict[str, int] = {}
+        self._removed: set = set()   # global rows tombstoned so far
 
     # ---- layout ---------------------------------------------------------------------------------
     @property
@@ -90,19 +104,141 @@ class ShardedGallery:
         self.bounds = self.bounds[:-1] + [(lo, hi + n)]
         if self.rank == self.world - 1 and self.store is not None:
             self.store.append_rows(vecs, tags, prenormalised)
+        return hi
+
+    # ---- id-level API (the dict), collective: every rank makes the same calls in the same order ----
+    def tenant_code(self, company_id: Optional[str], create: bool = True) -> int:
+        """Same codes on every rank because every rank sees the same upserts in the same order."""
+        if company_id is None:
+            return 0
+        key = str(company_id)
+        if key not in self._tenants:
+            if not create:
+                return 0x7FFFFFFF            # a tag no row carries
+            self._tenants[key] = len(self._tenants) + 1
+        return self._tenants[key]
+
+    def __len__(self):
+        return len(self._row_of)
+
+    def __contains__(self, pid: str):
+        return str(pid) in self._row_of
+
+    def row_of(self, pid: str) -> int:
+        return self._row_of.get(str(pid), -1)
+
+    def id_of(self, row: int) -> Optional[str]:
+        """Id of a GLOBAL row; rows filled synthetically carry the implicit id ``"%024x" % row``."""
+        row = int(row)
+        if row < 0:
+            return None
+        pid = self._id_of.get(row)
+        if pid is None and row < self.total_rows and row not in self._removed:
+            return "%024x" % row
+        return pid
+
+    def metadata(self, pid: str) -> Optional[Dict]:
+        return self._meta.get(str(pid))
+
+    def load(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
+             meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
+        """Initial load of an EMPTY sharded gallery (the reference's load_all_embeddings,
+        infrenceServer.py:260-341): the batch, in dict order, is cut into balanced contiguous blocks and each
+        rank ingests only its own.  Ids must be distinct."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
+        if self.total_rows:
+            raise RuntimeError("load() needs an empty gallery; use upsert() afterwards")
+        if len(ids) != len(vecs) or len(set(map(str, ids))) != len(ids):
+            raise ValueError("ids must be distinct and as many as vecs")
+        tags = np.array([self.tenant_code(c) for c in (company_ids or [None] * len(ids))], np.int32)
+        lo, hi = self.plan(len(ids))
+        if self.store is not None and hi > lo:
+            self.store.append_rows(vecs[lo:hi], tags[lo:hi], prenormalised)
+        for r, p in enumerate(ids):
+            self._row_of[str(p)] = r
+            self._id_of[r] = str(p)
+        if meta is not None:
+            for p, m in zip(ids, meta):
+                self._meta[str(p)] = m
+
+    def upsert(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
+               meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
+        """``self.embeddings[id] = v / ||v||`` (infrenceServer.py:273,326; peopleCount.py:790,808) over the
+        sharded gallery.  An existing id is overwritten in place ON ITS OWNER rank (it keeps its global
+        position, as dict assignment does); new ids append at the end of the global order, i.e. to the last
+        rank's block.  Position within a batch: first occurrence; content: last."""
+        vecs = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
+        if len(ids) != len(vecs):
+            raise ValueError("ids and vecs differ in length")
+        tags = np.array([self.tenant_code(c) for c in (company_ids or [None] * len(ids))], np.int32)
+        last = {str(p): i for i, p in enumerate(ids)}
+        new_i, old_i = [], []
+        for p in dict.fromkeys(str(p) for p in ids):
+            (old_i if p in self._row_of else new_i).append(last[p])
+        lo, hi = self.bounds[self.rank]
+        mine = [i for i in old_i if lo <= self._row_of[str(ids[i])] < hi]
+        if mine and self.store is not None:
+            self.store.overwrite_rows([self._row_of[str(ids[i])] - lo for i in mine], vecs[mine], tags[mine],
+                                      prenormalised)
+        if new_i:
+            first = self.append_local(vecs[new_i], tags[new_i], prenormalised)
+            for j, i in enumerate(new_i):
+                self._row_of[str(ids[i])] = first + j
+                self._id_of[first + j] = str(ids[i])
+        if meta is not None:
+            for p, m in zip(ids, meta):
+                self._meta[str(p)] = m
+
+    def remove(self, ids: Iterable[str]) -> int:
+        """``del self.embeddings[id]`` (infrenceServer.py:248-251): the owner rank tombstones the row; a later
+        re-enrolment appends at the end, as ``del d[k]; d[k] = v`` does.  Unknown ids are ignored."""
+        lo, hi = self.bounds[self.rank]
+        gone, local = 0, []
+        for p in ids:
+            p = str(p)
+            r = self._row_of.pop(p, None)
+            if r is None:
+                continue
+            gone += 1
+            self._id_of.pop(r, None)
+            self._meta.pop(p, None)
+            self._removed.add(r)
+            if lo <= r < hi:
+                local.append(r - lo)
+        if local and self.store is not None:
+            self.store.remove_rows(local)
+        return gone
+
+    def remove_rows_global(self, rows: Iterable[int]) -> int:
+        """Tombstone GLOBAL rows that have no id entry (synthetic fills)."""
+        lo, hi = self.bounds[self.rank]
+        rows = [int(r) for r in rows]
+        for r in rows:
+            pid = self._id_of.pop(r, None)
+            if pid is not None:
+                self._row_of.pop(pid, None)
+                self._meta.pop(pid, None)
+            self._removed.add(r)
+        local = [r - lo for r in rows if lo <= r < hi]
+        if local and self.store is not None:
+            self.store.remove_rows(local)
+        return len(rows)
 
 
 class ShardedMatcher:
     def __init__(self, gallery: ShardedGallery,
                  local_match: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 exchange: str = "auto"):
+                 exchange: str = "auto", metric: str = "cosine"):
         """exchange: "p2p" (fused push + flag + merge kernel over NVLink peer memory), "nccl" (all-gather +
         merge kernel) or "auto" (p2p when the peer mapping can be set up, else nccl; `self.exchange` tells
         which one runs, `self.p2p_error` why not)."""
         self.g = gallery
+        if metric not in N.METRICS:
+            raise ValueError("metric must be one of %s" % sorted(N.METRICS))
+        self.metric = metric
         self._local = local_match or self._local_cuda
         self._merge = merge or self._merge_cuda
-        self._matcher = Matcher(gallery.store) if gallery.store is not None else None
+        self._matcher = Matcher(gallery.store, metric) if gallery.store is not None else None
         self._buf = None
         if exchange not in ("auto", "p2p", "nccl"):
             raise ValueError("exchange must be auto, p2p or nccl")
@@ -151,7 +287,7 @@ class ShardedMatcher:
         self.exchange = "p2p"
         return True
 
-    def _match_exchange_p2p(self, Q, rows_l, scores_l, F, k, threshold, variant, out):
+    def _match_exchange_p2p(self, Q, rows_l, scores_l, F, k, threshold, variant, tenant, out):
         """frg_match_exchange: local match whose select stage pushes each query's top-k to all ranks as it
         becomes final, then the push-stragglers + poll + merge kernel - one enqueue, no collective call."""
         import torch
@@ -160,8 +296,9 @@ class ShardedMatcher:
         self._epoch += 1
         x = N.Exchange(rank=self.g.rank, world=self.g.world, peer_bufs=int(hdl.buffer_ptrs_dev), block_cap=cap,
                        epoch=((self._epoch - 1) % 0xFFFFFFFF) + 1, reserved=0)
-        p = N.MatchParams(metric=N.METRIC_COSINE, variant=N.VARIANTS[variant], threshold=float(np.float32(threshold)),
-                          tenant=-1, row_offset=int(self.g.offset), flags=0, reserved=0)
+        p = N.MatchParams(metric=N.METRICS[self.metric], variant=N.VARIANTS[variant],
+                          threshold=float(np.float32(threshold)), tenant=int(tenant), row_offset=int(self.g.offset),
+                          flags=0, reserved=0)
         stream = torch.cuda.current_stream(Q.device).cuda_stream
         N.check(N.lib.frg_match_exchange(
             self.g.store.handle, C.c_void_p(Q.data_ptr()), F, k, C.byref(p), C.byref(x),
@@ -169,10 +306,10 @@ class ShardedMatcher:
             C.c_void_p(scores.data_ptr()), C.c_void_p(accept.data_ptr()), C.c_void_p(stream)))
 
     # ---- CUDA pieces ------------------------------------------------------------------------------
-    def _local_cuda(self, Q, k, threshold, variant, rows_out, scores_out):
+    def _local_cuda(self, Q, k, threshold, variant, rows_out, scores_out, tenant=-1):
         acc = self._accept_scratch(Q)
         self._matcher.match_device(Q, k, threshold, variant=variant, row_offset=self.g.offset,
-                                   out=(rows_out, scores_out, acc))
+                                   out=(rows_out, scores_out, acc), tenant=tenant)
 
     def _accept_scratch(self, Q):
         import torch
@@ -183,41 +320,44 @@ class ShardedMatcher:
     def _merge_cuda(self, gathered, parts, F, k, threshold, out):
         import torch
         rows, scores, accept = out
-        stride_bytes = F * k * 12
+        rows_bytes, stride_bytes = block_layout(F, k)
         base = gathered.data_ptr()
         stream = torch.cuda.current_stream(gathered.device).cuda_stream
         N.check(N.lib.frg_merge_topk_strided(
-            gathered.device.index, C.c_void_p(base + F * k * 8), stride_bytes // 4, C.c_void_p(base),
-            stride_bytes // 8, parts, F, k, N.METRIC_COSINE, float(np.float32(threshold)),
+            gathered.device.index, C.c_void_p(base + rows_bytes), stride_bytes // 4, C.c_void_p(base),
+            stride_bytes // 8, parts, F, k, N.METRICS[self.metric], float(np.float32(threshold)),
             C.c_void_p(rows.data_ptr()), C.c_void_p(scores.data_ptr()), C.c_void_p(accept.data_ptr()),
             C.c_void_p(stream)))
 
     # ---- the collective match ---------------------------------------------------------------------
     def match(self, Q, k: int = 1, threshold: float = LIVE_THRESHOLD, variant: str = "auto",
-              broadcast: bool = False, out=None):
+              broadcast: bool = False, out=None, company_id: Optional[str] = None):
         """Q: float32 [F, dim] tensor on this rank's device, identical on every rank (or rank 0's with
-        broadcast=True).  Returns (rows int64 [F,k] GLOBAL rows, scores fp32 [F,k], accept uint8 [F])
-        on every rank."""
+        broadcast=True).  company_id: only that tenant's rows take part (infrenceServer.py:343-380).
+        Returns (rows int64 [F,k] GLOBAL rows, scores fp32 [F,k], accept uint8 [F]) on every rank;
+        ``ids_of(rows)`` turns rows into the reference's id strings."""
         import torch
         import torch.distributed as dist
         F = Q.shape[0]
         if broadcast and self.g.world > 1:
             dist.broadcast(Q, src=0, group=self.g.group)
-        # packed per-rank block: F*k int64 rows, then F*k fp32 scores  (12 bytes per slot)
-        block = F * k * 12
-        if (F * k) % 2:                      # keep every block 8-byte aligned
-            raise ValueError("F*k must be even (pad the batch)")
+        tenant = -1 if company_id is None else self.g.tenant_code(company_id, create=False)
+        # packed per-rank block: F*k int64 rows, then F*k fp32 scores, padded to 8 bytes
+        rows_bytes, block = block_layout(F, k)
         local = torch.empty((block,), dtype=torch.uint8, device=Q.device)
-        rows_l = local[:F * k * 8].view(torch.int64).view(F, k)
-        scores_l = local[F * k * 8:].view(torch.float32).view(F, k)
+        rows_l = local[:rows_bytes].view(torch.int64).view(F, k)
+        scores_l = local[rows_bytes:rows_bytes + F * k * 4].view(torch.float32).view(F, k)
         if out is None:
             out = (torch.empty((F, k), dtype=torch.int64, device=Q.device),
                    torch.empty((F, k), dtype=torch.float32, device=Q.device),
                    torch.empty((F,), dtype=torch.uint8, device=Q.device))
         if self.g.world > 1 and self._p2p_ready(Q, F, k):
-            self._match_exchange_p2p(Q, rows_l, scores_l, F, k, threshold, variant, out)
+            self._match_exchange_p2p(Q, rows_l, scores_l, F, k, threshold, variant, tenant, out)
             return out
-        self._local(Q, k, threshold, variant, rows_l, scores_l)
+        if tenant == -1:
+            self._local(Q, k, threshold, variant, rows_l, scores_l)
+        else:
+            self._local(Q, k, threshold, variant, rows_l, scores_l, tenant=tenant)
         if self.g.world > 1:
             gathered = torch.empty((self.g.world * block,), dtype=torch.uint8, device=Q.device)
             dist.all_gather_into_tensor(gathered, local, group=self.g.group)
@@ -225,3 +365,8 @@ class ShardedMatcher:
             gathered = local
         self._merge(gathered, self.g.world, F, k, threshold, out)
         return out
+
+    def ids_of(self, rows) -> List[List[Optional[str]]]:
+        """Global rows of a match result -> id strings (None for unfilled slots)."""
+        r = rows.cpu().numpy() if hasattr(rows, "cpu") else np.asarray(rows)
+        return [[self.g.id_of(x) for x in rr] for rr in r.reshape(len(r), -1)]

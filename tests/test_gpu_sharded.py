@@ -31,6 +31,36 @@ def test_sharded_world1_equals_plain_matcher():
     store.close()
 
 
+def test_sharded_world1_enrolment_and_tenants():
+    """ShardedGallery's id-level API on one rank equals GalleryStore's (same dict semantics), odd F*k."""
+    import torch
+    import facerecognition_infrenceengine_b200 as frg
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+    rng = np.random.default_rng(3)
+    n, d = 3001, 512
+    ids = ["%024x" % (i + 1) for i in range(n)]
+    V = rng.standard_normal((n, d)).astype(np.float32)
+    comp = ["acme" if i % 2 else "globex" for i in range(n)]
+    plain = frg.GalleryStore(dim=d, capacity=n + 8)
+    plain.upsert(ids, V, comp)
+    store = frg.GalleryStore(dim=d, capacity=n + 8)
+    g = ShardedGallery(dim=d, device=0, store=store, rank=0, world=1)
+    g.load(ids, V, comp)
+    for tgt in (plain, g):
+        tgt.upsert([ids[4], "x", "y"], V[:3], ["globex", "acme", "acme"])
+        tgt.remove([ids[9], "ghost"])
+        tgt.upsert([ids[9]], V[5:6], ["acme"])
+    Q = (V[[4, 0, 5]] + np.float32(0.02) * rng.standard_normal((3, d)).astype(np.float32))
+    m, pm = ShardedMatcher(g), frg.Matcher(plain)
+    for company in (None, "acme", "globex", "nobody"):
+        rows, scores, acc = m.match(torch.from_numpy(Q).cuda(), 1, 0.4, company_id=company)
+        torch.cuda.synchronize()
+        ref = pm.match(Q, 1, 0.4, company_id=company)
+        assert (rows.cpu().numpy() == ref.rows).all() and (scores.cpu().numpy() == ref.scores).all()
+        assert m.ids_of(rows) == ref.ids
+    store.close(); plain.close()
+
+
 WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
@@ -87,6 +117,44 @@ for kk in (1, 16):
     for x, y in zip(a, b):
         assert torch.equal(x, y), kk
     assert a[0][0].tolist() == list(range(n, n + kk)), a[0][0].tolist()      # ties -> earliest rows, global numbering
+# id-level enrolment over the shards (SURVEY 8e): load in balanced blocks, overwrite on the owner rank, append
+# on the last rank, tombstone, tenant filter - against the reference's dict semantics, with odd F*k
+rng = np.random.default_rng(9)
+n2 = 5001
+ids2 = ["%%024x" %% (i + 7) for i in range(n2)]
+V2 = rng.standard_normal((n2, d)).astype(np.float32)
+comp2 = ["acme" if i %% 3 else "globex" for i in range(n2)]
+store2 = frg.GalleryStore(dim=d, capacity=n2 + 64, device=local)
+g2 = ShardedGallery(dim=d, device=local, store=store2)
+g2.load(ids2, V2, comp2)
+refv = {p: mo.normalise(v) for p, v in zip(ids2, V2)}; refc = dict(zip(ids2, comp2)); order = list(ids2)
+up = [ids2[3], ids2[n2 - 3], "new-a", "new-b", "new-a"]; upv = rng.standard_normal((5, d)).astype(np.float32)
+upc = ["acme", "globex", "acme", "initech", "acme"]
+g2.upsert(up, upv, upc)
+for p_, v_, c_ in zip(up, upv, upc):
+    if p_ not in refv: order.append(p_)
+    refv[p_] = mo.normalise(v_); refc[p_] = c_
+assert g2.remove([ids2[10], ids2[n2 - 10], "nobody"]) == 2
+for p_ in (ids2[10], ids2[n2 - 10]):
+    order.remove(p_); del refv[p_], refc[p_]
+g2.upsert([ids2[10]], upv[:1], ["acme"]); order.append(ids2[10]); refv[ids2[10]] = mo.normalise(upv[0]); refc[ids2[10]] = "acme"
+assert g2.total_rows == n2 + 3 and len(g2) == len(order)
+probe = [ids2[3], "new-a", ids2[10]]                       # F = 3, k = 1: odd F*k
+Qp = torch.from_numpy(np.stack([refv[p_] + np.float32(0.01) * rng.standard_normal(d).astype(np.float32) for p_ in probe])).cuda()
+for mm in (ShardedMatcher(g2, exchange="p2p"), ShardedMatcher(g2, exchange="nccl")):
+    for company in (None, "acme", "globex", "initech", "no-such-company"):
+        rows, scores, acc = mm.match(Qp, 1, 0.4, company_id=company)
+        torch.cuda.synchronize()
+        got = mm.ids_of(rows)
+        sub = {p_: refv[p_] for p_ in order if company is None or refc[p_] == company}
+        for fi in range(3):
+            want = mo.scan_best(mo.normalise(Qp[fi].cpu().numpy()), sub)
+            assert got[fi][0] == want[0], (company, fi, got[fi], want)
+            if want[0] is not None:
+                assert abs(float(scores[fi, 0]) - float(want[1])) <= 1e-4
+                assert bool(acc[fi]) == bool(np.float32(want[1]) >= np.float32(0.4))
+if dist.get_rank() == 0:
+    print("ENROL_OK world=%%d" %% dist.get_world_size())
 # every rank holds the same merged result
 chk = a[0].clone()
 dist.broadcast(chk, src=0)
@@ -109,3 +177,4 @@ def test_sharded_two_ranks_nccl(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK world=2" in r.stdout
     assert "P2P_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ENROL_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

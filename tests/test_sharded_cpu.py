@@ -23,10 +23,13 @@ def _free_port():
 
 def _merge_numpy(gathered, parts, F, k, threshold, out):
     """Reads the packed [rows | scores] blocks exactly as frg_merge_topk_strided does."""
-    block = F * k * 12
+    from facerecognition_infrenceengine_b200.sharded import block_layout
+    rb, block = block_layout(F, k)
+    assert block % 8 == 0 and block >= F * k * 12
     buf = gathered.numpy()
-    rows = np.stack([buf[p * block:p * block + F * k * 8].view(np.int64).reshape(F, k) for p in range(parts)])
-    scores = np.stack([buf[p * block + F * k * 8:(p + 1) * block].view(np.float32).reshape(F, k) for p in range(parts)])
+    rows = np.stack([buf[p * block:p * block + rb].view(np.int64).reshape(F, k) for p in range(parts)])
+    scores = np.stack([buf[p * block + rb:p * block + rb + F * k * 4].view(np.float32).reshape(F, k)
+                       for p in range(parts)])
     o_r, o_s, o_a = (t.numpy() for t in out)      # views onto the caller's tensors
     for f in range(F):
         cand = [(-(scores[p, f, j]), rows[p, f, j]) for p in range(parts) for j in range(k) if rows[p, f, j] >= 0]
@@ -49,9 +52,11 @@ def _worker(rank, world, port, n, F, k, ret):
         from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher, shard_bounds
         d = 512
         G = synth.gallery(n, d)
-        G[n - 3] = G[5]                       # an exact tie that straddles the two shards
         Q, _ = synth.queries(F, n, d)
-        Q[0] = G[5]
+        tie = F > 1        # (a 1-row batch takes another BLAS path per shard shape: scores differ by an ulp)
+        if tie:
+            G[n - 3] = G[5]                   # an exact tie that straddles the two shards
+            Q[0] = G[5]
         g = ShardedGallery(dim=d, store=None)
         lo, hi = g.plan(n)
         assert g.bounds == shard_bounds(n, world) and g.offset == lo and g.total_rows == n
@@ -70,16 +75,109 @@ def _worker(rank, world, port, n, F, k, ret):
         assert (rows.numpy() == ref_r).all()
         assert np.abs(scores.numpy() - ref_s).max() < 1e-6
         assert (acc.numpy().astype(bool) == ref_a).all()
-        assert list(rows.numpy()[0, :2]) == [5, n - 3][:k]        # the tie resolves to the lower GLOBAL row
+        if tie:
+            assert list(rows.numpy()[0, :2]) == [5, n - 3][:k]    # the tie resolves to the lower GLOBAL row
         # appends go to the last rank and extend the global order
         g.append_local(G[:4])
         assert g.total_rows == n + 4 and g.bounds[0] == (0, n // 2)
+        _enrolment_scenario(rank, world, F, k)
         ret[rank] = 1
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,F,k", [(4001, 6, 5), (2000, 4, 1)])
+class _HostShard:
+    """Stands in for the device store of one rank (append / overwrite / tombstone of LOCAL rows), so that the
+    routing of ShardedGallery.upsert / remove can be checked without a GPU.  Normalises on ingest like the
+    real store (oracle arithmetic: test infrastructure)."""
+
+    def __init__(self, dim):
+        self.vecs = np.zeros((0, dim), np.float32)
+        self.tags = np.zeros(0, np.int32)
+
+    def append_rows(self, vecs, tags=None, prenormalised=False):
+        first = len(self.vecs)
+        v = np.asarray(vecs, np.float32) if prenormalised else mo.normalise_rows(np.asarray(vecs, np.float32))
+        self.vecs = np.concatenate([self.vecs, v])
+        self.tags = np.concatenate([self.tags, np.zeros(len(v), np.int32) if tags is None else np.asarray(tags, np.int32)])
+        return first
+
+    def overwrite_rows(self, rows, vecs, tags=None, prenormalised=False):
+        v = np.asarray(vecs, np.float32) if prenormalised else mo.normalise_rows(np.asarray(vecs, np.float32))
+        for j, r in enumerate(rows):
+            assert 0 <= r < len(self.vecs), "overwrite routed to a rank that does not own the row"
+            self.vecs[r] = v[j]
+            self.tags[r] = 0 if tags is None else tags[j]
+
+    def remove_rows(self, rows):
+        for r in rows:
+            assert 0 <= r < len(self.vecs), "removal routed to a rank that does not own the row"
+            self.tags[r] = -1
+
+
+def _enrolment_scenario(rank, world, F, k):
+    """Sharded upsert / remove / tenant filter against the reference's dict semantics (GalleryOracle follows
+    infrenceServer.py:260-341): every rank makes the same calls, only owners touch their rows."""
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+    d, n0 = 64, 41
+    rng = np.random.default_rng(5)
+    ids0 = ["%024x" % (i + 1000) for i in range(n0)]
+    V0 = rng.standard_normal((n0, d)).astype(np.float32)
+    comp = ["acme" if i % 3 else "globex" for i in range(n0)]
+    g = ShardedGallery(dim=d, store=_HostShard(d))
+    g.load(ids0, V0, comp)        # contiguous balanced blocks: each rank ingests only its own
+    assert len(g.store.vecs) == g.local_rows and g.total_rows == n0 and g.row_of(ids0[-1]) == n0 - 1
+    ref_ids, ref_vecs, ref_comp = list(ids0), {p: mo.normalise(v) for p, v in zip(ids0, V0)}, dict(zip(ids0, comp))
+
+    def ref_apply_upsert(ids, vecs, comps):
+        for p, v, c in zip(ids, vecs, comps):
+            if p not in ref_vecs:
+                ref_ids.append(p)
+            ref_vecs[p] = mo.normalise(v)
+            ref_comp[p] = c
+
+    def ref_apply_remove(ids):
+        for p in ids:
+            if p in ref_vecs:
+                ref_ids.remove(p)
+                del ref_vecs[p], ref_comp[p]
+
+    # 1. overwrite ids owned by different ranks + two new ids (one repeated inside the batch: position of
+    #    the first occurrence, content of the last)
+    up_ids = [ids0[2], ids0[n0 - 2], "new-a", "new-b", "new-a"]
+    up_v = rng.standard_normal((5, d)).astype(np.float32)
+    up_c = ["acme", "globex", "acme", "initech", "acme"]
+    g.upsert(up_ids, up_v, up_c, meta=[{"name": p} for p in up_ids])
+    ref_apply_upsert(up_ids, up_v, up_c)
+    # 2. remove one id per rank and an unknown one; re-enrol one of them (goes to the END)
+    assert g.remove([ids0[5], ids0[n0 - 5], "nobody"]) == 2
+    ref_apply_remove([ids0[5], ids0[n0 - 5]])
+    g.upsert([ids0[5]], up_v[:1], ["acme"])
+    ref_apply_upsert([ids0[5]], up_v[:1], ["acme"])
+    assert g.total_rows == n0 + 3 and len(g) == len(ref_ids) and ids0[5] in g and "nobody" not in g
+    assert g.row_of(ids0[5]) == n0 + 2 and g.id_of(5) is None and g.metadata("new-b") == {"name": "new-b"}
+    assert g.bounds[0] == (0, n0 // world)                       # only the last block grew
+
+    def local_match(Qt, k_, thr, variant, rows_out, scores_out, tenant=-1):
+        lo_ = g.offset
+        r, s, _ = mo.match_topk(Qt.numpy(), g.store.vecs, k_, thr, tags=g.store.tags, tenant=tenant)
+        rows_out.copy_(torch.from_numpy(np.where(r >= 0, r + lo_, -1)))
+        scores_out.copy_(torch.from_numpy(s))
+
+    m = ShardedMatcher(g, local_match=local_match, merge=_merge_numpy)
+    Q = np.stack([ref_vecs[p] for p in (ids0[2], "new-a", ids0[5], ids0[n0 - 2], ids0[7])][:max(1, F)])
+    for company in (None, "acme", "globex", "initech", "no-such-company"):
+        rows, scores, acc = m.match(torch.from_numpy(Q.copy()), k, 0.4, company_id=company)
+        sub = [p for p in ref_ids if company is None or ref_comp[p] == company]
+        for f in range(len(Q)):
+            want = mo.scan_best(Q[f], {p: ref_vecs[p] for p in sub})     # the reference's own loop
+            got = m.ids_of(rows)[f][0]
+            assert got == want[0], (company, f, got, want)
+            if want[0] is not None:
+                assert abs(float(scores[f, 0]) - float(want[1])) < 1e-6
+
+
+@pytest.mark.parametrize("n,F,k", [(4001, 6, 5), (2000, 4, 1), (2000, 3, 1), (1500, 1, 3)])
 def test_sharded_match_world2_gloo(n, F, k):
     import facerecognition_infrenceengine_b200  # noqa: F401  (builds / loads the library before forking)
     port = _free_port()
