@@ -60,7 +60,7 @@ extern "C" {
 #define FRG_STORE_BF16_PLANE  1u /* keep the bf16 scan plane next to the fp32 master (needed by TC variants) */
 #define FRG_STORE_RAW         2u /* never normalise on ingest (Euclidean galleries, cluster means).  Together with
                                    FRG_STORE_BF16_PLANE the plane is the EUCLIDEAN scan plane: each row carries
-                                   -0.5*||g||^2 in 64 more bf16 columns, so that the tensor-core product with
+                                   -0.5*||g||^2 in 16 more bf16 columns, so that the tensor-core product with
                                    [q, 1, 1, 1, 0..] is q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2 */
 #define FRG_STORE_BF16_ONLY   4u /* keep ONLY the bf16 scan plane (1 KB / 512-d row instead of 3 KB): "bf16 gallery
                                    mode".  Matches run as FRG_VARIANT_TC_BF16 (scores within 4e-3 of fp32);

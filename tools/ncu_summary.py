@@ -52,5 +52,49 @@ def full(path):
                 print("  %-66s %s %s" % (k, r[i], units[i]))
 
 
+def dispatch(path):
+    """CSV of `tools/dispatch_probe.py` under ncu: per (variant, batch) the dominant kernel's time, DRAM bytes,
+    achieved GB/s and tensor-pipe utilisation.  first_match_kernel launches separate the cases."""
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from dispatch_probe import CASES
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ii, ki, mi, vi = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    ui = hdr.index("Metric Unit")
+    scale = {"nsecond": 1, "ns": 1, "usecond": 1e3, "us": 1e3, "msecond": 1e6, "ms": 1e6, "second": 1e9, "s": 1e9,
+             "byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}             # -> ns and bytes
+    launches = OrderedDict()
+    for r in rows[1:]:
+        launches.setdefault(int(r[ii]), {"name": r[ki].split("(")[0]})[r[mi]] = (
+            float(r[vi].replace(",", "")) * scale.get(r[ui], 1))
+    cases, cur = [], None
+    for _, L in sorted(launches.items()):
+        if "first_match" in L["name"]:
+            cur = []
+            cases.append(cur)
+        elif cur is not None:
+            cur.append(L)
+    print("# 1 M x 512 gallery, top-5, one match per case under ncu --clock-control none (cold cache, serialised:")
+    print("# compare variants at the same batch, not absolutes).  HBM-bound cases: algorithmic bytes = 2.048 GB (fp32")
+    print("# master, scan_f32: once per 4 queries) / 1.024 GB (bf16 plane, tc_exact: once per 128 queries)")
+    print("%-9s %5s | %-26s %4s %10s %9s %8s %8s %8s" % ("variant", "F", "dominant kernel", "n", "total us", "GB read",
+                                                        "GB/s", "dram %", "tensor %"))
+    for (variant, F), ks in zip(CASES, cases):
+        if not ks:
+            continue
+        by = OrderedDict()
+        for L in ks:
+            by.setdefault(L["name"], []).append(L)
+        name, group = max(by.items(), key=lambda kv: sum(x["gpu__time_duration.sum"] for x in kv[1]))
+        t = sum(x["gpu__time_duration.sum"] for x in group)                    # ns
+        b = sum(x["dram__bytes_read.sum"] for x in group)
+        dr = sum(x["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"] * x["gpu__time_duration.sum"] for x in group) / t
+        tp = sum(x["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"] * x["gpu__time_duration.sum"] for x in group) / t
+        other = sum(x["gpu__time_duration.sum"] for L in by.values() for x in L) - t
+        print("%-9s %5d | %-26s %4d %10.1f %9.3f %8.0f %8.1f %8.1f   (+%.1f us in the other scan launches)" % (
+            variant, F, name[-26:], len(group), t / 1e3, b / 1e9, b / t, dr, tp, other / 1e3))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "dispatch": dispatch}[sys.argv[1]](sys.argv[2])

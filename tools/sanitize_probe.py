@@ -1,5 +1,7 @@
 """A small tour of every kernel for compute-sanitizer (run on the GPU box):
     compute-sanitizer --tool memcheck python tools/sanitize_probe.py
+(compute-sanitizer is closed on this GPU pool - the call is refused there; the tour still runs as a plain
+parity pass over every kernel: python tools/sanitize_probe.py)
 cosine and Euclidean TC pipelines (single-CTA and CTA-pair forms, fused probe form), tenant masks, tombstones,
 candidate overflow -> exact fallback, exact scan, first_match, ingest / overwrite / compaction."""
 import sys
