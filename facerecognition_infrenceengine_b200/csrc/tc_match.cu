@@ -246,6 +246,7 @@ struct TcScanParams {
   int k;                   // L[q] = k-th largest of the 32 group maxima (computed in the prologue)
   int* arrive;             // FUSED: CTAs that have published their probe-tile maxima
   int arrive_target;       // FUSED: wait (bounded) for this many before deriving the floor; 0 = do not wait
+  int probe_div;           // FUSED: the probe is 1/probe_div of every CTA's chunk (at least one tile)
   int seg;                 // candidate slots per (query, chunk) private segment
   int2* cand;              // [nq][chunks][seg] (row, score bits): written while scanning
   int* cand_total;         // [nq] candidates of the query over all chunks (atomicAdd at the CTA's end)
@@ -313,7 +314,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   // a probe (group maxima only, published to all CTAs so that everyone can derive the floor L[q]),
   // and once more at the very end to emit from them
   const int n_tiles = tile_end - tile_begin;
-  const int n_probe = MODE == kModeFused ? (n_tiles + 63) / 64 : 0;
+  const int n_probe = MODE == kModeFused ? (n_tiles + p.probe_div - 1) / p.probe_div : 0;
   const int n_iter = n_tiles + n_probe;
   auto tile_of = [&](int it) { return it < n_tiles ? tile_begin + it : tile_begin + (it - n_tiles); };
 
@@ -933,6 +934,12 @@ struct TcPlan {
   size_t off_keys, off_cnt, off_cand, off_dense, off_flag, total;
 };
 
+// FUSED: share of every CTA's chunk probed before the floor is derived (FRG_TC_PROBE_DIV, default 64)
+static int probe_div() {
+  static const int v = []() { const char* e = getenv("FRG_TC_PROBE_DIV"); const int d = e ? atoi(e) : 64; return d < 1 ? 64 : d; }();
+  return v;
+}
+
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
 
 static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
@@ -984,7 +991,8 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   // fused: the probe is 1/64 of every chunk, or one tile per CTA if that is more
   int eff_stride = stride;
   if (pl->fused) {
-    const int64_t probe_rows = int64_t((tiles_all / pl->chunks_main + 63) / 64) * pl->chunks_main * tile_rows;
+    const int pd = probe_div();
+    const int64_t probe_rows = int64_t((tiles_all / pl->chunks_main + pd - 1) / pd) * pl->chunks_main * tile_rows;
     eff_stride = int(rows / (probe_rows > 0 ? probe_rows : 1)) + 1;
     if (eff_stride > 64) eff_stride = 64;
   }
@@ -1097,6 +1105,7 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
     // 1+2. ONE kernel: every CTA probes its first tile, publishes the group maxima, derives L[q] from
     // what all CTAs published, filters the rest of its chunk and finally the probe tile itself
     p.tile_scale = 1;
+    p.probe_div = probe_div();
     p.arrive = n_flagged + 2;
     {
       // the first wave holds min(all CTAs, one per SM): later waves find the counter already there
