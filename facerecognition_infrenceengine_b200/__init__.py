@@ -11,12 +11,12 @@ from ._native import NativeError
 from .gallery import GalleryStore
 from .matcher import (CAMPUS_THRESHOLD, CAMPUS_UNKNOWN, LIVE_THRESHOLD, CameraProcessor,
                       FaceRecognitionProcessor, Matcher, MatchResult)
-from .manager import EmbeddingManager, GalleryView, ListSource
+from .manager import BroadcastSource, EmbeddingManager, GalleryView, ListSource
 from .enrol import EnrolmentChecker
 from .clustering import UnknownClusterer
 from .aggregator import BatchAggregator
 
 __all__ = ["GalleryStore", "Matcher", "MatchResult", "FaceRecognitionProcessor", "CameraProcessor",
-           "EmbeddingManager", "GalleryView", "ListSource", "EnrolmentChecker", "UnknownClusterer",
+           "EmbeddingManager", "GalleryView", "ListSource", "BroadcastSource", "EnrolmentChecker", "UnknownClusterer",
            "BatchAggregator", "NativeError", "LIVE_THRESHOLD",
            "CAMPUS_THRESHOLD", "CAMPUS_UNKNOWN"]

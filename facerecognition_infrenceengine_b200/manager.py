@@ -63,6 +63,36 @@ class ListSource:
         return [str(d["_id"]) for d in self.employees if inactive_employee(d)]
 
 
+class BroadcastSource:
+    """Document source for a row-sharded gallery (one process per GPU): rank 0 asks the real source, every
+    rank receives the same documents, so the replicated id / tenant tables of ``ShardedGallery`` stay identical
+    and every rank applies the same upserts and removals in the same order.  Pass a CPU (gloo) process group
+    for this control traffic - ``dist.new_group(backend="gloo")`` - so that it never interleaves with the
+    collectives of the data path when the sync thread runs beside the matcher."""
+
+    def __init__(self, source, group=None):
+        import torch.distributed as dist
+        self.source = source
+        self.group = group
+        self.rank = dist.get_rank(group)
+
+    def _bcast(self, fetch):
+        import torch.distributed as dist
+        box = [fetch() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                   group=self.group)
+        return box[0]
+
+    def employee_docs(self, since: Optional[datetime] = None) -> List[Dict]:
+        return self._bcast(lambda: list(self.source.employee_docs(since)))
+
+    def visitor_docs(self, since: Optional[datetime] = None) -> List[Dict]:
+        return self._bcast(lambda: list(self.source.visitor_docs(since)))
+
+    def inactive_employee_ids(self) -> List[str]:
+        return self._bcast(lambda: list(self.source.inactive_employee_ids()))
+
+
 class GalleryView:
     """What the matcher needs instead of a dict copy: the store and an optional tenant filter."""
 
@@ -73,6 +103,8 @@ class GalleryView:
     def __len__(self):
         if self.company_id is None:
             return len(self.store)
+        if hasattr(self.store, "count_tenant"):          # sharded gallery: host-side table, no device read
+            return self.store.count_tenant(self.company_id)
         code = self.store.tenant_code(self.company_id, create=False)
         _, _, tags = self.store.snapshot_arrays()
         return int((tags == code).sum())
@@ -86,11 +118,14 @@ class EmbeddingManager:
     mode='campus': full reload every 60 s, never evicts (peopleCount.py:766-776)."""
 
     def __init__(self, source, dim: int = 512, device: int = 0, mode: str = "live",
-                 sync_interval: Optional[float] = None, capacity: int = 1024, bf16_plane: bool = True):
+                 sync_interval: Optional[float] = None, capacity: int = 1024, bf16_plane: bool = True,
+                 store=None):
+        """store: an existing ``GalleryStore``, or a ``sharded.ShardedGallery`` (one process per GPU; give every
+        rank the same documents, e.g. through ``BroadcastSource``).  Default: a new store on `device`."""
         assert mode in ("live", "campus")
         self.source = source
         self.mode = mode
-        self.store = GalleryStore(dim, capacity, device, bf16_plane)
+        self.store = store if store is not None else GalleryStore(dim, capacity, device, bf16_plane)
         self.embeddings_lock = threading.Lock()
         self.last_sync_time: Optional[datetime] = None
         self.is_initial_load = True

@@ -112,15 +112,19 @@ class FaceRecognitionProcessor:
     ``person_info`` (metadata, or ``{'name': 'Unknown', 'type': 'unknown'}``), the reported score
     (0 when rejected) and the matched id (None when rejected)."""
 
-    def __init__(self, store: GalleryStore, recognition_threshold: float = LIVE_THRESHOLD):
-        self.matcher = Matcher(store)
+    def __init__(self, store, recognition_threshold: float = LIVE_THRESHOLD, matcher=None):
+        """store: a ``GalleryStore`` - or a ``ShardedGallery`` together with ``matcher=ShardedMatcher(store)``
+        (one process per GPU; every rank makes the same calls)."""
+        self.store = store
+        self.matcher = matcher if matcher is not None else Matcher(store)
+        self._match = getattr(self.matcher, "match_host", None) or self.matcher.match
         self.recognition_threshold = recognition_threshold
 
     def recognize(self, embeddings: np.ndarray, company_id: Optional[str] = None) -> List[Dict]:
-        store = self.matcher.store
+        store = self.store
         if len(embeddings) == 0 or len(store) == 0:      # `if not embeddings: return frame` (:523-525)
             return []
-        r = self.matcher.match(embeddings, 1, self.recognition_threshold, company_id)
+        r = self._match(embeddings, 1, self.recognition_threshold, company_id)
         out = []
         for f in range(len(embeddings)):
             if r.accept[f]:
@@ -137,9 +141,11 @@ class CameraProcessor:
     """Drop-in for the matching half of peopleCount.CameraProcessor (:822-896): three-way decision
     at 0.45 / 0.35 over ALL tenants, and the same stats dict."""
 
-    def __init__(self, store: GalleryStore, recognition_threshold: float = CAMPUS_THRESHOLD,
-                 unknown_threshold: float = CAMPUS_UNKNOWN):
-        self.matcher = Matcher(store)
+    def __init__(self, store, recognition_threshold: float = CAMPUS_THRESHOLD,
+                 unknown_threshold: float = CAMPUS_UNKNOWN, matcher=None):
+        self.store = store
+        self.matcher = matcher if matcher is not None else Matcher(store)
+        self._match = getattr(self.matcher, "match_host", None) or self.matcher.match
         self.recognition_threshold = recognition_threshold
         self.unknown_threshold = unknown_threshold
 
@@ -147,13 +153,13 @@ class CameraProcessor:
         """Returns (events, stats): events[f] is ('recognized', id, float score) |
         ('unknown', None, None) | ('ignored', None, None)."""
         stats = {"faces": 0, "recognized": 0, "unknown": 0}
-        store = self.matcher.store
+        store = self.store
         if len(store) == 0:                               # peopleCount.py:850-851
             return [], stats
         stats["faces"] = len(embeddings)
         if len(embeddings) == 0:
             return [], stats
-        r = self.matcher.match(embeddings, 1, self.recognition_threshold)
+        r = self._match(embeddings, 1, self.recognition_threshold)
         unknown_thr = np.float32(self.unknown_threshold)
         events = []
         for f in range(len(embeddings)):

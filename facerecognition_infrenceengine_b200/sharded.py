@@ -27,7 +27,7 @@ import numpy as np
 
 from . import _native as N
 from .gallery import GalleryStore
-from .matcher import LIVE_THRESHOLD, Matcher
+from .matcher import LIVE_THRESHOLD, Matcher, MatchResult
 
 
 def block_layout(F: int, k: int) -> Tuple[int, int]:
@@ -68,7 +68,9 @@ class ShardedGallery:
         self._id_of: Dict[int, str] = {}
         self._meta: Dict[str, Dict] = {}
         self._tenants: Dict[str, int] = {}
+        self._tenant_of: Dict[str, int] = {}     # id -> tenant code (company subset sizes without a device read)
         self._removed: set = set()   # global rows tombstoned so far
+        self._anon = 0               # live rows without an id entry (synthetic fills)
 
     # ---- layout ---------------------------------------------------------------------------------
     @property
@@ -93,6 +95,7 @@ class ShardedGallery:
         only on (seed, r), so the data is identical at 1, 2, 4 or 8 GPUs and never touches the host."""
         lo, hi = self.plan(n_rows)
         self.store.fill_synthetic(hi - lo, lo, seed)
+        self._anon = n_rows
 
     def append_local(self, vecs: np.ndarray, tags=None, prenormalised: bool = False):
         """Collective enrolment: every rank passes the SAME batch; each keeps the rows whose global
@@ -119,7 +122,7 @@ class ShardedGallery:
         return self._tenants[key]
 
     def __len__(self):
-        return len(self._row_of)
+        return len(self._row_of) + self._anon
 
     def __contains__(self, pid: str):
         return str(pid) in self._row_of
@@ -140,6 +143,18 @@ class ShardedGallery:
     def metadata(self, pid: str) -> Optional[Dict]:
         return self._meta.get(str(pid))
 
+    def ids(self) -> List[str]:
+        """Live ids in global gallery (= dict) order."""
+        return [self._id_of[r] for r in sorted(self._id_of)]
+
+    def count_tenant(self, company_id: Optional[str]) -> int:
+        code = self.tenant_code(company_id, create=False)
+        return sum(1 for c in self._tenant_of.values() if c == code)
+
+    def stats(self):
+        """Device-side figures of THIS rank's shard."""
+        return self.store.stats()
+
     def load(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
              meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
         """Initial load of an EMPTY sharded gallery (the reference's load_all_embeddings,
@@ -157,6 +172,7 @@ class ShardedGallery:
         for r, p in enumerate(ids):
             self._row_of[str(p)] = r
             self._id_of[r] = str(p)
+            self._tenant_of[str(p)] = int(tags[r])
         if meta is not None:
             for p, m in zip(ids, meta):
                 self._meta[str(p)] = m
@@ -170,6 +186,8 @@ class ShardedGallery:
         vecs = np.ascontiguousarray(vecs, dtype=np.float32).reshape(-1, self.dim)
         if len(ids) != len(vecs):
             raise ValueError("ids and vecs differ in length")
+        if self.total_rows == 0 and len(set(map(str, ids))) == len(ids):
+            return self.load(ids, vecs, company_ids, meta, prenormalised)       # the initial load: balanced blocks
         tags = np.array([self.tenant_code(c) for c in (company_ids or [None] * len(ids))], np.int32)
         last = {str(p): i for i, p in enumerate(ids)}
         new_i, old_i = [], []
@@ -185,6 +203,8 @@ class ShardedGallery:
             for j, i in enumerate(new_i):
                 self._row_of[str(ids[i])] = first + j
                 self._id_of[first + j] = str(ids[i])
+        for i in old_i + new_i:
+            self._tenant_of[str(ids[i])] = int(tags[i])
         if meta is not None:
             for p, m in zip(ids, meta):
                 self._meta[str(p)] = m
@@ -202,6 +222,7 @@ class ShardedGallery:
             gone += 1
             self._id_of.pop(r, None)
             self._meta.pop(p, None)
+            self._tenant_of.pop(p, None)
             self._removed.add(r)
             if lo <= r < hi:
                 local.append(r - lo)
@@ -218,6 +239,9 @@ class ShardedGallery:
             if pid is not None:
                 self._row_of.pop(pid, None)
                 self._meta.pop(pid, None)
+                self._tenant_of.pop(pid, None)
+            elif r not in self._removed and self._anon > 0:
+                self._anon -= 1
             self._removed.add(r)
         local = [r - lo for r in rows if lo <= r < hi]
         if local and self.store is not None:
@@ -364,6 +388,20 @@ class ShardedMatcher:
         else:
             gathered = local
         self._merge(gathered, self.g.world, F, k, threshold, out)
+        return out
+
+    def match_host(self, Q: np.ndarray, k: int = 1, threshold: float = LIVE_THRESHOLD,
+                   company_id: Optional[str] = None, variant: str = "auto", with_ids: bool = True) -> MatchResult:
+        """Host (numpy) batch in, ``MatchResult`` out - the call shape of ``Matcher.match``, so that
+        ``FaceRecognitionProcessor`` / ``CameraProcessor`` run unchanged over a sharded gallery
+        (``matcher=ShardedMatcher(g)``).  Collective: every rank passes the same batch."""
+        import torch
+        dev = torch.device("cuda", self.g.store.device if self.g.device is None else self.g.device)
+        Qd = torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.g.dim)).to(dev)
+        rows, scores, acc = self.match(Qd, k, threshold, variant, company_id=company_id)
+        out = MatchResult(rows.cpu().numpy(), scores.cpu().numpy(), acc.cpu().numpy().astype(np.bool_))
+        if with_ids:
+            out.ids = self.ids_of(out.rows)
         return out
 
     def ids_of(self, rows) -> List[List[Optional[str]]]:

@@ -61,6 +61,78 @@ def test_sharded_world1_enrolment_and_tenants():
     store.close(); plain.close()
 
 
+def _manager_scenario(frg, gal, matcher, src_factory, g, rank=0):
+    """The reference's own EmbeddingManager scenario (tests/golden/managers.npz, produced by the unmodified
+    infrenceServer.py under stubs) over a sharded gallery: ids order, company subsets and the match results of
+    FaceRecognitionProcessor.recognize_faces.  Only `rank` 0 edits the documents (BroadcastSource ships them)."""
+    from datetime import datetime, timedelta, timezone
+    st = g["stored"]
+    A, B = "a" * 24, "b" * 24
+    t0 = datetime(2026, 1, 1)
+
+    def emp(i):
+        return {"_id": "%024x" % i, "embedding": st[i], "companyId": A if i < 8 or i >= 12 else B, "status": "active",
+                "blacklisted": False, "lastUpdated": t0, "employeeName": "e%d" % i}
+
+    def vis(i):
+        return {"_id": "%024x" % (100 + i), "embedding": st[20 + i], "companyId": A if i < 3 else B,
+                "lastUpdated": t0, "visitorName": "v%d" % i}
+
+    E = [emp(i) for i in range(12)]
+    E[3]["status"] = "inactive"; E[5]["blacklisted"] = True; E[6]["embedding_status"] = "pending"
+    V = [vis(i) for i in range(6)]
+    V[4]["embedding_status"] = "pending"
+    m = frg.EmbeddingManager(src_factory(E, V), mode="live", store=gal)
+
+    def same(prefix):
+        ref_ids, ref_G = list(g[prefix + "_ids"]), g[prefix + "_G"]
+        assert gal.ids() == ref_ids
+        lo, hi = gal.bounds[gal.rank]
+        vecs, tags = gal.store.read_rows(0, hi - lo)
+        for i, pid in enumerate(ref_ids):
+            r = gal.row_of(pid)
+            if lo <= r < hi:
+                a, b = vecs[r - lo], ref_G[i]
+                assert tags[r - lo] >= 0 and (np.isnan(a) == np.isnan(b)).all()
+                assert np.isnan(b).all() or np.nanmax(np.abs(a - b)) <= 2e-7
+
+    same("ref_live_load")
+    s = m.get_stats()
+    assert [s["total_embeddings"], s["employees"], s["visitors"]] == list(g["ref_live_load_stats"])
+    later = datetime.now(timezone.utc).replace(tzinfo=None) + timedelta(seconds=5)
+    if rank == 0:
+        E[1]["embedding"] = st[30]; E[1]["lastUpdated"] = later
+        E[0]["status"] = "inactive"
+        E.append(dict(emp(12), lastUpdated=later))
+        V[1]["embedding"] = st[31]; V[1]["lastUpdated"] = later
+        E[3]["status"] = "active"; E[3]["lastUpdated"] = later
+    m.force_sync()
+    same("ref_live_sync1")
+    if rank == 0:
+        E[0]["status"] = "active"
+        E[0]["lastUpdated"] = datetime.now(timezone.utc).replace(tzinfo=None) + timedelta(seconds=10)
+    m.force_sync()
+    same("ref_live_sync2")
+    proc = frg.FaceRecognitionProcessor(gal, matcher=matcher)
+    for comp, tag in ((A, "a"), (B, "b")):
+        view = m.get_embeddings_for_company(comp)
+        assert len(view) == len(g["ref_live_tenant_%s" % tag])
+        out = proc.recognize(g["mgr_queries"], view.company_id)
+        assert [x["person_id"] is not None for x in out] == list(g["ref_live_match_%s_known" % tag])
+        assert np.abs(np.array([x["recognition_score"] for x in out], np.float32)
+                      - g["ref_live_match_%s_score" % tag]).max() <= 1e-4
+
+
+def test_sharded_world1_embedding_manager_golden(golden):
+    import facerecognition_infrenceengine_b200 as frg
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
+    g = golden("managers.npz")
+    store = frg.GalleryStore(dim=g["stored"].shape[1], capacity=64)
+    gal = ShardedGallery(dim=store.dim, device=0, store=store, rank=0, world=1)
+    _manager_scenario(frg, gal, ShardedMatcher(gal), lambda E, V: frg.ListSource(E, V), g)
+    store.close()
+
+
 WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
@@ -155,6 +227,18 @@ for mm in (ShardedMatcher(g2, exchange="p2p"), ShardedMatcher(g2, exchange="nccl
                 assert bool(acc[fi]) == bool(np.float32(want[1]) >= np.float32(0.4))
 if dist.get_rank() == 0:
     print("ENROL_OK world=%%d" %% dist.get_world_size())
+# EmbeddingManager + FaceRecognitionProcessor over the sharded gallery, documents visible to rank 0 only
+sys.path.insert(0, os.path.join(%r, "tests"))
+from test_gpu_sharded import _manager_scenario
+gm = np.load(os.path.join(%r, "tests", "golden", "managers.npz"))
+ctl = dist.new_group(backend="gloo")
+store3 = frg.GalleryStore(dim=gm["stored"].shape[1], capacity=64, device=local)
+g3 = ShardedGallery(dim=store3.dim, device=local, store=store3)
+_manager_scenario(frg, g3, ShardedMatcher(g3),
+                  lambda E, V: frg.BroadcastSource(frg.ListSource(E, V) if dist.get_rank() == 0 else frg.ListSource([], []), ctl),
+                  gm, rank=dist.get_rank())
+if dist.get_rank() == 0:
+    print("MANAGER_OK world=%%d" %% dist.get_world_size())
 # every rank holds the same merged result
 chk = a[0].clone()
 dist.broadcast(chk, src=0)
@@ -170,7 +254,7 @@ def test_sharded_two_ranks_nccl(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % ROOT)
+    script.write_text(WORKER % (ROOT, ROOT, ROOT))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=600)
@@ -178,3 +262,4 @@ def test_sharded_two_ranks_nccl(tmp_path):
     assert "SHARDED_OK world=2" in r.stdout
     assert "P2P_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ENROL_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MANAGER_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -114,6 +114,11 @@ class _HostShard:
             assert 0 <= r < len(self.vecs), "removal routed to a rank that does not own the row"
             self.tags[r] = -1
 
+    def stats(self):
+        from types import SimpleNamespace
+        return SimpleNamespace(rows=len(self.vecs), live=int((self.tags >= 0).sum()), capacity=len(self.vecs),
+                               bytes=self.vecs.nbytes, version=0)
+
 
 def _enrolment_scenario(rank, world, F, k):
     """Sharded upsert / remove / tenant filter against the reference's dict semantics (GalleryOracle follows
@@ -215,3 +220,94 @@ def test_matcher_wiring_without_injected_pieces():
     import pytest
     with pytest.raises(ValueError):
         ShardedMatcher(g, exchange="smoke-signals")
+
+
+# ---- EmbeddingManager over a sharded gallery: the reference's own manager scenario (tests/golden/managers.npz,
+#      produced by the unmodified infrenceServer.EmbeddingManager under stubs) replayed on two ranks
+def _manager_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from datetime import datetime, timedelta, timezone
+        import facerecognition_infrenceengine_b200 as frg
+        from facerecognition_infrenceengine_b200.sharded import ShardedGallery
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "managers.npz"))
+        st = g["stored"]
+        A, B = "a" * 24, "b" * 24
+        t0 = datetime(2026, 1, 1)
+
+        def emp(i):
+            return {"_id": "%024x" % i, "embedding": st[i], "companyId": A if i < 8 or i >= 12 else B,
+                    "status": "active", "blacklisted": False, "lastUpdated": t0, "employeeName": "e%d" % i}
+
+        def vis(i):
+            return {"_id": "%024x" % (100 + i), "embedding": st[20 + i], "companyId": A if i < 3 else B,
+                    "lastUpdated": t0, "visitorName": "v%d" % i}
+
+        E = [emp(i) for i in range(12)]
+        E[3]["status"] = "inactive"; E[5]["blacklisted"] = True; E[6]["embedding_status"] = "pending"
+        V = [vis(i) for i in range(6)]
+        V[4]["embedding_status"] = "pending"
+        # only rank 0 can see the documents; the others receive them through the broadcast
+        src = frg.BroadcastSource(frg.ListSource(E, V) if rank == 0 else frg.ListSource([], []))
+        gal = ShardedGallery(dim=st.shape[1], store=_HostShard(st.shape[1]))
+        m = frg.EmbeddingManager(src, mode="live", store=gal)
+
+        def same(prefix):
+            ref_ids, ref_G = list(g[prefix + "_ids"]), g[prefix + "_G"]
+            assert gal.ids() == ref_ids, (prefix, gal.ids(), ref_ids)
+            lo, hi = gal.bounds[rank]
+            assert len(gal.store.vecs) == hi - lo
+            mine = 0
+            for i, pid in enumerate(ref_ids):                  # every live id sits on exactly its owner rank
+                r = gal.row_of(pid)
+                if lo <= r < hi:
+                    mine += 1
+                    a, b = gal.store.vecs[r - lo], ref_G[i]
+                    assert gal.store.tags[r - lo] >= 0
+                    assert (np.isnan(a) == np.isnan(b)).all()         # a zero template is a NaN row on both sides
+                    assert np.isnan(b).all() or np.nanmax(np.abs(a - b)) <= 2e-7
+            assert int((gal.store.tags >= 0).sum()) == mine     # and nothing else is live here
+            tot = torch.tensor([mine]); dist.all_reduce(tot)
+            assert int(tot) == len(ref_ids)
+
+        same("ref_live_load")
+        s = m.get_stats()
+        assert [s["total_embeddings"], s["employees"], s["visitors"]] == list(g["ref_live_load_stats"])
+        assert gal.bounds[0][1] - gal.bounds[0][0] in (len(gal) // 2, (len(gal) + 1) // 2)   # balanced initial load
+        later = datetime.now(timezone.utc).replace(tzinfo=None) + timedelta(seconds=5)
+        if rank == 0:
+            E[1]["embedding"] = st[30]; E[1]["lastUpdated"] = later
+            E[0]["status"] = "inactive"
+            E.append(dict(emp(12), lastUpdated=later))
+            V[1]["embedding"] = st[31]; V[1]["lastUpdated"] = later
+            E[3]["status"] = "active"; E[3]["lastUpdated"] = later
+        m.force_sync()
+        same("ref_live_sync1")
+        if rank == 0:
+            E[0]["status"] = "active"
+            E[0]["lastUpdated"] = datetime.now(timezone.utc).replace(tzinfo=None) + timedelta(seconds=10)
+        m.force_sync()
+        same("ref_live_sync2")
+        for comp, key in ((A, "ref_live_tenant_a"), (B, "ref_live_tenant_b")):
+            assert len(m.get_embeddings_for_company(comp)) == len(g[key])
+            code = gal.tenant_code(comp, create=False)
+            assert sorted(p for p in gal.ids() if gal._tenant_of[p] == code) == list(g[key])
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_embedding_manager_replays_reference_scenario_gloo():
+    import facerecognition_infrenceengine_b200  # noqa: F401
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_manager_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert dict(ret) == {0: 1, 1: 1}
