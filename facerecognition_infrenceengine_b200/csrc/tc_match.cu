@@ -957,8 +957,9 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   const int tile_rows = pl->pair ? 2 * kTileR : kTileR;
   // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
   // leaves >= 16 K sampled rows
+  static const int64_t pre_min_rows = []() { const char* e = getenv("FRG_TC_PRE_MIN_ROWS"); const long v = e ? atol(e) : 16384; return int64_t(v < 1 ? 16384 : v); }();
   int stride = 1;
-  while (stride < 64 && rows / (stride * 2) >= 16384) stride *= 2;
+  while (stride < 64 && rows / (stride * 2) >= pre_min_rows) stride *= 2;
   pl->stride = stride;
   const int tiles_all = int((rows + tile_rows - 1) / tile_rows);
   auto chunks_for = [&](int tiles) {
