@@ -23,10 +23,12 @@ DUPLICATE_THRESHOLD = 0.4      # trainingServer.py:71
 
 
 class EnrolmentChecker:
-    def __init__(self, store: GalleryStore, duplicate_threshold: float = DUPLICATE_THRESHOLD,
-                 similarity_threshold: float = SIMILARITY_THRESHOLD):
+    def __init__(self, store, duplicate_threshold: float = DUPLICATE_THRESHOLD,
+                 similarity_threshold: float = SIMILARITY_THRESHOLD, matcher=None):
+        """store: a ``GalleryStore``, or a ``ShardedGallery`` with ``matcher=ShardedMatcher(store)`` (the
+        duplicate scan then runs on every rank's block and the lowest global row wins; collective)."""
         self.store = store
-        self.matcher = Matcher(store)
+        self.matcher = matcher if matcher is not None else Matcher(store)
         self.duplicate_threshold = duplicate_threshold
         self.similarity_threshold = similarity_threshold
         self._scratch: Optional[GalleryStore] = None
@@ -47,7 +49,8 @@ class EnrolmentChecker:
         if n < 2:
             return True, None
         if self._scratch is None:
-            self._scratch = GalleryStore(dim=self.store.dim, capacity=16, device=self.store.device, bf16_plane=False)
+            dev = self.store.device if getattr(self.store, "device", None) is not None else self.store.store.device
+            self._scratch = GalleryStore(dim=self.store.dim, capacity=16, device=dev, bf16_plane=False)
         sc = self._scratch
         if sc.rows:
             sc.remove_rows(list(range(sc.rows)))

@@ -404,6 +404,44 @@ class ShardedMatcher:
             out.ids = self.ids_of(out.rows)
         return out
 
+    def first_above(self, Q: np.ndarray, threshold: float, strict: bool = False, company_id: Optional[str] = None,
+                    query_prenormalised: bool = False, local_first: Optional[Callable] = None):
+        """First row IN GLOBAL GALLERY ORDER whose exact score reaches the threshold - the rule of the enrol-time
+        duplicate check (trainingServer.py:170-200) over a sharded gallery: every rank scans its block
+        (frg_first_match, global rows), the lowest global row over the ranks wins (one MIN all-reduce) and its
+        owner's score is taken (one MAX all-reduce).  Collective.  Returns (rows int64 [F], scores fp32 [F]) as
+        numpy arrays, row -1 / score -1.0 where no rank has a hit."""
+        import torch
+        import torch.distributed as dist
+        Q = np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.g.dim)
+        tenant = -1 if company_id is None else self.g.tenant_code(company_id, create=False)
+        if local_first is not None:                      # host-logic tests
+            rows, scores = local_first(Q, threshold, strict, tenant)
+        else:
+            F = len(Q)
+            rows, scores = np.empty(F, np.int64), np.empty(F, np.float32)
+            p = N.MatchParams(metric=N.METRICS[self.metric], variant=N.VARIANTS["scan_f32"],
+                              threshold=float(np.float32(threshold)), tenant=int(tenant),
+                              row_offset=int(self.g.offset),
+                              flags=(N.FIRST_STRICT if strict else 0) | (N.QUERY_PRENORMALISED if query_prenormalised else 0),
+                              reserved=0)
+            N.check(N.lib.frg_first_match_host(self.g.store.handle, Q.ctypes.data_as(C.c_void_p), F, C.byref(p),
+                                               rows.ctypes.data_as(C.c_void_p), scores.ctypes.data_as(C.c_void_p)))
+        if self.g.world == 1:
+            return rows, scores
+        on_gpu = dist.get_backend(self.g.group) == "nccl"
+        dev = torch.device("cuda", self.g.store.device if self.g.device is None else self.g.device) if on_gpu else "cpu"
+        none = np.iinfo(np.int64).max
+        r = torch.from_numpy(np.where(rows >= 0, rows, none)).to(dev)
+        best = r.clone()
+        dist.all_reduce(best, op=dist.ReduceOp.MIN, group=self.g.group)
+        sc = torch.from_numpy(scores).to(dev)
+        sc = torch.where((r == best) & (best != none), sc, torch.full_like(sc, -float("inf")))
+        dist.all_reduce(sc, op=dist.ReduceOp.MAX, group=self.g.group)
+        best, sc = best.cpu().numpy(), sc.cpu().numpy()
+        hit = best != none
+        return np.where(hit, best, -1), np.where(hit, sc, np.float32(-1.0)).astype(np.float32)
+
     def ids_of(self, rows) -> List[List[Optional[str]]]:
         """Global rows of a match result -> id strings (None for unfilled slots)."""
         r = rows.cpu().numpy() if hasattr(rows, "cpu") else np.asarray(rows)

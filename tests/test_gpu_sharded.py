@@ -225,6 +225,15 @@ for mm in (ShardedMatcher(g2, exchange="p2p"), ShardedMatcher(g2, exchange="nccl
             if want[0] is not None:
                 assert abs(float(scores[fi, 0]) - float(want[1])) <= 1e-4
                 assert bool(acc[fi]) == bool(np.float32(want[1]) >= np.float32(0.4))
+# enrol-time duplicate check over the shards (trainingServer.py:170-200): first hit in GLOBAL order
+chk = frg.EnrolmentChecker(g2, matcher=ShardedMatcher(g2, exchange="nccl"))
+two_hits = np.float32(0.6) * refv[ids2[n2 - 3]] + np.float32(0.8) * refv[ids2[20]]     # rows on different ranks
+for company in (None, "acme", "globex", "nobody"):
+    sub = [p_ for p_ in order if company is None or refc[p_] == company]
+    for probe_v in (two_hits, refv["new-b"], V2[77], rng.standard_normal(d).astype(np.float32)):
+        where = mo.duplicate_check(probe_v, [refv[p_] for p_ in sub], 0.4)
+        dup, pid = chk.check_duplicate_face(probe_v, company)
+        assert dup == (where >= 0) and (pid == sub[where] if dup else pid is None), (company, dup, pid, where)
 if dist.get_rank() == 0:
     print("ENROL_OK world=%%d" %% dist.get_world_size())
 # EmbeddingManager + FaceRecognitionProcessor over the sharded gallery, documents visible to rank 0 only

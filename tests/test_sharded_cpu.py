@@ -170,6 +170,37 @@ def _enrolment_scenario(rank, world, F, k):
         scores_out.copy_(torch.from_numpy(s))
 
     m = ShardedMatcher(g, local_match=local_match, merge=_merge_numpy)
+
+    # first row in GLOBAL order above a threshold (trainingServer.py:170-200 over the shards): each rank scans
+    # its block with the oracle's duplicate_check, the lowest global row over the ranks wins
+    def local_first(Qn, thr, strict, tenant):
+        rows, scores = np.full(len(Qn), -1, np.int64), np.full(len(Qn), -1.0, np.float32)
+        for f, q in enumerate(Qn):
+            qn = mo.normalise(q)
+            for r in range(len(g.store.vecs)):
+                if g.store.tags[r] < 0 or (tenant >= 0 and g.store.tags[r] != tenant):
+                    continue
+                sc = np.dot(qn, g.store.vecs[r])
+                if (sc > np.float32(thr)) if strict else (sc >= np.float32(thr)):
+                    rows[f], scores[f] = r + g.offset, sc
+                    break
+        return rows, scores
+
+    probe = np.stack([0.6 * ref_vecs[ids0[n0 - 2]] + 0.8 * ref_vecs[ids0[3]],       # two hits, on different ranks
+                      ref_vecs["new-b"], rng.standard_normal(d).astype(np.float32)])
+    for company in (None, "acme", "globex"):
+        rows_f, sc_f = m.first_above(probe, 0.4, strict=True, company_id=company, local_first=local_first)
+        sub = [p for p in ref_ids if company is None or ref_comp[p] == company]
+        for f in range(len(probe)):
+            where = mo.duplicate_check(probe[f], [ref_vecs[p] for p in sub], 0.4)       # the reference's scan
+            dup = where >= 0
+            assert (rows_f[f] >= 0) == dup, (company, f)
+            if dup:
+                assert m.g.id_of(rows_f[f]) == sub[where]
+                assert abs(sc_f[f] - np.dot(mo.normalise(probe[f]), ref_vecs[sub[where]])) < 1e-6
+            else:
+                assert sc_f[f] == np.float32(-1.0)
+
     Q = np.stack([ref_vecs[p] for p in (ids0[2], "new-a", ids0[5], ids0[n0 - 2], ids0[7])][:max(1, F)])
     for company in (None, "acme", "globex", "initech", "no-such-company"):
         rows, scores, acc = m.match(torch.from_numpy(Q.copy()), k, 0.4, company_id=company)
