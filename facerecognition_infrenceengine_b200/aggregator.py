@@ -22,10 +22,13 @@ class BatchAggregator:
     """submit(embeddings [f, dim], company_id) -> Future of (rows [f,k], scores [f,k], accept [f]).
 
     A batch is flushed when `max_batch` faces are waiting or the oldest request is `max_delay_ms` old.
-    Requests with different company_id are batched separately (the tenant filter is per call)."""
+    Requests with different company_id are batched separately (the tenant filter is per call).
+    `workers` batches are in flight at once, each on its own host thread (= its own CUDA stream inside
+    frg_match_host): with two, the copies and launch latency of one batch hide behind the kernels of the
+    other (bench `e2e.concurrent`: +10 % at 1024 queries per batch, +30 % at 64)."""
 
     def __init__(self, match_fn: Callable[[np.ndarray, Optional[str]], Tuple[np.ndarray, np.ndarray, np.ndarray]],
-                 max_batch: int = 256, max_delay_ms: float = 5.0):
+                 max_batch: int = 256, max_delay_ms: float = 5.0, workers: int = 1):
         self.match_fn = match_fn
         self.max_batch = max_batch
         self.max_delay = max_delay_ms / 1e3
@@ -34,8 +37,9 @@ class BatchAggregator:
         self._stop = False
         self.batches = 0
         self.faces = 0
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        self._threads = [threading.Thread(target=self._run, daemon=True) for _ in range(max(1, int(workers)))]
+        for t in self._threads:
+            t.start()
 
     def submit(self, embeddings: np.ndarray, company_id: Optional[str] = None) -> Future:
         fut: Future = Future()
@@ -50,8 +54,9 @@ class BatchAggregator:
     def close(self):
         with self._cv:
             self._stop = True
-            self._cv.notify()
-        self._thread.join(timeout=5)
+            self._cv.notify_all()
+        for t in self._threads:
+            t.join(timeout=5)
 
     def _take(self):
         """Called with the lock held: the requests of the oldest request's tenant, up to max_batch faces."""
@@ -74,18 +79,21 @@ class BatchAggregator:
                 if self._stop and not self._pending:
                     return
                 # wait for more faces, but never past the oldest request's deadline
-                while not self._stop:
+                while not self._stop and self._pending:
                     waiting = sum(len(p[0]) for p in self._pending)
                     left = self._pending[0][3] + self.max_delay - time.monotonic()
                     if waiting >= self.max_batch or left <= 0:
                         break
                     self._cv.wait(timeout=left)
+                if not self._pending:            # another worker took the batch while this one waited
+                    continue
                 take, tenant = self._take()
             try:
                 Q = np.concatenate([t[0] for t in take], axis=0)
                 rows, scores, accept = self.match_fn(Q, tenant)
-                self.batches += 1
-                self.faces += len(Q)
+                with self._cv:
+                    self.batches += 1
+                    self.faces += len(Q)
                 o = 0
                 for e, _, fut, _ in take:
                     fut.set_result((rows[o:o + len(e)], scores[o:o + len(e)], accept[o:o + len(e)]))

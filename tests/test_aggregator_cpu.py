@@ -85,3 +85,28 @@ def test_many_producers():
             assert (rows == i * 100 + j).all()
     assert sum(c[0] for c in calls) == 8 * 20 * 3 and len(calls) < 8 * 20      # it did batch
     agg.close()
+
+
+def test_two_workers_keep_two_batches_in_flight():
+    """workers=2: while one batch is inside the matcher the next one is already running (its copies and
+    launches overlap the first one's kernels on the GPU); results still route back to their requests."""
+    lock = threading.Lock()
+    state = {"now": 0, "peak": 0, "calls": 0}
+
+    def slow(Q, tenant):
+        with lock:
+            state["now"] += 1
+            state["calls"] += 1
+            state["peak"] = max(state["peak"], state["now"])
+        time.sleep(0.05)
+        with lock:
+            state["now"] -= 1
+        return Q[:, :1].astype(np.int64), Q[:, 1:2].copy(), np.ones(len(Q), bool)
+
+    agg = BatchAggregator(slow, max_batch=4, max_delay_ms=1, workers=2)
+    futs = [agg.submit(frame(i, 4)) for i in range(8)]           # 8 full batches
+    for i, f in enumerate(futs):
+        rows, scores, acc = f.result(timeout=10)
+        assert (rows[:, 0] == i).all() and list(scores[:, 0]) == [0, 1, 2, 3]
+    agg.close()
+    assert state["calls"] == 8 and state["peak"] == 2 and agg.batches == 8 and agg.faces == 32
