@@ -342,3 +342,69 @@ def test_sharded_embedding_manager_replays_reference_scenario_gloo():
         p.join(timeout=180)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert dict(ret) == {0: 1, 1: 1}
+
+
+# ---- property: any sequence of upserts / removals over W ranks leaves the shards holding exactly what the
+#      reference's dict holds, in the dict's order (no communication is involved: the ranks are emulated in
+#      one process, each with its own gallery object and host shard, all receiving the same calls)
+from hypothesis import given, settings          # noqa: E402
+from hypothesis import strategies as st         # noqa: E402
+
+
+@st.composite
+def _op_sequences(draw):
+    world = draw(st.sampled_from([1, 2, 3, 8]))
+    n_ops = draw(st.integers(1, 12))
+    ops = []
+    for _ in range(n_ops):
+        if draw(st.integers(0, 3)) == 0:
+            ops.append(("remove", draw(st.lists(st.integers(0, 15), min_size=1, max_size=4))))
+        else:
+            ids = draw(st.lists(st.integers(0, 15), min_size=1, max_size=6))
+            ops.append(("upsert", ids, draw(st.integers(0, 2 ** 31 - 1))))
+    return world, ops
+
+
+@settings(max_examples=120, deadline=None)
+@given(_op_sequences())
+def test_sharded_upserts_follow_the_dict(data):
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery
+    world, ops = data
+    d = 8
+    gals = [ShardedGallery(dim=d, store=_HostShard(d), rank=r, world=world) for r in range(world)]
+    ref = {}                                                   # the reference's Dict[str, np.ndarray]
+    comp = {}
+    for op in ops:
+        if op[0] == "remove":
+            ids = ["p%d" % i for i in op[1]]
+            for g in gals:
+                g.remove(ids)
+            for p in ids:
+                ref.pop(p, None)
+                comp.pop(p, None)
+        else:
+            ids = ["p%d" % i for i in op[1]]
+            rng = np.random.default_rng(op[2])
+            V = rng.integers(1, 9, size=(len(ids), d)).astype(np.float32)
+            C_ = ["c%d" % (i % 3) for i in op[1]]
+            for g in gals:
+                g.upsert(ids, V, C_)
+            for p, v, c in zip(ids, V, C_):
+                ref[p] = mo.normalise(v)                       # dict assignment: position of the first, value of the last
+                comp[p] = c
+    for g in gals:
+        assert g.ids() == list(ref) and len(g) == len(ref)
+        assert g.bounds == gals[0].bounds and g.bounds[-1][1] == g.total_rows
+        assert all(b[1] == g.bounds[i + 1][0] for i, b in enumerate(g.bounds[:-1]))
+    live = 0
+    for r, g in enumerate(gals):
+        lo, hi = g.bounds[r]
+        assert len(g.store.vecs) == hi - lo
+        live += int((g.store.tags >= 0).sum())
+    assert live == len(ref)
+    for p, v in ref.items():
+        row = gals[0].row_of(p)
+        owner = next(r for r, (lo, hi) in enumerate(gals[0].bounds) if lo <= row < hi)
+        sh = gals[owner].store
+        assert np.array_equal(sh.vecs[row - gals[owner].bounds[owner][0]], v)
+        assert sh.tags[row - gals[owner].bounds[owner][0]] == gals[owner].tenant_code(comp[p], create=False)
