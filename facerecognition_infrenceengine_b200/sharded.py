@@ -21,6 +21,8 @@ The reference has no distributed code at all; this file is new capability, not a
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -41,6 +43,16 @@ def block_layout(F: int, k: int) -> Tuple[int, int]:
 def shard_bounds(n_rows: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous, balanced row blocks: rank r owns [lo, hi)."""
     return [((n_rows * r) // world, (n_rows * (r + 1)) // world) for r in range(world)]
+
+
+def _locked(fn):
+    """Id-level calls of one rank are serialised (the sync thread mutates the tables the matcher threads read):
+    the reference's embeddings_lock."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with self._lock:
+            return fn(self, *a, **kw)
+    return wrapper
 
 
 def owner_of(row: int, bounds: List[Tuple[int, int]]) -> int:
@@ -71,6 +83,7 @@ class ShardedGallery:
         self._tenant_of: Dict[str, int] = {}     # id -> tenant code (company subset sizes without a device read)
         self._removed: set = set()   # global rows tombstoned so far
         self._anon = 0               # live rows without an id entry (synthetic fills)
+        self._lock = threading.RLock()
 
     # ---- layout ---------------------------------------------------------------------------------
     @property
@@ -90,6 +103,7 @@ class ShardedGallery:
         self.bounds = shard_bounds(n_rows, self.world)
         return self.bounds[self.rank]
 
+    @_locked
     def fill_synthetic(self, n_rows: int, seed: int = 1234):
         """Every rank materialises ITS block of the frg-synth-v1 gallery on its own GPU; row r depends
         only on (seed, r), so the data is identical at 1, 2, 4 or 8 GPUs and never touches the host."""
@@ -97,6 +111,7 @@ class ShardedGallery:
         self.store.fill_synthetic(hi - lo, lo, seed)
         self._anon = n_rows
 
+    @_locked
     def append_local(self, vecs: np.ndarray, tags=None, prenormalised: bool = False):
         """Collective enrolment: every rank passes the SAME batch; each keeps the rows whose global
         position falls into its block after the gallery has been re-planned to the new size... which
@@ -110,6 +125,7 @@ class ShardedGallery:
         return hi
 
     # ---- id-level API (the dict), collective: every rank makes the same calls in the same order ----
+    @_locked
     def tenant_code(self, company_id: Optional[str], create: bool = True) -> int:
         """Same codes on every rank because every rank sees the same upserts in the same order."""
         if company_id is None:
@@ -130,6 +146,7 @@ class ShardedGallery:
     def row_of(self, pid: str) -> int:
         return self._row_of.get(str(pid), -1)
 
+    @_locked
     def id_of(self, row: int) -> Optional[str]:
         """Id of a GLOBAL row; rows filled synthetically carry the implicit id ``"%024x" % row``."""
         row = int(row)
@@ -143,10 +160,12 @@ class ShardedGallery:
     def metadata(self, pid: str) -> Optional[Dict]:
         return self._meta.get(str(pid))
 
+    @_locked
     def ids(self) -> List[str]:
         """Live ids in global gallery (= dict) order."""
         return [self._id_of[r] for r in sorted(self._id_of)]
 
+    @_locked
     def count_tenant(self, company_id: Optional[str]) -> int:
         code = self.tenant_code(company_id, create=False)
         return sum(1 for c in self._tenant_of.values() if c == code)
@@ -155,6 +174,7 @@ class ShardedGallery:
         """Device-side figures of THIS rank's shard."""
         return self.store.stats()
 
+    @_locked
     def load(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
              meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
         """Initial load of an EMPTY sharded gallery (the reference's load_all_embeddings,
@@ -177,6 +197,7 @@ class ShardedGallery:
             for p, m in zip(ids, meta):
                 self._meta[str(p)] = m
 
+    @_locked
     def upsert(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
                meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
         """``self.embeddings[id] = v / ||v||`` (infrenceServer.py:273,326; peopleCount.py:790,808) over the
@@ -209,6 +230,7 @@ class ShardedGallery:
             for p, m in zip(ids, meta):
                 self._meta[str(p)] = m
 
+    @_locked
     def remove(self, ids: Iterable[str]) -> int:
         """``del self.embeddings[id]`` (infrenceServer.py:248-251): the owner rank tombstones the row; a later
         re-enrolment appends at the end, as ``del d[k]; d[k] = v`` does.  Unknown ids are ignored."""
@@ -230,6 +252,7 @@ class ShardedGallery:
             self.store.remove_rows(local)
         return gone
 
+    @_locked
     def remove_rows_global(self, rows: Iterable[int]) -> int:
         """Tombstone GLOBAL rows that have no id entry (synthetic fills)."""
         lo, hi = self.bounds[self.rank]
