@@ -542,9 +542,25 @@ def ours_arm(args, rank, world):
         # BASELINE config 1 as the reference runs it: 10 000 x 512 gallery, 64 faces, ONE core
         G1 = G[:10000]
         Q1, _ = synth.queries(64, 10000, dim)
-        qps1, _, _ = run_cpu_loop(G1, Q1, 0.45, 1, 1, 0)
+        qps1, _, res1 = run_cpu_loop(G1, Q1, 0.45, 1, 1, 0)
+        # ... and the same frame through the GPU, end to end from host buffers (frg_match_host), as the
+        # reference's call site would use it: one call per frame, result waited for
+        st1 = frg.GalleryStore(dim=dim, capacity=10000, device=local)
+        st1.append_rows(G1, prenormalised=True)
+        m1 = frg.Matcher(st1)
+        for _ in range(20):
+            r1 = m1.match(Q1, 1, 0.45, with_ids=False)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            r1 = m1.match(Q1, 1, 0.45, with_ids=False)
+        gpu1_s = (time.perf_counter() - t0) / 200
+        same1 = all((a[0] is None and r_ < 0) or (a[0] is not None and int(a[0], 16) == r_) for a, r_ in zip(res1, r1.rows[:, 0])) \
+            and all(a[2] == bool(b) for a, b in zip(res1, r1.accept))
+        st1.close()
         cpu = {"value": qps, "unit": UNIT, "cores": procs, "kind": "port",
                "config1_10k_x_64_one_core_queries_per_s": qps1,
+               "config1_10k_x_64_gpu_e2e_queries_per_s": 64 / gpu1_s, "config1_gpu_ms_per_frame": gpu1_s * 1e3,
+               "config1_gpu_agrees": bool(same1),
                "sample": "%d queries over %d worker processes x %d rows, top-1 + threshold 0.45, "
                          "per-face Python loop of peopleCount.py:860-887" % (q_cpu, procs, n),
                "seconds": per_step, "gpu_agrees": bool(same)}
