@@ -275,7 +275,6 @@ int frg_store_destroy(frg_store* s) {
     cudaDeviceSynchronize();
     cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
     if (s->last_write) cudaEventDestroy(s->last_write);
-    ::operator delete(s->tmap_plane);
   }
   delete s;
   return FRG_OK;

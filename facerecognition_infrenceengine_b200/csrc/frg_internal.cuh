@@ -67,6 +67,23 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Function attributes are sticky per (function, device): set them once per thread and device instead of in front
+// of every launch (a handful of driver calls per match otherwise).
+template <typename F>
+inline cudaError_t func_attr_once(F* kern, cudaFuncAttribute attr, int value) {
+  struct Key { const void* f; int dev, attr, value; };
+  static thread_local std::vector<Key> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const void* f = reinterpret_cast<const void*>(kern);
+  for (const Key& k : done)
+    if (k.f == f && k.dev == dev && k.attr == int(attr) && k.value == value) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, attr, value);
+  if (e == cudaSuccess) done.push_back(Key{f, dev, int(attr), value});
+  return e;
+}
+
 struct DeviceInfo {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
@@ -110,7 +127,6 @@ struct frg_store {
   bool has_write = false;
   std::vector<cudaStream_t> readers;  // streams that matched since the last mutation
   // tensor-map cache for the TC variants (rebuilt when the plane pointer / row count changes)
-  void* tmap_plane = nullptr;         // opaque CUtensorMap storage (128 B)
   int64_t tmap_rows = -1;
   const void* tmap_ptr = nullptr;
 };

@@ -34,7 +34,7 @@ static int launch_merge(const float* scores, const RowT* rows, int parts, int nq
   const int ie = internal_euclid ? 1 : 0;
 #define FRG_MERGE(K)                                                                                            \
   do {                                                                                                          \
-    cudaFuncSetAttribute(merge_kernel<RowT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);           \
+    func_attr_once(merge_kernel<RowT, K>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);           \
     merge_kernel<RowT, K><<<grid, 128, 0, st>>>(scores, rows, parts, nq, k_in, k_out, metric, threshold,        \
                                                 row_offset, ie, score_stride, row_stride, out_rows, out_scores,  \
                                                 out_accept);                                                    \

@@ -104,7 +104,7 @@ int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_
                                   __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
                                   int* n_flagged, cudaStream_t st) {
   if (nq <= 0) return FRG_OK;
-  FRG_CUDA(cudaFuncSetAttribute(prepare_queries_euclid_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  FRG_CUDA(func_attr_once(prepare_queries_euclid_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   // group maxima start from "nothing seen" = the ordered key of -3e38 (Euclidean scores are unbounded below)
   uint32_t none_bits;
   const float none = kEuclidNone;
@@ -123,7 +123,7 @@ int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, fl
   if (nq <= 0) return FRG_OK;
   const int warps_per_block = 4;
   // same smem/L1 split as the tensor-core kernels that follow: no carve-out switch between launches
-  FRG_CUDA(cudaFuncSetAttribute(normalise_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  FRG_CUDA(func_attr_once(normalise_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   normalise_queries_kernel<<<(nq + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(
       q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, cand_total, n_flagged);
   note_launch(nullptr);

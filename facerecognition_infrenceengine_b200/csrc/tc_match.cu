@@ -1021,7 +1021,7 @@ static int launch_tc_scan(const CUtensorMap& qm, const CUtensorMap& gm, const CU
                           int qtiles, int chunks, cudaStream_t st) {
   const size_t smem = tc_smem_bytes(p.dim);
   auto kern = tc_scan_kernel<MODE, MASKED, PAIR>;
-  FRG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)));
+  FRG_CUDA(func_attr_once(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(qtiles, chunks);
   cfg.blockDim = dim3(kTcThreads);
@@ -1135,7 +1135,7 @@ int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_
   const int grid = nq;                                   // one CTA per query
   const int rs = rescore ? 1 : 0;
 #define FRG_SELECT_M(KK, EU)                                                                                    \
-  FRG_CUDA(cudaFuncSetAttribute(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+  FRG_CUDA(func_attr_once(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
   FRG_CUDA(launch_kernel(select_rescore_kernel<KK, EU>, dim3(grid), dim3(kSelectWarps * 32), 0, st, true, dense, \
       cnt, pl.stage_entries, nq, k, s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores,   \
       out_accept, flagged, n_flagged, push))

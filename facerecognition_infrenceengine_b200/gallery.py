@@ -25,7 +25,9 @@ from . import _native as N
 
 
 def _ptr(a: Optional[np.ndarray]):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    # the plain address: ndarray.ctypes.data_as() costs ~7 us per call, four of them were a third of a
+    # small frame's end-to-end time
+    return None if a is None else a.ctypes.data
 
 
 class GalleryStore:

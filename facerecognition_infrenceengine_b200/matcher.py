@@ -33,8 +33,8 @@ class MatchResult:
 
 
 def _params(metric: str, variant: str, threshold: float, tenant: int, row_offset: int) -> N.MatchParams:
-    return N.MatchParams(metric=N.METRICS[metric], variant=N.VARIANTS[variant], threshold=float(np.float32(threshold)),
-                         tenant=int(tenant), row_offset=int(row_offset), flags=0, reserved=0)
+    return N.MatchParams(N.METRICS[metric], N.VARIANTS[variant], float(np.float32(threshold)),
+                         int(tenant), int(row_offset), 0, 0)
 
 
 class Matcher:
@@ -54,9 +54,9 @@ class Matcher:
             out = MatchResult(np.empty((F, k), np.int64), np.empty((F, k), np.float32), np.zeros(F, np.uint8))
         tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
         p = _params(self.metric, variant, threshold, tenant, row_offset)
-        N.check(N.lib.frg_match_host(self.store.handle, Q.ctypes.data_as(C.c_void_p), F, int(k), C.byref(p),
-                                     out.rows.ctypes.data_as(C.c_void_p), out.scores.ctypes.data_as(C.c_void_p),
-                                     out.accept.ctypes.data_as(C.c_void_p)))
+        N.check(N.lib.frg_match_host(self.store.handle, Q.ctypes.data, F, int(k), C.byref(p),
+                                     out.rows.ctypes.data, out.scores.ctypes.data,
+                                     out.accept.ctypes.data))
         out.variant, out.launches = N.last_variant(), N.last_launch_count()
         if out.accept.dtype != np.bool_:
             out.accept = out.accept.view(np.bool_)
@@ -99,8 +99,8 @@ class Matcher:
         tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
         p = _params(self.metric, "scan_f32", threshold, tenant, 0)
         p.flags = (N.FIRST_STRICT if strict else 0) | (N.QUERY_PRENORMALISED if query_prenormalised else 0)
-        N.check(N.lib.frg_first_match_host(self.store.handle, Q.ctypes.data_as(C.c_void_p), F, C.byref(p),
-                                           rows.ctypes.data_as(C.c_void_p), scores.ctypes.data_as(C.c_void_p)))
+        N.check(N.lib.frg_first_match_host(self.store.handle, Q.ctypes.data, F, C.byref(p),
+                                           rows.ctypes.data, scores.ctypes.data))
         return rows, scores
 
 

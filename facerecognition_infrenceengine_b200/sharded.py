@@ -448,8 +448,8 @@ class ShardedMatcher:
                               row_offset=int(self.g.offset),
                               flags=(N.FIRST_STRICT if strict else 0) | (N.QUERY_PRENORMALISED if query_prenormalised else 0),
                               reserved=0)
-            N.check(N.lib.frg_first_match_host(self.g.store.handle, Q.ctypes.data_as(C.c_void_p), F, C.byref(p),
-                                               rows.ctypes.data_as(C.c_void_p), scores.ctypes.data_as(C.c_void_p)))
+            N.check(N.lib.frg_first_match_host(self.g.store.handle, Q.ctypes.data, F, C.byref(p),
+                                               rows.ctypes.data, scores.ctypes.data))
         if self.g.world == 1:
             return rows, scores
         on_gpu = dist.get_backend(self.g.group) == "nccl"
