@@ -124,11 +124,11 @@ class FaceRecognitionProcessor:
         store = self.store
         if len(embeddings) == 0 or len(store) == 0:      # `if not embeddings: return frame` (:523-525)
             return []
-        r = self._match(embeddings, 1, self.recognition_threshold, company_id)
+        r = self._match(embeddings, 1, self.recognition_threshold, company_id, with_ids=False)
         out = []
         for f in range(len(embeddings)):
             if r.accept[f]:
-                pid = r.ids[f][0]
+                pid = store.id_of(r.rows[f, 0])            # ids only for the faces that matched
                 info = store.metadata(pid) or {"name": pid, "type": "employee"}
                 out.append({"person_id": pid, "person_info": info, "recognition_score": r.scores[f, 0]})
             else:
@@ -159,16 +159,19 @@ class CameraProcessor:
         stats["faces"] = len(embeddings)
         if len(embeddings) == 0:
             return [], stats
-        r = self._match(embeddings, 1, self.recognition_threshold)
-        unknown_thr = np.float32(self.unknown_threshold)
+        r = self._match(embeddings, 1, self.recognition_threshold, with_ids=False)
+        # three-way decision in fp32 (peopleCount.py:876-887); ids are looked up only for recognised faces
+        accept = r.accept.tolist()
+        below = (r.scores[:, 0] < np.float32(self.unknown_threshold)).tolist()   # best_score stays -1 when nothing matched
+        rows, scores = r.rows[:, 0].tolist(), r.scores[:, 0].tolist()
         events = []
-        for f in range(len(embeddings)):
-            if r.accept[f]:
-                events.append(("recognized", r.ids[f][0], float(r.scores[f, 0])))
-                stats["recognized"] += 1
-            elif r.scores[f, 0] < unknown_thr:            # best_score stays -1 when nothing matched
+        for f in range(len(accept)):
+            if accept[f]:
+                events.append(("recognized", store.id_of(rows[f]), scores[f]))
+            elif below[f]:
                 events.append(("unknown", None, None))
-                stats["unknown"] += 1
             else:
                 events.append(("ignored", None, None))
+        stats["recognized"] = sum(accept)
+        stats["unknown"] = sum(1 for a, b in zip(accept, below) if b and not a)
         return events, stats
