@@ -1,0 +1,85 @@
+"""Host logic of the two drop-in processors on CPU: the decision code of FaceRecognitionProcessor
+(infrenceServer.py:545-552) and CameraProcessor (peopleCount.py:876-887) over the reference's own outputs
+(tests/golden/edge_cases.npz, cfg1_10k_x_64.npz: scores within 1 ulp of every threshold, ties, a NaN row, the
+nothing-matches frame).  The matcher is injected and answers with the reference's best row / score from the golden
+file (test infrastructure), so what is under test is only what the product does AFTER the kernels."""
+import numpy as np
+
+import facerecognition_infrenceengine_b200 as frg
+from facerecognition_infrenceengine_b200.matcher import MatchResult
+
+KIND = {"recognized": 0, "unknown": 1, "ignored": 2}
+
+
+class _Store:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def id_of(self, row):
+        return None if row < 0 else "%024x" % row
+
+    def metadata(self, pid):
+        return {"name": "n" + pid[-4:], "type": "employee"}
+
+
+class _GoldenMatcher:
+    """match_host() answers with the reference's own best row and score."""
+
+    def __init__(self, rows, scores):
+        self.rows, self.scores = np.asarray(rows, np.int64), np.asarray(scores, np.float32)
+        self.calls = []
+
+    def match_host(self, Q, k, threshold, company_id=None, variant="auto", with_ids=True):
+        self.calls.append((len(Q), k, float(threshold), company_id, with_ids))
+        rows = self.rows[:len(Q), None].copy()
+        scores = np.where(rows[:, 0] >= 0, self.scores[:len(Q)], np.float32(-1.0)).astype(np.float32)[:, None]
+        accept = (rows[:, 0] >= 0) & (scores[:, 0] >= np.float32(threshold))      # the kernels' fp32 compare
+        return MatchResult(rows, scores, accept)
+
+
+def _check(g, n):
+    Q = np.zeros((len(g["ref_best_row"]), 8), np.float32)
+    m = _GoldenMatcher(g["ref_best_row"], g["ref_best_score"])
+    store = _Store(n)
+    events, stats = frg.CameraProcessor(store, matcher=m).process(Q)
+    assert [KIND[e[0]] for e in events] == list(g["ref_campus_kind"])
+    rec = np.asarray(g["ref_campus_kind"]) == 0
+    assert [e[1] for e, ok in zip(events, rec) if ok] == ["%024x" % r for r in np.asarray(g["ref_best_row"])[rec]]
+    assert all(isinstance(e[2], float) for e, ok in zip(events, rec) if ok)       # float(best_score), :881
+    assert all(e[1] is None and e[2] is None for e, ok in zip(events, rec) if not ok)
+    assert stats["faces"] == len(Q) and stats["recognized"] == int(rec.sum())
+    assert stats["unknown"] == int((np.asarray(g["ref_campus_kind"]) == 1).sum())
+    live = frg.FaceRecognitionProcessor(store, matcher=m).recognize(Q, "acme")
+    got_row = np.array([int(x["person_id"], 16) if x["person_id"] else -1 for x in live])
+    assert (got_row == g["ref_live_row"]).all()
+    for x, row in zip(live, g["ref_live_row"]):
+        if row < 0:
+            assert x["person_info"] == {"name": "Unknown", "type": "unknown"} and x["recognition_score"] == 0
+        else:
+            assert x["person_info"]["type"] == "employee"
+    assert m.calls[0][1:] == (1, 0.45, None, False) and m.calls[1][3] == "acme"
+    assert abs(m.calls[1][2] - 0.4) < 1e-12
+
+
+def test_decisions_at_the_threshold_edges(golden):
+    g = golden("edge_cases.npz")
+    _check(g, len(g["gallery"]))
+
+
+def test_decisions_config1(golden):
+    g = golden("cfg1_10k_x_64.npz")
+    _check(g, int(g["n"]))
+    assert np.abs(np.array(g["ref_live_score"], np.float32)[g["ref_live_row"] >= 0]
+                  - np.array(g["ref_best_score"], np.float32)[g["ref_live_row"] >= 0]).max() == 0
+
+
+def test_empty_gallery_and_empty_frame():
+    m = _GoldenMatcher([], [])
+    assert frg.FaceRecognitionProcessor(_Store(0), matcher=m).recognize(np.zeros((3, 8), np.float32)) == []
+    assert frg.CameraProcessor(_Store(0), matcher=m).process(np.zeros((3, 8), np.float32)) == (
+        [], {"faces": 0, "recognized": 0, "unknown": 0})                         # peopleCount.py:850-851
+    ev, st = frg.CameraProcessor(_Store(5), matcher=m).process(np.zeros((0, 8), np.float32))
+    assert ev == [] and st == {"faces": 0, "recognized": 0, "unknown": 0} and m.calls == []
