@@ -305,10 +305,13 @@ class ShardedMatcher:
         cap, total = C.c_int64(), C.c_int64()
         N.check(N.lib.frg_exchange_bytes(self.g.world, F, k, C.byref(cap), C.byref(total)))
         group = self.g.group if self.g.group is not None else dist.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(group.group_name)
-        except Exception:            # noqa: BLE001  (newer torch: enabled implicitly)
-            pass
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")      # newer torch: enabled implicitly, the call only warns
+            try:
+                symm.enable_symm_mem_for_group(group.group_name)
+            except Exception:        # noqa: BLE001
+                pass
         t = symm.empty(int(total.value), dtype=torch.uint8, device=Q.device)
         t.zero_()                                    # flags and ticket start at 0; epochs start at 1
         hdl = symm.rendezvous(t, group)
