@@ -8,15 +8,18 @@
 // top-k has S >= tau - 2*eps, tau = k-th best coarse score.  Pipeline per batch:
 //
 //   1. pre-pass  (tc_scan_kernel<GROUPMAX>) over every stride-th 128-row tile of the scan plane:
-//      per query, the running maximum of each of 32 disjoint row groups (row mod 32).  The k-th
-//      largest of those 32 maxima (floor_kernel) is attained by k distinct rows, hence L[q] <= tau.
+//      per query, the running maximum of each of 32 disjoint row groups (row mod 32), folded across
+//      CTAs with atomicMax on order-preserving keys.  The k-th largest of those 32 maxima (derived by
+//      every FILTER thread in its prologue) is attained by k distinct rows, hence L[q] <= tau.
 //   2. filter    (tc_scan_kernel<FILTER>) over the whole plane: append every (row, S) with
 //      S >= L[q] - 2*eps to the query's candidate list (a few hundred rows out of 10^6).
 //   3. select + rescore (select_rescore_kernel): tau from the candidates, keep S >= tau - 2*eps,
 //      recompute those few scores EXACTLY in fp32 from the master rows (same arithmetic as the
 //      streaming scan), order by (score desc, row asc), apply the threshold.
 //   4. queries whose lists overflowed (adversarial duplicates, sparse tenants) are re-done by the
-//      exact streaming scan inside the same enqueue (fallback_* kernels) - never by the host.
+//      exact streaming scan inside the same enqueue (scan_f32_flagged_kernel) - never by the host.
+//   For a handful of queries (nq <= 8) steps 1 and 2 run as ONE kernel (MODE = FUSED: every CTA probes
+//   its first tile, publishes the group maxima, derives the floor, filters, re-visits the probe tile).
 //
 // Kernel anatomy (one CTA per SM, 320 threads):
 //   warp 0   TMA producer: gallery tiles [128 rows x 64 k] bf16, 128B-swizzled, 6-stage mbarrier ring
