@@ -165,6 +165,23 @@ class GalleryStore:
                 return "%024x" % (g0 + row - r0)
         return None
 
+    def ids_of(self, rows) -> List[List[Optional[str]]]:
+        """id_of over a whole [F, k] result (one pass over plain Python ints: ~0.1 us per slot)."""
+        get, anon = self._id_of.get, self._anon
+
+        def one(r):
+            if r < 0:
+                return None
+            pid = get(r)
+            if pid is None:
+                for r0, n, g0 in anon:
+                    if r0 <= r < r0 + n:
+                        return "%024x" % (g0 + r - r0)
+            return pid
+
+        rows = np.asarray(rows)
+        return [[one(r) for r in rr] for rr in rows.reshape(len(rows), -1).tolist()]
+
     def metadata(self, pid: str) -> Optional[Dict]:
         return self._meta.get(str(pid))
 

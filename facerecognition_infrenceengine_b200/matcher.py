@@ -61,7 +61,7 @@ class Matcher:
         if out.accept.dtype != np.bool_:
             out.accept = out.accept.view(np.bool_)
         if with_ids:
-            out.ids = [[self.store.id_of(r) for r in rr] for rr in out.rows]
+            out.ids = self.store.ids_of(out.rows)
         return out
 
     # ---- device tensors in/out, enqueued on the caller's stream (torch is only the allocator here)
