@@ -171,6 +171,56 @@ static int count_live(frg_store* s) {
   return FRG_OK;
 }
 
+// ---- tenant extents (frg_store::extents); s->mu held
+static void extent_add(frg_store* s, int32_t tag, int64_t lo, int64_t hi) {
+  if (tag < 0 || hi <= lo) return;
+  auto it = s->extents.find(tag);
+  if (it == s->extents.end()) { s->extents.emplace(tag, frg_store::Extent{lo, hi}); return; }
+  if (lo < it->second.lo) it->second.lo = lo;
+  if (hi > it->second.hi) it->second.hi = hi;
+}
+
+// rows / tags are HOST arrays (or null: append at `base` / tag 0)
+static void extents_note_upsert(frg_store* s, const int64_t* hrows, const int32_t* htags, int64_t n, int64_t base) {
+  if (!htags && !hrows) { extent_add(s, 0, base, base + n); return; }
+  // runs of equal tags over consecutive rows (bulk loads) cost one map update each
+  int64_t i = 0;
+  while (i < n) {
+    const int32_t tag = htags ? htags[i] : 0;
+    int64_t lo = hrows ? hrows[i] : base + i, hi = lo + 1;
+    int64_t j = i + 1;
+    while (j < n && (htags ? htags[j] : 0) == tag) {
+      const int64_t r = hrows ? hrows[j] : base + j;
+      if (r < lo) lo = r;
+      if (r + 1 > hi) hi = r + 1;
+      ++j;
+    }
+    extent_add(s, tag, lo, hi);
+    i = j;
+  }
+}
+
+// the whole gallery, or - for a tenant-filtered call whose tag extents are known - only the row window that
+// tenant's rows can sit in (FRG_TENANT_WINDOW=0 turns the window off)
+static GalleryWindow window_of(const frg_store* s, int32_t tenant) {
+  GalleryWindow w;
+  w.master = s->master; w.plane = s->plane; w.tags = s->tags; w.gmax_bits = s->gmax_bits;
+  w.rows = s->rows; w.row0 = 0; w.dim = s->dim; w.plane_dim = s->plane_dim; w.flags = s->flags;
+  w.maybe_dead = s->maybe_dead;
+  static const bool on = []() { const char* e = getenv("FRG_TENANT_WINDOW"); return !e || atoi(e) != 0; }();
+  if (on && tenant >= 0 && s->extents_known) {
+    int64_t lo = 0, hi = 0;
+    auto it = s->extents.find(tenant);
+    if (it != s->extents.end()) { lo = it->second.lo; hi = it->second.hi < s->rows ? it->second.hi : s->rows; }
+    if (hi < lo) hi = lo;
+    w.row0 = lo; w.rows = hi - lo;
+    if (w.master) w.master += lo * s->dim;
+    if (w.plane) w.plane += lo * s->plane_dim;
+    w.tags += lo;
+  }
+  return w;
+}
+
 }  // namespace frg
 
 using namespace frg;
@@ -299,8 +349,10 @@ int frg_store_stats(frg_store* s, frg_store_stats_t* out) {
   return FRG_OK;
 }
 
+// hrows / htags: HOST copies of rows / tags when the caller has them (host_known), for the tenant extents
 static int upsert_impl(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
-                       int64_t n, uint32_t flags, void* stream, bool tags_may_be_negative) {
+                       int64_t n, uint32_t flags, void* stream, bool tags_may_be_negative,
+                       bool host_known, const int64_t* hrows, const int32_t* htags) {
   if (!s || (n > 0 && !vecs) || n < 0) { set_error("upsert: bad argument"); return FRG_ERR_INVALID; }
   if (n == 0) return FRG_OK;
   DeviceGuard g(s->device);
@@ -311,6 +363,8 @@ static int upsert_impl(frg_store* s, const int64_t* rows, const float* vecs, con
   const bool normalise = !(flags & FRG_ROWS_PRENORMALISED) && !(s->flags & FRG_STORE_RAW);
   FRG_CHECK(launch_ingest(vecs, rows, tags, n, s->rows, s->dim, normalise, s->master, s->plane, s->plane_dim,
                           s->gmax_bits, s->tags, st));
+  if (host_known) extents_note_upsert(s, hrows, htags, n, s->rows);
+  else s->extents_known = false;             // positions / tags live in device memory only
   if (!rows) s->rows += n;
   s->live = -1;
   if (tags && tags_may_be_negative) s->maybe_dead = true;
@@ -320,7 +374,7 @@ static int upsert_impl(frg_store* s, const int64_t* rows, const float* vecs, con
 int frg_store_upsert(frg_store* s, const int64_t* rows, const float* vecs, const int32_t* tags,
                      int64_t n, uint32_t flags, void* stream) {
   // device-resident tags cannot be inspected here: assume they may carry -1 (tombstones)
-  return upsert_impl(s, rows, vecs, tags, n, flags, stream, true);
+  return upsert_impl(s, rows, vecs, tags, n, flags, stream, true, !rows && !tags, nullptr, nullptr);
 }
 
 
@@ -404,7 +458,7 @@ int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, 
     if (tags) memcpy(h + vb + rb, tags, tb);
     cudaError_t e = cudaMemcpyAsync(d, h, vb + rb + tb, cudaMemcpyHostToDevice, st);
     g_upload_ring.release(slot, st);
-    int rc = e == cudaSuccess ? upsert_impl(s, dr, dv, dt, n, flags, st, negative)
+    int rc = e == cudaSuccess ? upsert_impl(s, dr, dv, dt, n, flags, st, negative, true, rows, tags)
                               : cuda_fail(e, "upsert_host staging", __FILE__, __LINE__);
     cudaError_t ef = cudaFreeAsync(d, st);
     if (rc == FRG_OK && ef != cudaSuccess) rc = cuda_fail(ef, "cudaFreeAsync", __FILE__, __LINE__);
@@ -416,7 +470,7 @@ int frg_store_upsert_host(frg_store* s, const int64_t* rows, const float* vecs, 
   if (e == cudaSuccess && rows) e = cudaMemcpyAsync(dr, rows, size_t(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && tags) e = cudaMemcpyAsync(dt, tags, size_t(n) * sizeof(int32_t), cudaMemcpyHostToDevice, st);
   int rc = e == cudaSuccess ? FRG_OK : cuda_fail(e, "upsert_host staging", __FILE__, __LINE__);
-  if (rc == FRG_OK) rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative);
+  if (rc == FRG_OK) rc = upsert_impl(s, dr, dv, dt, n, flags, st, negative, true, rows, tags);
   cudaError_t ef = cudaFreeAsync(d, st);
   if (rc == FRG_OK) {
     e = cudaStreamSynchronize(st);
@@ -487,6 +541,10 @@ int frg_store_compact(frg_store* s, int64_t* old_to_new) {
     }
   }
   const int64_t m = int64_t(src.size());
+  // the host copy of the tags gives the extents exactly, at the rows' NEW positions
+  s->extents.clear();
+  for (int64_t i = 0; i < m; ++i) extent_add(s, t[size_t(src[size_t(i)])], i, i + 1);
+  s->extents_known = true;
   if (m == n) { s->live = n; s->maybe_dead = false; return FRG_OK; }
   float* nm; __nv_bfloat16* np; int32_t* nt;
   FRG_CHECK(alloc_arrays(s, s->capacity, &nm, &np, &nt));
@@ -546,6 +604,7 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
   FRG_CHECK(store_begin_write(s, st));
   FRG_CHECK(launch_synth(n, s->rows, global_row0, seed, tag, s->dim, s->master, s->plane, s->plane_dim,
                          s->gmax_bits, s->tags, st));
+  extent_add(s, tag, s->rows, s->rows + n);
   s->rows += n;
   if (s->live >= 0 && tag >= 0) s->live += n;
   if (tag < 0) s->maybe_dead = true;
@@ -581,7 +640,7 @@ struct ExchangeTail {
   uint8_t* fin_accept = nullptr;
 };
 
-static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, int sm_count,
+static int match_scan(const GalleryWindow* s, const float* q, int nq, int k, const frg_match_params_t* p, int sm_count,
                       int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st,
                       const ExchangeTail& tail = ExchangeTail()) {
   if (!s->master && s->rows > 0) {
@@ -610,7 +669,7 @@ static int match_scan(frg_store* s, const float* q, int nq, int k, const frg_mat
   return rc;
 }
 
-static int match_tc(frg_store* s, const float* q, int nq, int k, const frg_match_params_t* p, bool rescore,
+static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const frg_match_params_t* p, bool rescore,
                     int sm_count, int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st,
                     const ExchangeTail& tail = ExchangeTail()) {
   const char* why = "";
@@ -697,13 +756,17 @@ static int match_impl(frg_store* s, const float* q, int32_t nq, int32_t k, const
                                            // store as of this call (peopleCount.py:816-819 semantics)
   FRG_CHECK(store_begin_read(s, st));
   struct SeqBump { ~SeqBump() { ++g_match_seq; } } bump;      // sampled profiling: every 4th match is bracketed
+  // a tenant-filtered call scans only the rows that tenant can sit in (the whole gallery otherwise)
+  const GalleryWindow w = window_of(s, p->tenant);
+  frg_match_params_t pw = *p;
+  pw.row_offset += w.row0;
   switch (pick_variant(s, p, nq)) {
     case FRG_VARIANT_SCAN_F32:
-      return match_scan(s, q, nq, k, p, di.sm_count, out_rows, out_scores, out_accept, st, tail);
+      return match_scan(&w, q, nq, k, &pw, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     case FRG_VARIANT_TC_EXACT:
-      return match_tc(s, q, nq, k, p, true, di.sm_count, out_rows, out_scores, out_accept, st, tail);
+      return match_tc(&w, q, nq, k, &pw, true, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     case FRG_VARIANT_TC_BF16:
-      return match_tc(s, q, nq, k, p, false, di.sm_count, out_rows, out_scores, out_accept, st, tail);
+      return match_tc(&w, q, nq, k, &pw, false, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     default:
       set_error("match: unknown variant %d", p->variant);
       return FRG_ERR_INVALID;
@@ -824,9 +887,10 @@ int frg_first_match(frg_store* s, const float* q, int32_t nq, const frg_match_pa
   float* qn = reinterpret_cast<float*>(ws);
   int rc = launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, nullptr, nullptr,
                                     nullptr, nullptr, st);
+  const GalleryWindow w = window_of(s, p->tenant);
   if (rc == FRG_OK)
-    rc = launch_first_match(s->master, s->tags, s->rows, s->dim, qn, nq, p->tenant, p->threshold,
-                            (p->flags & FRG_FIRST_STRICT) != 0, p->row_offset,
+    rc = launch_first_match(w.master, w.tags, w.rows, s->dim, qn, nq, p->tenant, p->threshold,
+                            (p->flags & FRG_FIRST_STRICT) != 0, p->row_offset + w.row0,
                             reinterpret_cast<unsigned long long*>(ws + qn_bytes), di.sm_count, out_rows, out_scores, st);
   cudaError_t e = cudaFreeAsync(ws, st);
   if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);

@@ -7,6 +7,7 @@
 
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "frg.h"
@@ -126,10 +127,29 @@ struct frg_store {
   cudaEvent_t last_write = nullptr;   // recorded after every mutation
   bool has_write = false;
   std::vector<cudaStream_t> readers;  // streams that matched since the last mutation
-  // tensor-map cache for the TC variants (rebuilt when the plane pointer / row count changes)
-  int64_t tmap_rows = -1;
-  const void* tmap_ptr = nullptr;
+  // Row extent [lo, hi) every tenant tag can sit in (a superset: never shrunk by removals, rebuilt exactly by
+  // compact()).  A tenant-filtered match scans only that window: infrenceServer.py:343-380 filters EVERY frame
+  // by company, and a company's people are typically enrolled as one contiguous block.  Known only while every
+  // mutation carried its tags / rows in host memory (the *_host entry points, fill_synthetic).
+  struct Extent { int64_t lo, hi; };
+  std::unordered_map<int32_t, Extent> extents;
+  bool extents_known = true;
 };
+
+namespace frg {
+// What the match kernels see of a store: the whole gallery, or the row window of one tenant.
+struct GalleryWindow {
+  const float* master = nullptr;
+  const __nv_bfloat16* plane = nullptr;
+  const int32_t* tags = nullptr;
+  uint32_t* gmax_bits = nullptr;
+  int64_t rows = 0;       // rows in the window
+  int64_t row0 = 0;       // store row of the window's first row (added to every returned row)
+  int dim = 0, plane_dim = 0;
+  uint32_t flags = 0;
+  bool maybe_dead = false;
+};
+}  // namespace frg
 
 namespace frg {
 
@@ -215,7 +235,7 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
 // metric cosine: qb = [nq][dim] bf16 unit queries, eps == nullptr (constant bound).
 // metric euclidean: qb = [nq][dim + kEuclidQPad] augmented image, eps[nq] per-query bounds.
 // push: the select stage sends every query's final top-k straight to all ranks (XPush::peer_bufs != null)
-int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
+int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
                     uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st);

@@ -1072,7 +1072,7 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
 
 // qn / qb: normalised fp32 queries and their bf16 image [nq][dim]; ws: tc_workspace_bytes() of scratch.
 // Leaves the overflowed queries in (flagged, n_flagged) for the caller's exact fallback pass.
-int launch_tc_match(const frg_store* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
+int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
                     uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st) {

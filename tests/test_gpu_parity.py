@@ -238,6 +238,59 @@ def test_store_semantics_follow_the_dict(frg, variant):
     store.close()
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_tenant_row_windows(frg, variant):
+    """infrenceServer.py:343-380 filters every frame by company.  A tenant-filtered call scans only the row window
+    that tenant's rows can sit in (the store tracks one extent per tag); results must equal the oracle's masked
+    scan whether a company's rows are one contiguous block, a tiny block inside one tile, interleaved with another
+    company's, stretched by a re-enrolment at the end, or re-packed by compaction."""
+    d, n = 512, 60_000
+    G = synth.gallery(n, d, 5)
+    comp = np.empty(n, object)
+    comp[:7000] = "A"; comp[7000:7100] = "B"; comp[7100:40_000] = "C"
+    comp[40_000:] = np.where(np.arange(n - 40_000) % 2 == 0, "D", "E")
+    ids = hex_ids(n)
+    store = frg.GalleryStore(dim=d, capacity=n + 16)
+    store.upsert(ids, G, list(comp), prenormalised=True)
+    rng = np.random.default_rng(3)
+    src = np.array([10, 6999, 7000, 7050, 7099, 7100, 25_000, 39_999, 40_000, 40_001, 59_999, 59_998])
+    Q = np.concatenate([G[src] + np.float32(0.03) * rng.standard_normal((len(src), d)).astype(np.float32),
+                        rng.standard_normal((4, d)).astype(np.float32)])
+    m = frg.Matcher(store)
+
+    def compare():
+        Gn, tags = store.read_rows()
+        for company in ("A", "B", "C", "D", "E", None, "nobody"):
+            tenant = None if company is None else store.tenant_code(company, create=False)
+            for k in (1, 5):
+                check_against_oracle(frg, store, Q, Gn, k, 0.4, tags=tags, tenant=tenant, company=company,
+                                     variant=variant)
+            if company not in (None, "nobody"):
+                # first row of the tenant at / above 0.5, in gallery order (trainingServer.py:170-200)
+                rows, scores = m.first_above(Q, 0.5, company_id=company)
+                S = mo.cosine_scores(Q, Gn)
+                for f in range(len(Q)):
+                    ok = np.nonzero((tags == tenant) & (S[f] >= np.float32(0.5)))[0]
+                    near = np.nonzero((tags == tenant) & (np.abs(S[f] - 0.5) <= TOL))[0]
+                    if len(near) == 0:
+                        assert rows[f] == (ok[0] if len(ok) else -1)
+
+    compare()
+    r = m.match(Q[:3], 1, 0.4, company_id="nobody")
+    assert (r.rows == -1).all() and not r.accept.any() and r.launches > 0       # a company nobody belongs to
+    # B's people leave and one comes back: the row lands at the END, B's extent now spans most of the gallery
+    store.remove(ids[7000:7060])
+    store.upsert([ids[7010]], G[7010:7011], ["B"], prenormalised=True)
+    assert store.row_of(ids[7010]) == n
+    compare()
+    # in-place update that moves a row to another company
+    store.upsert([ids[20_000]], G[20_000:20_001], ["A"], prenormalised=True)
+    compare()
+    store.compact()                                   # extents are rebuilt from the tags at the new positions
+    compare()
+    store.close()
+
+
 def test_embedding_manager_replays_reference_scenario(frg, golden):
     """tests/golden/managers.npz: ids order and loaded matrices of BOTH reference managers."""
     from datetime import datetime, timedelta, timezone
