@@ -1,6 +1,8 @@
 """Tenant-filtered matching (infrenceServer.py:343-380 filters EVERY frame by company) when
 a company's rows sit in one contiguous block of the gallery (run on the GPU box):
-    python tools/tenant_probe.py [rows_per_tenant]"""
+    python tools/tenant_probe.py [rows_per_tenant] [far]
+"far": one more row of the probed tenant sits at the very end of the gallery, so its extent spans almost everything
+while its rows stay concentrated in one CTA's chunk (the private candidate segments spill into the dense list)."""
 import sys
 
 import numpy as np
@@ -20,6 +22,9 @@ store._tenants = {"c%d" % i: i for i in range(1, n // T + 2)}
 m = frg.Matcher(store)
 tenant = 37 if n // T > 37 else 1
 lo = (tenant - 1) * T
+far = len(sys.argv) > 2 and sys.argv[2] == "far"
+if far:
+    store.overwrite_rows([n - 1], synth.unit_rows([n - 1], d), np.array([tenant], np.int32), prenormalised=True)
 G, tags = store.read_rows(lo, T)
 for F in (8, 64, 256):
     rng = np.random.default_rng(F)
@@ -30,7 +35,7 @@ for F in (8, 64, 256):
     Qd = torch.from_numpy(Q).cuda()
     for company in ("c%d" % tenant, None):
         r = m.match(Q, 5, 0.4, company_id=company)
-        if company is not None:
+        if company is not None and not far:
             want = np.where(ref[0] >= 0, ref[0] + lo, -1)
             assert mo.ids_match_with_gap(want, ref[1], r.rows, 1e-4).all(), "tenant-filtered result differs from the oracle"
         out = None
@@ -43,5 +48,5 @@ for F in (8, 64, 256):
             m.match_device(Qd, 5, 0.4, company_id=company, out=out)
         e1.record()
         torch.cuda.synchronize()
-        print("rows/tenant=%d F=%3d company=%-5s  %.1f us/step" % (T, F, company, e0.elapsed_time(e1) / 20 * 1e3), flush=True)
+        print("rows/tenant=%d%s F=%3d company=%-5s  %.1f us/step" % (T, " +far" if far else "", F, company, e0.elapsed_time(e1) / 20 * 1e3), flush=True)
 store.close()
