@@ -451,7 +451,6 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     float gmax[kGroups];                                 // GROUPMAX / FUSED probe: running maximum per row group
     float thr = INFINITY;
     int emitted = 0;
-    bool spill_dead = false;     // the query's dense list is already full: stop spilling into it
     int2* my_seg = nullptr;
     // L[q] = k-th largest of the 32 group maxima published so far.  The groups are disjoint row sets,
     // so that value is reached by k distinct valid rows: L[q] <= tau, whatever subset has been seen.
@@ -551,17 +550,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (v[j] >= thr) {
-                const int2 entry = make_int2(row0 + j, __float_as_int(v[j]));
-                if (emitted < p.seg) {
-                  my_seg[emitted] = entry;
-                } else if (!spill_dead) {
-                  // private segment full (a tenant's rows, or near-duplicates, concentrated in this CTA's
-                  // chunk): straight into the query's dense list, one atomic per entry - until the list
-                  // itself is full, after which the query is going to the exact fallback anyway
-                  const int pos = atomicAdd(p.cand_total + q, 1);
-                  if (pos < p.dense_cap) p.dense[size_t(q) * p.dense_cap + pos] = entry;
-                  else spill_dead = true;
-                }
+                if (emitted < p.seg) my_seg[emitted] = make_int2(row0 + j, __float_as_int(v[j]));
                 ++emitted;
               }
             }
@@ -624,11 +613,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
           if (gmax[j] > p.none_score) atomicMax(o + j, float_key(gmax[j]));
       } else {
         // pack this thread's few candidates into the query's dense list: one atomicAdd per (query, CTA),
-        // outside the scan loop.  Entries beyond the private segment went to the dense list as they came
-        // (above); the total stays the exact candidate count, and a total beyond dense_cap makes select
-        // hand the query to the exact fallback (at most one count per gallery row: no wrap below 2^31 rows).
+        // outside the scan loop.  A private-segment overflow poisons the total so that select flags it
+        // (2^20 > any dense_cap; a query has at most 2 * 148 segments, so the sum of poisons cannot wrap).
+        const int base = atomicAdd(p.cand_total + q, emitted > p.seg ? (1 << 20) : emitted);
         const int mine_n = emitted < p.seg ? emitted : p.seg;
-        const int base = atomicAdd(p.cand_total + q, mine_n);
         for (int i = 0; i < mine_n; ++i)
           if (unsigned(base + i) < unsigned(p.dense_cap)) p.dense[size_t(q) * p.dense_cap + base + i] = my_seg[i];
       }
@@ -715,7 +703,7 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   pdl_trigger();
 
   const int total = cand_total[q];
-  if (total > dense_cap) {                           // more candidates than the list holds
+  if (total > dense_cap) {                           // also set by a poisoned total (segment overflow)
     // the dense list is incomplete (and partly unwritten): leave the query to the exact fallback
     if (threadIdx.x == 0) flagged[atomicAdd(n_flagged, 1)] = q;
     return;

@@ -164,7 +164,7 @@ def test_overwrite_in_place_and_compaction_keep_the_norm_terms(frg):
 
 def test_one_outlier_row_of_huge_norm_overflows_every_query(frg):
     """The filter's bound uses the LARGEST row norm of the store: one row 30x longer than the rest makes
-    every row a candidate of every query, every private segment overflows (the spilled totals must not
+    every row a candidate of every query, every private segment overflows (the poisoned totals must not
     wrap), and all queries are redone by the exact scan on the device - slow, still right."""
     rng = np.random.default_rng(14)
     n, d = 40_000, 128

@@ -415,7 +415,7 @@ def test_candidate_overflow_falls_back_to_exact_scan(frg):
 
 def test_every_row_is_a_candidate(frg):
     """Degenerate gallery - the same template enrolled 50 000 times: every row ties with every other,
-    every private candidate segment of every CTA overflows at once (the spilled totals must not
+    every private candidate segment of every CTA overflows at once (their poisoned totals must not
     wrap).  The exact fallback answers: ties go to the earliest rows, in order."""
     d, n = 512, 50_000
     g = synth.gallery(1, d, 5)[0]
