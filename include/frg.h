@@ -91,7 +91,10 @@ typedef struct frg_match_params_t {
   float   threshold;   /* cosine: accept iff score >= threshold, compared in fp32 (NumPy>=2 semantics of
                           infrenceServer.py:545 / peopleCount.py:876); euclidean: accept iff dist <= threshold */
   int32_t tenant;      /* < 0: all tenants (peopleCount.py:848); else only rows with this tag
-                          (company subset, infrenceServer.py:343-380) */
+                          (company subset, infrenceServer.py:343-380).  The store remembers the row extent each
+                          tag can sit in (as long as tags / rows reach it through the *_host mutators or
+                          fill_synthetic; frg_store_compact re-tightens it): a tenant-filtered call scans only
+                          that window, so enrol a company's people together */
   int64_t row_offset;  /* added to every returned row (global row of a shard's first row) */
   uint32_t flags;      /* FRG_QUERY_PRENORMALISED (match and first_match), FRG_FIRST_STRICT (first_match) */
   uint32_t reserved;
