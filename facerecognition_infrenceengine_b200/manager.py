@@ -132,6 +132,7 @@ class EmbeddingManager:
         self.sync_interval = sync_interval if sync_interval is not None else (30 if mode == "live" else 60)
         self.running = False
         self.sync_thread: Optional[threading.Thread] = None
+        self._evicted_since_compaction = 0
         self._initial_load()
 
     # ---- loading ----------------------------------------------------------------------------
@@ -165,7 +166,27 @@ class EmbeddingManager:
     def _remove_inactive_employees(self):
         """infrenceServer.py:234-258."""
         with self.embeddings_lock:
-            return self.store.remove(self.source.inactive_employee_ids())
+            gone = self.store.remove(self.source.inactive_employee_ids())
+            self._evicted_since_compaction += gone
+            self._maybe_compact()
+            return gone
+
+    # the reference's `del self.embeddings[id]` frees the entry; here an evicted row stays behind as a tombstone
+    # (and keeps its company's row window wide) until the store is compacted.  Do that once tombstones are
+    # both many and a sizeable share of the gallery - never for the odd eviction.
+    COMPACT_MIN_DEAD = 1024
+    COMPACT_DEAD_SHARE = 0.25
+
+    def _maybe_compact(self):
+        if self._evicted_since_compaction < self.COMPACT_MIN_DEAD or not hasattr(self.store, "compact"):
+            return False
+        st = self.store.stats()
+        dead = int(st.rows) - int(st.live)
+        if dead >= self.COMPACT_MIN_DEAD and dead >= self.COMPACT_DEAD_SHARE * int(st.rows):
+            self.store.compact()
+            self._evicted_since_compaction = 0
+            return True
+        return False
 
     def _sync_embeddings(self):
         if self.mode == "live":

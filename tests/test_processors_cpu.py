@@ -83,3 +83,53 @@ def test_empty_gallery_and_empty_frame():
         [], {"faces": 0, "recognized": 0, "unknown": 0})                         # peopleCount.py:850-851
     ev, st = frg.CameraProcessor(_Store(5), matcher=m).process(np.zeros((0, 8), np.float32))
     assert ev == [] and st == {"faces": 0, "recognized": 0, "unknown": 0} and m.calls == []
+
+
+def test_manager_compacts_after_heavy_eviction_only():
+    """EmbeddingManager squeezes tombstones out once they are many AND a sizeable share of the gallery (the
+    reference's `del self.embeddings[id]`, infrenceServer.py:248-251, frees the entry at once); the odd eviction
+    never triggers it.  Host logic only: the store is a stand-in that counts."""
+    from types import SimpleNamespace
+    from facerecognition_infrenceengine_b200.manager import EmbeddingManager, ListSource
+
+    class Store:
+        def __init__(self):
+            self.rows, self.live, self.compactions, self.ids_ = 0, 0, 0, set()
+
+        def upsert(self, ids, vecs, comps=None, meta=None):
+            new = [i for i in ids if i not in self.ids_]
+            self.ids_.update(new); self.rows += len(new); self.live += len(new)
+
+        def remove(self, ids):
+            gone = [i for i in ids if i in self.ids_]
+            self.ids_.difference_update(gone); self.live -= len(gone)
+            return len(gone)
+
+        def stats(self):
+            return SimpleNamespace(rows=self.rows, live=self.live, capacity=self.rows, bytes=0, version=0)
+
+        def compact(self):
+            self.compactions += 1; self.rows = self.live
+
+    def emp(i, status="active"):
+        return {"_id": "%024x" % i, "embedding": np.ones(8, np.float32), "companyId": "c", "status": status,
+                "blacklisted": False, "lastUpdated": None}
+
+    E = [emp(i) for i in range(6000)]
+    st = Store()
+    m = EmbeddingManager(ListSource(E, []), mode="live", store=st)
+    assert st.rows == 6000 and st.compactions == 0
+    for e in E[:10]:
+        e["status"] = "inactive"                    # a few evictions: tombstones stay
+    m._remove_inactive_employees()
+    assert st.live == 5990 and st.rows == 6000 and st.compactions == 0
+    for e in E[:1200]:
+        e["status"] = "inactive"                    # many, but under a quarter of the gallery
+    m._remove_inactive_employees()
+    assert st.live == 4800 and st.compactions == 0
+    for e in E[:2000]:
+        e["status"] = "inactive"                    # a third of the gallery is dead now
+    m._remove_inactive_employees()
+    assert st.live == 4000 and st.compactions == 1 and st.rows == 4000
+    m._remove_inactive_employees()                  # nothing new: nothing happens
+    assert st.compactions == 1
