@@ -176,8 +176,9 @@ def reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, args.batch), cpu_sample_queries_per_step=q_per_step),
-            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "config": workload_config(args, args.batch, world),
+            "cpu_baseline": {"value": qps, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                             "sample_queries_per_step": q_per_step},
             "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "setup_s": gen_s}
     emit_json(line)
@@ -195,13 +196,15 @@ def workload_config(args, batch, world=1):
                                     args.rows_total, world, args.rows, batch, args.k),
                     "sharding": "gallery rows", "gallery_rows_total": args.rows_total})
     elif world > 1 and args.shard == "gallery":
-        cfg.update({"workload": "configs[1] per GPU, gallery row-sharded over %d GPUs (%d rows each, %d total), "
-                                "queries replicated, per-rank top-k exchanged and merged (config.exchange)" % (
-                                    world, args.rows, args.rows * world),
+        cfg.update({"workload": "gallery_rows_total=%d: configs[1] per GPU (weak scaling) - one gallery of %d x %d rows "
+                                "row-sharded over %d GPUs, every query of the batch matched against ALL of them, "
+                                "per-rank top-k exchanged and merged" % (
+                                    args.rows * world, world, args.rows, world),
                     "sharding": "gallery rows", "gallery_rows_total": args.rows * world,
-                    "value_definition": "1M-row-gallery-equivalent queries/s = batch * (total_rows / gallery_rows) / "
-                                        "step time: a query matched against N x 1M rows counts as N queries at "
-                                        "1M x 512; raw queries/s is in queries_per_s_raw"})
+                    "value_definition": "whole-job aggregate in the metric's own unit: `raw_queries_per_s` (batch / "
+                                        "step time, against gallery_rows_total rows) x gallery_rows_total / 1M, i.e. a "
+                                        "query matched against N x 1M rows counts as N queries at 1M x 512 - per-GPU "
+                                        "work is fixed, so this is what grows with N under weak scaling"})
     elif world > 1:
         cfg.update({"workload": "configs[1] replicated on %d GPUs, query stream sharded across ranks, no collective" % world,
                     "sharding": "queries (replicas)"})
@@ -209,6 +212,13 @@ def workload_config(args, batch, world=1):
             "l2_policy": "inputs larger than L2 (gallery %.2f GB fp32 + %.2f GB bf16 plane vs 126 MB L2)" % (
                 args.rows * args.dim * 4 / 1e9, args.rows * args.dim * 2 / 1e9)})
     return cfg
+
+
+def power_capped(clocks):
+    """The clock record of a timed region shows the power cap (or clocks well below max): the sustained cuBLAS
+    figure is the tensor denominator for that region, the burst figure otherwise (B200_PROFILING.md)."""
+    return bool(clocks and ("sw_power_cap" in (clocks.get("reasons") or []) or (
+        clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] < 0.9 * clocks["sm_max_mhz"])))
 
 
 def roofline_for(variant, n, dim, F, dom_launch_ms, peaks):
@@ -243,7 +253,8 @@ def ours_arm(args, rank, world):
     n, dim, k = args.rows, args.dim, args.k
 
     sharded = world > 1 and args.shard == "gallery"
-    store = frg.GalleryStore(dim=dim, capacity=n, device=local, bf16_only=args.bf16_only)
+    # (slack: the config 5 leg enrols a few thousand rows at the end; growing would re-allocate the gallery)
+    store = frg.GalleryStore(dim=dim, capacity=n + (16384 if world == 1 else 0), device=local, bf16_only=args.bf16_only)
     if sharded:
         from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher
         sg = ShardedGallery(dim=dim, device=local, store=store)
@@ -270,7 +281,8 @@ def ours_arm(args, rank, world):
                  torch.empty((F,), dtype=torch.uint8, device=dev)) for _ in range(nb)]
         return Qh, Qd, outs
 
-    def time_device(F, steps, warmup, Qd, outs, clocks=False):
+    def time_device(F, steps, warmup, Qd, outs, clocks=False, preload_s=None):
+        preload_s = args.clock_preload_s if preload_s is None else preload_s
         def step(i):
             if sharded:
                 smatcher.match(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
@@ -285,16 +297,28 @@ def ours_arm(args, rank, world):
             # nvidia-smi samples every 100 ms: keep the GPU under the SAME load for ~1 s right before the
             # timed region (untimed), so that the clock / throttle record describes the state the timed
             # steps run in even when K steps last only milliseconds
+            # step() is a COLLECTIVE on a row-sharded gallery: every rank must make the same number of calls.
+            # (Round 1 looped on each rank's own wall clock: ranks left after different counts and the rank with
+            # more calls polled for packets nobody would send.)  One block of 16 steps is timed, the slowest
+            # rank's time fixes the block count for everybody.
             sampler = ClockSampler(local)
             sampler.start()
-            t_end = time.perf_counter() + args.clock_preload_s
-            i = 0
-            while time.perf_counter() < t_end:
+            t0 = time.perf_counter()
+            for i in range(16):
                 step(i)
-                i += 1
-                if i % 64 == 0:
+            torch.cuda.synchronize()
+            blk = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(blk, op=torch.distributed.ReduceOp.MAX)
+            nblk = int(min(4096, max(0, np.ceil(preload_s / max(float(blk.item()), 1e-6)) - 1)))
+            for b in range(nblk):
+                for i in range(16):
+                    step(i)
+                if b % 4 == 3:
                     torch.cuda.synchronize()
             torch.cuda.synchronize()
+            if sharded:
+                smatcher.check_exchange()
         # Inside the timed region only the DOMINANT kernel is bracketed by events, on every 4th step (an
         # event pair costs ~6 us of stream time; bracketing every stage ~30 us per step = 12 % at batch 64,
         # tools/event_tax_probe.py), so the per-stage split comes from a separate short pass below.
@@ -333,6 +357,8 @@ def ours_arm(args, rank, world):
         torch.cuda.synchronize()
         per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(nsp))
         spread = {"p10": per[nsp // 10], "p50": per[nsp // 2], "p90": per[(nsp * 9) // 10], "steps": nsp}
+        if sharded:
+            smatcher.check_exchange()                # a void collective call raises here, with the reason
         if world > 1:
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -349,8 +375,7 @@ def ours_arm(args, rank, world):
     main = time_device(F, args.steps, args.warmup, Qd, outs, clocks=True)
     variant = main["variant"]
     clocks = main["clocks"]
-    peaks["use_sustained"] = bool(clocks and ("sw_power_cap" in clocks.get("reasons", []) or (
-        clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] < 0.9 * clocks["sm_max_mhz"])))
+    peaks["use_sustained"] = power_capped(clocks)
     ms_per_step, value = main["ms_per_step"], main["value"]
 
     # ---- the same batches with TWO in flight (two streams, alternating): what a server with two camera
@@ -388,10 +413,13 @@ def ours_arm(args, rank, world):
         off = sg.offset if sharded else 0
         sub_rows, sub_scores, sub_acc = mo.match_topk(Qh[0][:nchk], Gs, k + 1, 0.45)
         if sharded:
+            torch.distributed.barrier()          # the host work above took a different time on every rank
             smatcher.match(Qd[0], k, 0.45, variant=args.variant, out=outs[0])
         else:
             matcher.match_device(Qd[0], k, 0.45, variant=args.variant, out=outs[0])
         torch.cuda.synchronize()
+        if sharded:
+            smatcher.check_exchange()
         got_r, got_s, got_a = (x.cpu().numpy() for x in outs[0])
         ok = True
         for f in range(nchk):
@@ -429,6 +457,8 @@ def ours_arm(args, rank, world):
         else:
             matcher.match(Qp[i % nb].numpy(), k, 0.45, variant=args.variant, with_ids=False, out=res)
 
+    if world > 1:
+        torch.distributed.barrier()
     for i in range(max(3, args.warmup)):
         e2e_step(i)
     if world > 1:
@@ -441,6 +471,8 @@ def ours_arm(args, rank, world):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
+    if sharded:
+        smatcher.check_exchange()
     e2e = {"value": F * scale * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": F * dim * 4,
            "d2h_bytes_per_step": F * k * 12 + F, "ms_per_step": e2e_s / args.steps * 1e3,
            "callers": 1,
@@ -505,14 +537,28 @@ def ours_arm(args, rank, world):
                 r = main
             else:
                 _, Qd_s, outs_s = make_batches(Fs)
-                r = time_device(Fs, args.steps, args.warmup, Qd_s, outs_s)
+                # every point under its own ~0.5 s of identical load with its own clock record: a tensor-bound
+                # batch settles on the power cap, an HBM-bound one does not - each fraction uses the peak of
+                # the regime that point actually ran in
+                r = time_device(Fs, args.steps, args.warmup, Qd_s, outs_s, clocks=True,
+                                preload_s=min(args.clock_preload_s, 0.5))
                 del Qd_s, outs_s
-            rf = roofline_for(r["variant"], n, dim, Fs, r["dom_ms"] / max(r["dom_launches"], 1), peaks)
+            pk = dict(peaks, use_sustained=power_capped(r["clocks"]))
+            rf = roofline_for(r["variant"], n, dim, Fs, r["dom_ms"] / max(r["dom_launches"], 1), pk)
+            ck = r["clocks"] or {}
             sweep.append({"batch": Fs, "value": r["value"], "ms_per_step": r["ms_per_step"], "variant": r["variant"],
                           "bound": rf["bound"], "kernel_frac": rf["frac"], "kernel_ms": rf["launch_ms"],
+                          "peak": rf["peak"], "peak_kind": rf.get("peak_kind", "measured copy bandwidth"),
+                          "sm_mhz": ck.get("sm_mhz"), "clock_reasons": ck.get("reasons"),
                           "stage_ms": {k_: round(v, 4) for k_, v in r["stage_ms"].items()},
                           "step_ms_spread": {k_: round(v, 4) for k_, v in r["step_ms_spread"].items()},
-                          "step_frac_of_roofline": step_roofline_ms(n, dim, Fs, peaks) / r["ms_per_step"]})
+                          "step_frac_of_roofline": step_roofline_ms(n, dim, Fs, pk) / r["ms_per_step"]})
+
+    # ---- BASELINE configs[3] ("config 4" in DESIGN.md's 1-based count): the FIXED 100 M x 512 gallery
+    # row-sharded over the ranks, batch 4096, top-10, peer-memory exchange - every multi-GPU run carries it
+    config4 = None
+    if sharded and not args.rows_total and args.config4_rows > 0:
+        config4 = run_config4(args, rank, world, local, dev, peaks)
 
     if rank != 0:
         return
@@ -566,18 +612,29 @@ def ours_arm(args, rank, world):
                "seconds": per_step, "gpu_agrees": bool(same)}
         del G
 
+    # ---- the other single-GPU configs of BASELINE.json, one parity-checked number each
+    config3 = config5 = None
+    if world == 1 and not args.bf16_only and not args.no_extra_configs and (n, dim) == (1_000_000, 512):
+        config3 = run_config3(args, local, dev, peaks)
+        config5 = run_config5(args, store, matcher, dev, n, dim)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if args.rows_total else "weak",
             "vs_baseline": None, "dtype": "f32" if variant == "scan_f32" else "bf16 filter + f32 rescore",
-            "data": "synthetic", "config": dict(workload_config(args, F, world), **(
-                {"exchange": {"p2p": "frg_match_exchange: the select stage pushes each query's top-k to all ranks over "
-                                     "NVLink peer memory as {payload, epoch} packets, one kernel polls + merges "
-                                     "(no collective call on the data path)",
-                              "nccl": "NCCL all_gather_into_tensor + frg_merge_topk_strided"}.get(
-                                  smatcher.exchange, str(smatcher.exchange)),
-                 "exchange_fallback_reason": smatcher.p2p_error} if sharded else {})), "variant": variant,
-            "queries_per_s_raw": value / scale if sharded else value,
+            "data": "synthetic", "config": workload_config(args, F, world), "variant": variant,
+            "raw_queries_per_s": value / scale if sharded else value,
+            "gallery_rows_total": n_total,
+            "exchange": ({"path": smatcher.exchange,
+                          "what": {"p2p": "frg_match_exchange: the select stage pushes each query's top-k to all ranks "
+                                          "over NVLink peer memory as {payload, epoch} packets, a poll-only kernel merges "
+                                          "(no collective call on the data path; bounded waits, status codes)",
+                                   "nccl": "NCCL all_gather_into_tensor + frg_merge_topk_strided"}.get(
+                                       smatcher.exchange, str(smatcher.exchange)),
+                          "fallback_reason": smatcher.p2p_error} if sharded else None),
+            "config3": config3, "config4": config4, "config5": config5,
+            "notes": ["e2e may exceed the device-timed value on a power-capped box: the per-step host synchronisation "
+                      "of the e2e loop lets the SM clock recover between steps, the back-to-back device loop does not"],
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "pipelined": pipelined,
             "gpu_launches": main["launches_per_step"] * args.steps,
             "clocks": clocks, "parity": parity, "sweep": sweep, "peaks": peaks,
@@ -585,6 +642,211 @@ def ours_arm(args, rank, world):
             "timing": "CUDA events on the launching stream around the K steps; only the dominant kernel is "
                       "bracketed inside the timed region, per-stage and per-step figures come from separate passes"}
     emit_json(line)
+
+
+def timed_sharded_or_plain(step, steps, stream, dev, world):
+    """CUDA events around `steps` calls of step(i); max over ranks."""
+    import torch
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps
+
+
+def run_config4(args, rank, world, local, dev, peaks):
+    """BASELINE configs[3]: 512-d cosine, 100 M templates row-sharded over the ranks, batch 4096, top-10.
+    Strong scaling: the gallery is fixed, raw queries/s is the figure.  Collective (every rank calls it)."""
+    import torch
+    import facerecognition_infrenceengine_b200 as frg
+    from facerecognition_infrenceengine_b200 import _native as N
+    from facerecognition_infrenceengine_b200.sharded import ShardedGallery, ShardedMatcher, shard_bounds
+    from oracle import synth
+    total, F, k, dim = args.config4_rows, args.config4_batch, 10, 512
+    lo, hi = shard_bounds(total, world)[rank]
+    rows = hi - lo
+    # fp32 master + bf16 plane = 3 KB per row (2 GPUs: 154 GB each); fall back to the bf16-only store when
+    # that does not fit beside what is already resident
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    need = rows * (dim * 6 + 4) + (6 << 30)
+    fits = torch.tensor([1 if free_b >= need else 0], device=dev)
+    torch.distributed.all_reduce(fits, op=torch.distributed.ReduceOp.MIN)
+    bf16_only = not bool(fits.item())
+    store = frg.GalleryStore(dim=dim, capacity=rows, device=local, bf16_only=bf16_only)
+    sg = ShardedGallery(dim=dim, device=local, store=store)
+    sg.fill_synthetic(total, args.seed)
+    sm = ShardedMatcher(sg, exchange=args.exchange)
+    nb = 2
+    QT = [synth.queries(F, total, dim, q0=i * F) for i in range(nb)]
+    Qd = [torch.from_numpy(q).to(dev) for q, _ in QT]
+    outs = [(torch.empty((F, k), dtype=torch.int64, device=dev), torch.empty((F, k), dtype=torch.float32, device=dev),
+             torch.empty((F,), dtype=torch.uint8, device=dev)) for _ in range(nb)]
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        sm.match(Qd[i % nb], k, 0.45, variant=args.variant, out=outs[i % nb])
+
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    launches = N.last_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    per = timed_sharded_or_plain(step, 2, stream, dev, world)           # sizes the ~1 s of identical load
+    pre = int(min(64, max(1, np.ceil(args.clock_preload_s / max(per * 1e-3, 1e-6)))))
+    for i in range(pre):
+        step(i)
+    steps = max(20, args.steps)
+    N.check(N.lib.frg_profile_enable(3))
+    N.profile_collect()
+    ms = timed_sharded_or_plain(step, steps, stream, dev, world)
+    dom_ms, dom_launches = N.profile_collect()
+    N.profile_enable(False)
+    clocks = sampler.stop()
+    sm.check_exchange()
+    # ids verified on EVERY rank: the genuine queries' targets (known by construction, spread over all shards)
+    # must come back first, lists ordered, no row twice
+    ok = True
+    for i in range(nb):
+        r_, s_, a_ = (x.cpu().numpy() for x in outs[i])
+        tgt = QT[i][1]
+        hit = tgt >= 0
+        ok &= bool((r_[hit, 0] == tgt[hit]).all()) and bool(a_[hit].all()) and not bool(a_[~hit].any())
+        ok &= bool((np.diff(s_, axis=1) <= 0).all()) and all(len(set(x)) == k for x in r_[:64].tolist())
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    pk = dict(peaks, use_sustained=power_capped(clocks))
+    p_tc = pk["bf16_tflops_sustained"] if pk["use_sustained"] else pk["bf16_tflops"]
+    t_roof = max(rows * dim * 2 / (pk["hbm_gbs"] * 1e9), 2.0 * F * rows * dim / (p_tc * 1e12)) * 1e3
+    kern_ms = dom_ms / max(dom_launches, 1)
+    out = {"workload": "configs[3]: 512-d cosine, %d-template gallery row-sharded over %d B200 (%d rows each), batch %d, "
+                       "top-%d, peer-memory exchange + merge" % (total, world, rows, F, k),
+           "scaling": "strong", "gallery_rows_total": total, "rows_per_gpu": rows, "batch": F, "k": k,
+           "storage": "bf16-only plane (scores within 4e-3)" if bf16_only else "fp32 master + bf16 scan plane",
+           "exchange": sm.exchange, "steps": steps, "warmup": 3 + 2 + pre, "ms_per_step": ms,
+           "value": F / (ms * 1e-3), "unit": UNIT, "launches_per_step": launches,
+           "roofline_ms_per_step": t_roof, "roofline_queries_per_s": F / (t_roof * 1e-3),
+           "step_frac_of_roofline": t_roof / ms,
+           "kernel": {"name": "tc_scan_kernel<FILTER>", "launch_ms": kern_ms,
+                      "achieved_tflops": 2.0 * F * rows * dim / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None,
+                      "peak_tflops": p_tc, "peak_kind": "sustained" if pk["use_sustained"] else "burst"},
+           "ids_ok_all_ranks": bool(t.item() > 0), "clocks": clocks}
+    del sm, sg
+    store.close()
+    return out
+
+
+def run_config3(args, local, dev, peaks):
+    """BASELINE configs[2]: 128-d Euclidean, 10 M gallery, batch 256, top-1 (our definition - the reference has
+    no Euclidean path).  Tensor-core filter + exact rescoring, checked bit for bit against the exact fp32 scan."""
+    import torch
+    import facerecognition_infrenceengine_b200 as frg
+    from facerecognition_infrenceengine_b200 import _native as N
+    from oracle import matcher_oracle as mo
+    from oracle import synth
+    n, d, F, tol = args.config3_rows, 128, 256, 0.6
+    store = frg.GalleryStore(dim=d, capacity=n, device=local, raw=True)
+    store.fill_synthetic(n, 0, 99)
+    m = frg.Matcher(store, metric="euclidean")
+    Qh, tgt = synth.queries(F, n, d, seed=5, gallery_seed=99)
+    Q = torch.from_numpy(Qh).to(dev)
+    stream = torch.cuda.current_stream(dev)
+    res = {}
+
+    def step_v(variant):
+        def step(i):
+            res[variant] = m.match_device(Q, 1, tol, variant=variant, out=res.get(variant))
+        return step
+
+    for i in range(5):
+        step_v("tc_exact")(i)
+    N.check(N.lib.frg_profile_enable(3))
+    N.profile_collect()
+    ms = timed_sharded_or_plain(step_v("tc_exact"), max(20, args.steps), stream, dev, 1)
+    dom_ms, dom_l = N.profile_collect()
+    N.profile_enable(False)
+    step_v("scan_f32")(0)
+    torch.cuda.synchronize()
+    tc = [t.cpu().numpy() for t in res["tc_exact"]]
+    sc = [t.cpu().numpy() for t in res["scan_f32"]]
+    same = bool(np.array_equal(tc[0], sc[0]) and np.array_equal(tc[1].view(np.uint32), sc[1].view(np.uint32))
+                and np.array_equal(tc[2], sc[2]))
+    # fp64 direct-difference oracle over the rows that can matter: every returned row and every target
+    hit = tgt >= 0
+    rows_chk = np.unique(np.concatenate([tc[0][:, 0], tgt[hit]]))
+    Gs = synth.unit_rows(rows_chk, d, 99)
+    ref_r, ref_d, ref_a = mo.euclidean_topk(Qh, Gs, 1, tol)
+    oracle_ok = bool((rows_chk[ref_r[:, 0]] == tc[0][:, 0]).all() and np.abs(ref_d[:, 0] - tc[1][:, 0]).max() <= 1e-4
+                     and (ref_a == tc[2].astype(bool)).all())
+    roof = n * d * 4 / (peaks["hbm_gbs"] * 1e9) * 1e3
+    out = {"workload": "configs[2]: 128-d Euclidean (ours; the reference has no Euclidean metric - parity unpinned), "
+                       "%d-row gallery, batch %d, top-1" % (n, F),
+           "gallery_rows": n, "dim": d, "batch": F, "k": 1, "ms_per_step": ms, "value": F / (ms * 1e-3), "unit": UNIT,
+           "variant": "tc_exact (Euclidean scan plane)", "filter_kernel_ms": dom_ms / max(dom_l, 1),
+           "roofline_ms_fp32_gallery_bytes": roof, "step_frac_of_roofline": roof / ms,
+           "parity": {"bit_identical_to_exact_scan": same, "genuine_found": bool((tc[0][hit, 0] == tgt[hit]).all()),
+                      "fp64_oracle_on_returned_and_target_rows_ok": oracle_ok, "tolerance": 1e-4}}
+    store.close()
+    return out
+
+
+def run_config5(args, store, matcher, dev, n, dim):
+    """BASELINE configs[4]: peopleCount video stream - 32 frames x up to 50 faces = 1600 faces per batch against the
+    1 M gallery, with online enrol / evict between batches (64 upserts + 16 removals, host buffers).  Runs last: it
+    mutates the store."""
+    import torch
+    from oracle import synth
+    F, steps, warm = 1600, max(20, args.steps), 5
+    Qh, tgt = synth.queries(F, n, dim, q0=900_000)
+    Q = torch.from_numpy(Qh).to(dev)
+    new = synth.unit_rows(np.arange(64 * (steps + warm)), dim, 777, synth.STREAM_IMPOSTOR).reshape(steps + warm, 64, dim)
+    res = None
+    stream = torch.cuda.current_stream(dev)
+
+    def match_only(i):
+        nonlocal res
+        res = matcher.match_device(Q, 1, 0.45, variant=args.variant, out=res)
+
+    def step(i):
+        match_only(i)
+        store.upsert(["new%d_%d" % (i, j) for j in range(64)], new[i])           # 64 enrolments per batch
+        if i:
+            store.remove(["new%d_%d" % (i - 1, j) for j in range(0, 64, 4)])      # 16 evictions per batch
+
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(warm, warm + steps):
+        step(i)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    match_ms = timed_sharded_or_plain(match_only, steps, stream, dev, 1)
+    last = warm + steps - 1
+    probe = np.stack([new[last][1], new[last - 1][0], new[last - 1][1]])      # fresh, evicted, kept
+    r = matcher.match(probe, 1, 0.45)
+    rows = res[0].cpu().numpy()
+    hit = tgt >= 0
+    return {"workload": "configs[4]: 32 frames x 50 faces = %d faces per batch against the %d-row gallery, 64 enrolments + "
+                        "16 evictions (host buffers) between batches" % (F, n),
+            "batch": F, "k": 1, "steps": steps, "ms_per_step_with_updates": dt * 1e3, "value": F / dt, "unit": UNIT,
+            "ms_per_step_match_only": match_ms, "queries_per_s_match_only": F / (match_ms * 1e-3),
+            "timing": "wall clock around match + upsert + remove calls (mutators are asynchronous host calls)",
+            "parity": {"fresh_rows_found": bool(r.accept[0] and r.accept[2] and r.ids[0][0] == "new%d_1" % last),
+                       "evicted_row_rejected": bool(not r.accept[1]),
+                       "genuine_found": bool((rows[hit, 0] == tgt[hit]).all())}}
 
 
 _REAL_STDOUT = None
@@ -691,6 +953,11 @@ def main():
                          "all-gather + merge kernel; auto = p2p when the peer mapping can be set up")
     ap.add_argument("--e2e-callers", type=int, default=2,
                     help="host threads of the extra concurrent end-to-end measurement (1 = skip it)")
+    ap.add_argument("--config4-rows", type=int, default=100_000_000,
+                    help="N>1: total rows of the fixed-gallery leg (BASELINE configs[3]); 0 = skip it")
+    ap.add_argument("--config4-batch", type=int, default=4096)
+    ap.add_argument("--config3-rows", type=int, default=10_000_000)
+    ap.add_argument("--no-extra-configs", action="store_true", help="N=1: skip the config 3 / config 5 legs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)

@@ -8,15 +8,15 @@ Importing the package requires the built library (no CPU fallback):
 """
 from . import _native
 from ._native import NativeError
-from .gallery import GalleryStore
+from .gallery import GalleryStore, StaleRows
 from .matcher import (CAMPUS_THRESHOLD, CAMPUS_UNKNOWN, LIVE_THRESHOLD, CameraProcessor,
                       FaceRecognitionProcessor, Matcher, MatchResult)
 from .manager import BroadcastSource, EmbeddingManager, GalleryView, ListSource
-from .enrol import EnrolmentChecker
+from .enrol import EnrolmentChecker, EnrolmentGallery
 from .clustering import UnknownClusterer
 from .aggregator import BatchAggregator
 
 __all__ = ["GalleryStore", "Matcher", "MatchResult", "FaceRecognitionProcessor", "CameraProcessor",
-           "EmbeddingManager", "GalleryView", "ListSource", "BroadcastSource", "EnrolmentChecker", "UnknownClusterer",
+           "EmbeddingManager", "GalleryView", "ListSource", "BroadcastSource", "EnrolmentChecker", "EnrolmentGallery", "StaleRows", "UnknownClusterer",
            "BatchAggregator", "NativeError", "LIVE_THRESHOLD",
            "CAMPUS_THRESHOLD", "CAMPUS_UNKNOWN"]

@@ -18,6 +18,7 @@ VARIANT_AUTO, VARIANT_SCAN_F32, VARIANT_TC_EXACT, VARIANT_TC_BF16 = 0, 1, 2, 3
 STORE_BF16_PLANE, STORE_RAW, STORE_BF16_ONLY = 1, 2, 4
 ROWS_PRENORMALISED = 1
 FIRST_STRICT, QUERY_PRENORMALISED = 1, 2
+XCHG_PUSH_ONLY, XCHG_MERGE_ONLY = 1, 2
 MAX_K = 16
 
 VARIANTS = {"auto": VARIANT_AUTO, "scan_f32": VARIANT_SCAN_F32, "tc_exact": VARIANT_TC_EXACT,
@@ -45,7 +46,13 @@ class MatchParams(C.Structure):
 
 class Exchange(C.Structure):          # frg_exchange_t
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("peer_bufs", C.c_void_p),
-                ("block_cap", C.c_int64), ("epoch", C.c_uint32), ("reserved", C.c_uint32)]
+                ("block_cap", C.c_int64), ("epoch", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class ExchangeStatus(C.Structure):    # frg_exchange_status_t
+    _fields_ = [("code", C.c_int32), ("peer", C.c_int32), ("epoch", C.c_uint32), ("peer_epoch", C.c_uint32),
+                ("nq", C.c_int32), ("k", C.c_int32), ("peer_nq", C.c_int32), ("peer_k", C.c_int32),
+                ("slot", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/frg.h declares: (restype, argtypes)
@@ -78,6 +85,7 @@ SIGNATURES = {
                                      _P, _P, _P, _P, _P, _P]),
     "frg_exchange_merge_topk": (C.c_int, [C.c_int32, C.POINTER(Exchange), _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_float, _P, _P, _P, _P]),
+    "frg_exchange_status": (C.c_int, [C.c_int32, _P, C.c_int32, _P, C.POINTER(ExchangeStatus)]),
     "frg_last_launch_count": (C.c_int, []),
     "frg_last_variant": (C.c_char_p, []),
     "frg_profile_enable": (C.c_int, [C.c_int32]),

@@ -297,8 +297,8 @@ int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t fla
                      ? dim + kEuclidPad : dim;
   int rc = alloc_arrays(s, capacity, &s->master, &s->plane, &s->tags);
   if (rc == FRG_OK) {
-    cudaError_t eg = cudaMalloc(reinterpret_cast<void**>(&s->gmax_bits), sizeof(uint32_t));
-    if (eg == cudaSuccess) eg = cudaMemset(s->gmax_bits, 0, sizeof(uint32_t));
+    cudaError_t eg = cudaMalloc(reinterpret_cast<void**>(&s->gmax_bits), 2 * sizeof(uint32_t));
+    if (eg == cudaSuccess) eg = cudaMemset(s->gmax_bits, 0, 2 * sizeof(uint32_t));
     if (eg != cudaSuccess) {
       cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
       rc = cuda_fail(eg, "cudaMalloc(gmax)", __FILE__, __LINE__);
@@ -541,32 +541,57 @@ int frg_store_compact(frg_store* s, int64_t* old_to_new) {
     }
   }
   const int64_t m = int64_t(src.size());
-  // the host copy of the tags gives the extents exactly, at the rows' NEW positions
-  s->extents.clear();
-  for (int64_t i = 0; i < m; ++i) extent_add(s, t[size_t(src[size_t(i)])], i, i + 1);
-  s->extents_known = true;
-  if (m == n) { s->live = n; s->maybe_dead = false; return FRG_OK; }
-  float* nm; __nv_bfloat16* np; int32_t* nt;
-  FRG_CHECK(alloc_arrays(s, s->capacity, &nm, &np, &nt));
-  int64_t* dsrc = nullptr;
-  int rc = FRG_OK;
-  if (m > 0) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dsrc), size_t(m) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMemcpy(dsrc, src.data(), size_t(m) * sizeof(int64_t), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) rc = cuda_fail(e, "compact staging", __FILE__, __LINE__);
-    if (rc == FRG_OK) rc = launch_gather_rows(dsrc, m, s->dim, s->plane_dim, s->master, s->plane, s->tags, nm, np, nt, nullptr);
+  // the host copy of the tags gives the extents exactly, at the rows' NEW positions - built aside and swapped
+  // in only once the rows have really moved: a failed compaction must leave windows that match the data
+  std::unordered_map<int32_t, frg_store::Extent> fresh;
+  for (int64_t i = 0; i < m; ++i) {
+    const int32_t tag = t[size_t(src[size_t(i)])];
+    auto it = fresh.find(tag);
+    if (it == fresh.end()) fresh.emplace(tag, frg_store::Extent{i, i + 1});
+    else it->second.hi = i + 1;
+  }
+  // Stable compaction IN PLACE, chunk by chunk through a bounce buffer: a row only ever moves to a lower
+  // position (src[i] >= i), so once the sources of destination chunk [a, b) sit in the bounce buffer, writing
+  // [a, b) cannot touch a source of any later chunk (those are >= b).  No second full-capacity copy: a 100 M-row
+  // store compacts with ~200 MB of scratch.  Rows [0, first) stay where they are.
+  int64_t first = 0;
+  while (first < m && src[size_t(first)] == first) ++first;
+  if (first < m) {
+    static const int64_t chunk_rows = []() { const char* e = getenv("FRG_COMPACT_CHUNK_ROWS"); const long v = e ? atol(e) : 65536; return int64_t(v < 1 ? 65536 : v); }();
+    const int64_t chunk = m - first < chunk_rows ? m - first : chunk_rows;
+    float* bm; __nv_bfloat16* bp; int32_t* bt;
+    int64_t* dsrc = nullptr;
+    FRG_CHECK(alloc_arrays(s, chunk, &bm, &bp, &bt));            // nothing has changed yet if this fails
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dsrc), size_t(chunk) * sizeof(int64_t));
+    if (e != cudaSuccess) { cudaFree(bm); cudaFree(bp); cudaFree(bt); return cuda_fail(e, "compact staging", __FILE__, __LINE__); }
+    int rc = FRG_OK;
+    for (int64_t a = first; a < m && rc == FRG_OK; a += chunk) {
+      const int64_t cnt = m - a < chunk ? m - a : chunk;
+      e = cudaMemcpy(dsrc, src.data() + a, size_t(cnt) * sizeof(int64_t), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "compact staging", __FILE__, __LINE__); break; }
+      rc = launch_gather_rows(dsrc, cnt, s->dim, s->plane_dim, s->master, s->plane, s->tags, bm, bp, bt, nullptr);
+      if (rc != FRG_OK) break;
+      if (bm) e = cudaMemcpyAsync(s->master + a * s->dim, bm, size_t(cnt) * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, nullptr);
+      if (e == cudaSuccess && bp) e = cudaMemcpyAsync(s->plane + a * s->plane_dim, bp, size_t(cnt) * s->plane_dim * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, nullptr);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(s->tags + a, bt, size_t(cnt) * sizeof(int32_t), cudaMemcpyDeviceToDevice, nullptr);
+      if (e != cudaSuccess) rc = cuda_fail(e, "compact move", __FILE__, __LINE__);
+    }
     if (rc == FRG_OK) {
       e = cudaDeviceSynchronize();
       if (e != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize", __FILE__, __LINE__);
     }
-    cudaFree(dsrc);
+    cudaFree(dsrc); cudaFree(bm); cudaFree(bp); cudaFree(bt);
+    if (rc != FRG_OK) {
+      // a device failure in the middle (a sticky CUDA error: the context is gone anyway) - never trust windows
+      // computed for a layout that was not reached
+      s->extents_known = false;
+      return rc;
+    }
   }
-  if (rc != FRG_OK) { cudaFree(nm); cudaFree(np); cudaFree(nt); return rc; }
-  cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
-  s->master = nm; s->plane = np; s->tags = nt;
-  s->rows = m; s->live = m; s->version++;
-  s->maybe_dead = false;
-  s->readers.clear(); s->has_write = false;
+  s->extents.swap(fresh);
+  s->extents_known = true;
+  s->live = m; s->maybe_dead = false;
+  if (m != n) { s->rows = m; s->version++; }
   return FRG_OK;
 }
 
@@ -634,6 +659,7 @@ static int pick_variant(const frg_store* s, const frg_match_params_t* p, int nq)
 // caller's LOCAL scratch, the merged result of all ranks goes to fin_*.
 struct ExchangeTail {
   bool active = false;
+  bool merge = true;       // false: FRG_XCHG_PUSH_ONLY - push this shard's result, the caller merges later
   XPush x;
   int64_t* fin_rows = nullptr;
   float* fin_scores = nullptr;
@@ -660,9 +686,11 @@ static int match_scan(const GalleryWindow* s, const float* q, int nq, int k, con
   int rc = launch_normalise_queries(q, nq, s->dim, p->metric == FRG_METRIC_COSINE && !(p->flags & FRG_QUERY_PRENORMALISED), qn, nullptr, nullptr, nullptr, nullptr, st);
   if (rc == FRG_OK)
     rc = launch_scan_f32(a, ws + qn_bytes, p->row_offset, p->threshold, out_rows, out_scores, out_accept, st);
-  if (rc == FRG_OK && tail.active)       // no select stage here: the exchange kernel pushes every query itself
-    rc = launch_exchange_merge(tail.x, out_rows, out_scores, nullptr, nullptr, true, nq, k, p->metric, p->threshold,
-                               sm_count, tail.fin_rows, tail.fin_scores, tail.fin_accept, st);
+  if (rc == FRG_OK && tail.active)       // no select stage here: a push kernel sends every query (and the hello)
+    rc = launch_exchange_push(tail.x, out_rows, out_scores, nq, k, sm_count, st);
+  if (rc == FRG_OK && tail.active && tail.merge)
+    rc = launch_exchange_merge(tail.x, nq, k, p->metric, p->threshold, sm_count, tail.fin_rows, tail.fin_scores,
+                               tail.fin_accept, st);
   g_variant = "scan_f32";
   cudaError_t e = cudaFreeAsync(ws, st);
   if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
@@ -697,13 +725,13 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
   }
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
   const size_t qb_bytes = (size_t(nq) * (s->dim + (euclid ? kEuclidQPad : 0)) * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
-  const size_t eps_bytes = euclid ? ((size_t(nq) * sizeof(float) + 255) & ~size_t(255)) : 0;
+  const size_t eps_bytes = (size_t(nq) * sizeof(float) + 255) & ~size_t(255);     // per-query filter error bound
   const size_t tc_bytes = tc_workspace_bytes(s->rows, s->dim, nq, k, sm_count);
   unsigned char* ws = nullptr;
   FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + eps_bytes + tc_bytes, st));
   float* qn = reinterpret_cast<float*>(ws);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes);
-  float* eps = euclid ? reinterpret_cast<float*>(ws + qn_bytes + qb_bytes) : nullptr;
+  float* eps = reinterpret_cast<float*>(ws + qn_bytes + qb_bytes);
   unsigned char* tc_ws = ws + qn_bytes + qb_bytes + eps_bytes;
   int* flagged = nullptr; int* n_flagged = nullptr;
   uint32_t* keys = nullptr; int* ct0 = nullptr; int* nf0 = nullptr;
@@ -711,7 +739,7 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
   profile_begin(st, kStagePrep);
   int rc = euclid ? launch_prepare_queries_euclid(q, nq, s->dim, s->gmax_bits, qn, qb, eps, keys, ct0, nf0, st)
                   : launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, qb, keys, ct0,
-                                             nf0, st);
+                                             nf0, st, eps, s->gmax_bits);
   profile_end(st, 1);
   if (rc == FRG_OK)
     rc = launch_tc_match(s, p->metric, qn, qb, eps, nq, k, p->tenant, rescore, p->threshold, p->row_offset, tc_ws,
@@ -723,15 +751,15 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
     a.master = s->master; a.plane = s->plane; a.tags = s->tags; a.rows = s->rows; a.dim = s->dim;
     a.qn = qn; a.nq = nq; a.k = k; a.metric = p->metric; a.tenant = p->tenant; a.sm_count = sm_count;
     profile_begin(st, kStageFallback);
-    rc = launch_scan_f32_flagged(a, flagged, n_flagged, p->row_offset, p->threshold, out_rows, out_scores,
-                                 out_accept, st);
+    rc = launch_scan_f32_flagged(a, flagged, n_flagged, p->row_offset, p->threshold,
+                                 tail.active ? tail.x : XPush(), out_rows, out_scores, out_accept, st);
     profile_end(st, 1);
   }
-  if (rc == FRG_OK && tail.active)
-    // select has pushed every query it settled; the flagged ones (just redone above) are pushed here,
-    // then every query's `world` lists are merged as their packets arrive
-    rc = launch_exchange_merge(tail.x, out_rows, out_scores, flagged, n_flagged, false, nq, k, p->metric,
-                               p->threshold, sm_count, tail.fin_rows, tail.fin_scores, tail.fin_accept, st);
+  if (rc == FRG_OK && tail.active && tail.merge)
+    // select has pushed every query it settled, the fallback's last CTA the ones it redid: what is left is
+    // to wait for every rank's packets and merge each query's `world` lists as they arrive
+    rc = launch_exchange_merge(tail.x, nq, k, p->metric, p->threshold, sm_count, tail.fin_rows, tail.fin_scores,
+                               tail.fin_accept, st);
   g_variant = rescore ? "tc_exact" : "tc_bf16";
   cudaError_t e = cudaFreeAsync(ws, st);
   if (rc == FRG_OK && e != cudaSuccess) rc = cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
@@ -779,15 +807,23 @@ int frg_match(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_mat
 }
 
 static int check_exchange(const frg_exchange_t* x, int32_t nq, int32_t k, XPush* out) {
-  if (!x || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || !x->peer_bufs) {
-    set_error("exchange: bad descriptor");
+  if (!x || x->world < 1 || x->world > kExchangeMaxWorld || x->rank < 0 || x->rank >= x->world || !x->peer_bufs) {
+    set_error("exchange: bad descriptor (world 1..%d)", kExchangeMaxWorld);
     return FRG_ERR_INVALID;
   }
+  if ((x->flags & 0xffu) & ~uint32_t(FRG_XCHG_PUSH_ONLY | FRG_XCHG_MERGE_ONLY) ||
+      (x->flags & FRG_XCHG_PUSH_ONLY && x->flags & FRG_XCHG_MERGE_ONLY)) {
+    set_error("exchange: bad flags 0x%x", x->flags);
+    return FRG_ERR_INVALID;
+  }
+  if (nq >= (1 << 27)) { set_error("exchange: nq too large for the hello word"); return FRG_ERR_INVALID; }
   if (x->epoch == 0) { set_error("exchange: epochs start at 1 (the buffers are zero-initialised)"); return FRG_ERR_INVALID; }
   if (x->block_cap < int64_t(nq) * k * 24 || x->block_cap % 8) { set_error("exchange: block_cap too small / unaligned"); return FRG_ERR_INVALID; }
   out->peer_bufs = reinterpret_cast<unsigned char* const*>(x->peer_bufs);
   out->rank = x->rank; out->world = x->world; out->epoch = x->epoch;
-  out->block_cap = x->block_cap; out->nslots = int64_t(nq) * k;
+  out->block_cap = x->block_cap;
+  exchange_fill_defaults(out, nq, k);
+  if (x->flags >> 8) out->timeout_ns = (unsigned long long)(x->flags >> 8) * 1000000ull;    // FRG_XCHG_TIMEOUT_MS
   return FRG_OK;
 }
 
@@ -799,8 +835,21 @@ int frg_match_exchange(frg_store* s, const float* q, int32_t nq, int32_t k, cons
   ExchangeTail tail;
   FRG_CHECK(check_exchange(x, nq, k, &tail.x));
   tail.active = true;
+  tail.merge = !(x->flags & FRG_XCHG_PUSH_ONLY);
   tail.fin_rows = out_rows; tail.fin_scores = out_scores; tail.fin_accept = out_accept;
-  if (nq > 0 && (!out_rows || !out_scores)) { set_error("match_exchange: bad argument"); return FRG_ERR_INVALID; }
+  if (nq > 0 && tail.merge && (!out_rows || !out_scores)) { set_error("match_exchange: bad argument"); return FRG_ERR_INVALID; }
+  if (x->flags & FRG_XCHG_MERGE_ONLY) {
+    // this shard's result of the call went out earlier (FRG_XCHG_PUSH_ONLY): only wait and merge
+    reset_launches();
+    if (!s || !p) { set_error("match_exchange: bad argument"); return FRG_ERR_INVALID; }
+    if (nq == 0) return FRG_OK;
+    DeviceGuard g(s->device);
+    if (!g.ok) { set_error("cannot select device %d", s->device); return FRG_ERR_CUDA; }
+    DeviceInfo di;
+    FRG_CHECK(device_info(s->device, &di));
+    return launch_exchange_merge(tail.x, nq, k, p->metric, p->threshold, di.sm_count, out_rows, out_scores,
+                                 out_accept, static_cast<cudaStream_t>(stream));
+  }
   // the local stage writes this shard's own top-k (global rows) into the scratch; no local decision is kept
   return match_impl(s, q, nq, k, p, local_rows, local_scores, nullptr, stream, tail);
 }
@@ -953,7 +1002,7 @@ int frg_merge_topk_strided(int32_t device, const float* scores, int64_t score_pa
 }
 
 int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap, int64_t* total) {
-  if (world < 1 || world > 64 || nq < 0 || k < 1 || k > FRG_MAX_K || !block_cap || !total) {
+  if (world < 1 || world > kExchangeMaxWorld || nq < 0 || k < 1 || k > FRG_MAX_K || !block_cap || !total) {
     set_error("exchange_bytes: bad argument");
     return FRG_ERR_INVALID;
   }
@@ -977,8 +1026,47 @@ int frg_exchange_merge_topk(int32_t device, const frg_exchange_t* x, const int64
   if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
   DeviceInfo di;
   FRG_CHECK(device_info(device, &di));
-  return launch_exchange_merge(xp, local_rows, local_scores, nullptr, nullptr, true, nq, k, metric, threshold,
-                               di.sm_count, out_rows, out_scores, out_accept, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(x->flags & FRG_XCHG_MERGE_ONLY)) FRG_CHECK(launch_exchange_push(xp, local_rows, local_scores, nq, k, di.sm_count, st));
+  if (x->flags & FRG_XCHG_PUSH_ONLY) return FRG_OK;
+  return launch_exchange_merge(xp, nq, k, metric, threshold, di.sm_count, out_rows, out_scores, out_accept, st);
+}
+
+int frg_exchange_status(int32_t device, const void* own_buf, int32_t clear, void* stream, frg_exchange_status_t* out) {
+  if (!own_buf || !out) { set_error("exchange_status: NULL argument"); return FRG_ERR_INVALID; }
+  DeviceGuard g(device);
+  if (!g.ok) { set_error("cannot select device %d", device); return FRG_ERR_CUDA; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XStatus h{};
+  const unsigned char* rec = static_cast<const unsigned char*>(own_buf) + kExchangeStatusOff;
+  FRG_CUDA(cudaMemcpyAsync(&h, rec, sizeof(h), cudaMemcpyDeviceToHost, st));
+  if (clear) FRG_CUDA(cudaMemsetAsync(const_cast<unsigned char*>(rec), 0, sizeof(h), st));
+  FRG_CUDA(cudaStreamSynchronize(st));
+  memset(out, 0, sizeof(*out));
+  out->code = int32_t(h.code); out->peer = int32_t(h.peer); out->epoch = h.epoch; out->peer_epoch = h.seen_epoch;
+  out->nq = int32_t(h.want_hello >> 5); out->k = int32_t(h.want_hello & 31u);
+  out->peer_nq = int32_t(h.seen_hello >> 5); out->peer_k = int32_t(h.seen_hello & 31u);
+  out->slot = int32_t(h.query);
+  switch (h.code) {
+    case kXOk: return FRG_OK;
+    case kXHelloTimeout:
+      set_error("exchange: call %u (nq=%d, k=%d): rank %d never announced it (its last call on this parity: %u) - "
+                "the ranks made different numbers of collective calls, or that rank is down",
+                h.epoch, out->nq, out->k, out->peer, h.seen_epoch);
+      break;
+    case kXHelloMismatch:
+      set_error("exchange: call %u: this rank passed nq=%d, k=%d but rank %d passed nq=%d, k=%d",
+                h.epoch, out->nq, out->k, out->peer, out->peer_nq, out->peer_k);
+      break;
+    case kXDataTimeout:
+      set_error("exchange: call %u (nq=%d, k=%d): slot %d of rank %d never arrived (packet epoch %u)",
+                h.epoch, out->nq, out->k, out->slot, out->peer, h.seen_epoch);
+      break;
+    default:
+      set_error("exchange: status record holds unknown code %u", h.code);
+      break;
+  }
+  return FRG_ERR_STATE;
 }
 
 }  // extern "C"

@@ -121,7 +121,8 @@ struct frg_store {
   // plane_dim = dim + kEuclidPad (16), columns dim..dim+2 hold -0.5*||g||^2 split exactly into three bf16
   // terms (the rest 0), so that Qaug . Gaug = q.g - 0.5*||g||^2 with Qaug = [q, 1, 1, 1, 0...] (tc_match.cu)
   int plane_dim = 0;
-  uint32_t* gmax_bits = nullptr;      // device scalar: float bits of max ||g||^2 ever ingested (raw stores)
+  uint32_t* gmax_bits = nullptr;      // device uint32[2], float bits: [0] max ||g||^2 ever ingested (raw stores with a
+                                      // Euclidean plane), [1] max ||g - bf16(g)||^2 (any store with a plane)
   int32_t* tags = nullptr;            // [capacity]
   std::mutex mu;                      // guards the fields above and the stream bookkeeping
   cudaEvent_t last_write = nullptr;   // recorded after every mutation
@@ -161,15 +162,19 @@ int store_begin_read(frg_store* s, cudaStream_t stream);
 
 // ---- kernels' host launchers (defined in the .cu named in the comment) ----------------------
 // queries.cu: qn[f] = q[f] / ||q[f]|| (fp32), optional bf16 image
+// eps / bounds (tensor-core variants): eps[f] = rigorous bound of |bf16 filter score - fp32 score| for query f
+// against ANY row of the store, from the measured rounding residual of the query and bounds[1], the largest
+// residual of a stored row (store_kernels.cu)
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
                              __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* cand_total, int* n_flagged,
-                             cudaStream_t st);
+                             cudaStream_t st, float* eps = nullptr, const uint32_t* bounds = nullptr);
 // queries.cu: Euclidean tensor-core prep: qn = q as given, bf16 image [nq][dim + kEuclidQPad] = [q, 1, 1, 1, 0...],
 // eps[f] = filter error bound of query f from ||q|| and the store's max row norm
 int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_t* gmax_bits, float* qn,
                                   __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
                                   int* n_flagged, cudaStream_t st);
 
+struct XPush;      // exchange.cu, below
 // scan_f32.cu: exact scan; writes nq x k best (score desc, row asc) into rows32/scores
 struct ScanArgs {
   const float* master; const __nv_bfloat16* plane = nullptr;   // master == nullptr: bf16-only store, scan the plane
@@ -182,9 +187,10 @@ int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, floa
                     int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
 // scan_f32.cu: exact re-do of the queries listed on the device (tensor-core candidate overflow)
+// push: row-sharded gallery - the last CTA sends every redone query's final top-k to all ranks
 int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, int* n_flagged_and_ticket, int64_t row_offset,
-                            float threshold, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
-                            cudaStream_t st);
+                            float threshold, const XPush& push, int64_t* out_rows, float* out_scores,
+                            uint8_t* out_accept, cudaStream_t st);
 
 // merge.cu: generic k-way merge of sorted partial lists
 int launch_merge_i64(const float* scores, const int64_t* rows, int parts, int nq, int k_in, int k_out,
@@ -199,13 +205,24 @@ int launch_merge_i32(const float* scores, const int32_t* rows, int parts, int nq
 
 // exchange.cu: multi-GPU tail over NVLink peer memory.  XPush describes where this rank's results go:
 // into slot `rank` of every rank's exchange buffer, as 8-byte {payload, epoch} packets.
-constexpr int kExchangeHeader = 512;
+// Buffer layout: [header kExchangeHeader][parity 0: world blocks][parity 1: world blocks]; the header holds
+//   [0, 512)    hello packets [parity][source rank]: {(nq << 5) | k, epoch} - what the source believes this
+//               call is; a rank that polls first checks them, so a call-count or shape mismatch between ranks
+//               is REPORTED (status record) instead of waited on
+//   [512, 576)  status record of this rank's own poll kernel (XStatus), read by frg_exchange_status
+constexpr int kExchangeHeader = 1024;
+constexpr int kExchangeMaxWorld = 32;
+constexpr int kExchangeStatusOff = 512;
+enum XCode : uint32_t { kXOk = 0, kXHelloTimeout = 1, kXHelloMismatch = 2, kXDataTimeout = 3 };
+struct XStatus { uint32_t code, peer, epoch, seen_epoch, want_hello, seen_hello, query, pad; };
 struct XPush {
   unsigned char* const* peer_bufs = nullptr;   // DEVICE array of `world` peer-mapped buffer pointers; null = no exchange
   int rank = 0, world = 1;
   uint32_t epoch = 0;                          // 1, 2, 3, ... one more per collective call; never 0
+  uint32_t hello = 0;                          // (nq << 5) | k
   int64_t block_cap = 0;                       // bytes per (parity, source rank) block >= nslots * 24
   int64_t nslots = 0;                          // nq * k
+  unsigned long long timeout_ns = 0;           // bound of the poll kernel's wait for a peer
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ void xpush_slot(const XPush& x, int peer, int64_t slot, int64_t row, float score) {
@@ -216,12 +233,23 @@ __device__ __forceinline__ void xpush_slot(const XPush& x, int peer, int64_t slo
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(b + x.nslots + slot), "r"(uint32_t(r >> 32)), "r"(x.epoch) : "memory");
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(b + 2 * x.nslots + slot), "r"(__float_as_uint(score)), "r"(x.epoch) : "memory");
 }
+// "rank x.rank is in call x.epoch with this (nq, k)" -> header of `peer`
+__device__ __forceinline__ void xpush_hello(const XPush& x, int peer) {
+  uint2* h = reinterpret_cast<uint2*>(x.peer_bufs[peer]) + (x.epoch & 1u) * kExchangeMaxWorld + x.rank;
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(h), "r"(x.hello), "r"(x.epoch) : "memory");
+}
 #endif
-// push_list / n_push: device-resident list of the queries still to be pushed (null = none); push_all: all
-int launch_exchange_merge(const XPush& x, const int64_t* local_rows, const float* local_scores,
-                          const int* push_list, const int* n_push, bool push_all, int nq, int k, int metric,
-                          float threshold, int sm_count, int64_t* out_rows, float* out_scores,
-                          uint8_t* out_accept, cudaStream_t st);
+// hello word, slot count and the poll bound (FRG_EXCHANGE_TIMEOUT_MS, default 2000) of a call
+void exchange_fill_defaults(XPush* x, int nq, int k);
+// push kernel: hello + the listed queries' (or all queries') local top-k to every rank.  Only needed where no
+// earlier kernel of the match pushed (variants without a select stage; results computed elsewhere).
+int launch_exchange_push(const XPush& x, const int64_t* local_rows, const float* local_scores, int nq, int k,
+                         int sm_count, cudaStream_t st);
+// poll kernel: waits (bounded) for every rank's packets of this call and merges them.  It never pushes: every
+// local push was issued by an EARLIER kernel of the stream, so no CTA of it waits for a push that sits in a
+// CTA which is not resident yet.
+int launch_exchange_merge(const XPush& x, int nq, int k, int metric, float threshold, int sm_count,
+                          int64_t* out_rows, float* out_scores, uint8_t* out_accept, cudaStream_t st);
 
 // tc_match.cu: tcgen05 filter + exact rescoring.  Cosine: dim multiple of 64 and <= 512 (unit rows);
 // Euclidean: dim 128 / 256 over a raw store's augmented plane (plane_dim = dim + kEuclidPad).

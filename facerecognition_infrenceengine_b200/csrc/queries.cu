@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(128)
 normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int normalise,
                          float* __restrict__ qn, __nv_bfloat16* __restrict__ qb,
                          uint32_t* __restrict__ group_keys, int* __restrict__ cand_total,
-                         int* __restrict__ n_flagged) {
+                         int* __restrict__ n_flagged, float* __restrict__ eps, const uint32_t* __restrict__ bounds) {
   pdl_trigger();          // the next kernel of the match may be scheduled now (it waits before reading)
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -35,6 +35,7 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     norm = __fsqrt_rn(ss);
   }
+  float rq = 0.f;          // ||q - bf16(q)||^2 (each difference is exact in fp32)
   for (int v = lane; v < nvec; v += 32) {
     float4 x = __ldg(src + v);
     if (normalise) {
@@ -49,6 +50,20 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
       p.x = *reinterpret_cast<uint32_t*>(&lo);
       p.y = *reinterpret_cast<uint32_t*>(&hi);
       reinterpret_cast<uint2*>(qb + size_t(w) * dim)[v] = p;
+      const float2 l = __bfloat1622float2(lo), h = __bfloat1622float2(hi);
+      const float a = x.x - l.x, b = x.y - l.y, c = x.z - h.x, d = x.w - h.y;
+      rq = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, rq))));
+    }
+  }
+  if (eps) {
+    // |q^.g^ - q.g| <= ||q^|| ||g^ - g|| + ||q^ - q|| ||g||  with unit q, g (to fp32 rounding) and ||q^|| <= 1 + 2^-8;
+    // + 1 % for the fp32 evaluation of the residual norms, + 1e-4 for the tensor core's fp32 accumulation of 512
+    // exact products.  ~3.6e-3 for ordinary data, at most 2^-7 + 2^-16 (every element rounded the same way).
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rq += __shfl_xor_sync(0xffffffffu, rq, o);
+    if (lane == 0) {
+      const float rg = bounds ? __uint_as_float(bounds[1]) : 6.2e-5f;      // (2^-7)^2: the a-priori worst case
+      eps[w] = 1.01f * (1.00390625f * __fsqrt_rn(rg) + __fsqrt_rn(rq)) + 1e-4f;
     }
   }
 }
@@ -75,7 +90,7 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
   const float4* src = reinterpret_cast<const float4*>(q + size_t(w) * dim);
   const int nvec = dim >> 2;
   const int aug = dim + kEuclidQPad;
-  float ss = 0.f;
+  float ss = 0.f, rq = 0.f;
   for (int v = lane; v < nvec; v += 32) {
     const float4 x = __ldg(src + v);
     ss = fmaf(x.x, x.x, ss); ss = fmaf(x.y, x.y, ss); ss = fmaf(x.z, x.z, ss); ss = fmaf(x.w, x.w, ss);
@@ -86,17 +101,27 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
     p.x = *reinterpret_cast<uint32_t*>(&lo);
     p.y = *reinterpret_cast<uint32_t*>(&hi);
     reinterpret_cast<uint2*>(q_aug + size_t(w) * aug)[v] = p;
+    const float2 l = __bfloat1622float2(lo), h = __bfloat1622float2(hi);
+    const float a = x.x - l.x, b = x.y - l.y, c = x.z - h.x, d = x.w - h.y;
+    rq = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, rq))));
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    rq += __shfl_xor_sync(0xffffffffu, rq, o);
+  }
   if (lane < kEuclidQPad / 4) {
     // bf16(1.0) = 0x3F80
     const uint2 ones = lane == 0 ? make_uint2(0x3F803F80u, 0x00003F80u) : make_uint2(0u, 0u);
     reinterpret_cast<uint2*>(q_aug + size_t(w) * aug + dim)[lane] = ones;
   }
   if (lane == 0) {
-    const float g2 = __uint_as_float(*gmax_bits);
-    eps[w] = 4e-3f * __fsqrt_rn(ss) * __fsqrt_rn(g2) + 1e-4f * g2;
+    // |S - s| <= ||q^|| ||g^ - g|| + ||q^ - q|| ||g||  (the bias columns carry -0.5*||g||^2 exactly), residuals
+    // measured: the row side at ingest (gmax_bits[1]), the query side above; fp32 accumulation term scaled by the
+    // magnitudes it sums (||q|| ||g|| and the bias)
+    const float g2 = __uint_as_float(gmax_bits[0]), rg = __uint_as_float(gmax_bits[1]);
+    const float nq_ = __fsqrt_rn(ss), ng = __fsqrt_rn(g2);
+    eps[w] = 1.01f * (1.00390625f * nq_ * __fsqrt_rn(rg) + __fsqrt_rn(rq) * ng) + 1e-4f * (nq_ * ng + g2);
   }
 }
 
@@ -119,13 +144,13 @@ int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_
 
 int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, float* qn,
                              __nv_bfloat16* qn_bf16, uint32_t* group_keys, int* cand_total, int* n_flagged,
-                             cudaStream_t st) {
+                             cudaStream_t st, float* eps, const uint32_t* bounds) {
   if (nq <= 0) return FRG_OK;
   const int warps_per_block = 4;
   // same smem/L1 split as the tensor-core kernels that follow: no carve-out switch between launches
   FRG_CUDA(func_attr_once(normalise_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   normalise_queries_kernel<<<(nq + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(
-      q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, cand_total, n_flagged);
+      q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, cand_total, n_flagged, eps, bounds);
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;

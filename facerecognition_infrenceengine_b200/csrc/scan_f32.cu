@@ -231,7 +231,7 @@ scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restric
                         int* __restrict__ ctl, int K, int32_t tenant, float threshold, int64_t row_offset,
                         float* __restrict__ part_sc, int32_t* __restrict__ part_ix,
                         int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
-                        uint8_t* __restrict__ out_accept) {
+                        uint8_t* __restrict__ out_accept, const XPush x) {
   extern __shared__ unsigned char smem_raw[];
   float* l_sc = reinterpret_cast<float*>(smem_raw);
   int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
@@ -255,10 +255,22 @@ scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restric
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int slot = threadIdx.x >> 5; slot < nf; slot += kScanWarps)
+  for (int slot = threadIdx.x >> 5; slot < nf; slot += kScanWarps) {
+    const int q = flagged[slot];
     merge_one<int32_t, KMAX>(part_sc, part_ix, int(gridDim.x), nq_total, K, K, METRIC, threshold, row_offset,
-                             /*internal_euclid=*/METRIC == FRG_METRIC_EUCLIDEAN ? 1 : 0, slot, flagged[slot], int64_t(nq_total) * K, int64_t(nq_total) * K, out_rows, out_scores,
+                             /*internal_euclid=*/METRIC == FRG_METRIC_EUCLIDEAN ? 1 : 0, slot, q, int64_t(nq_total) * K, int64_t(nq_total) * K, out_rows, out_scores,
                              out_accept);
+    if (x.peer_bufs) {
+      // row-sharded gallery: the redone query's top-k is final now - send it to every rank (select skipped it)
+      __syncwarp();                // lane 0's result stores are visible to the warp
+      const int lane = threadIdx.x & 31;
+      for (int c = lane; c < x.world * K; c += 32) {
+        const int peer = c / K, j = c - peer * K;
+        const int64_t s_ = int64_t(q) * K + j;
+        xpush_slot(x, (x.rank + 1 + peer) % x.world, s_, out_rows[s_], out_scores[s_]);
+      }
+    }
+  }
 }
 
 static int scan_grid(const ScanArgs& a) {
@@ -348,28 +360,28 @@ int launch_scan_f32(const ScanArgs& a, void* workspace, int64_t row_offset, floa
 
 template <int NJ, int QB, int KMAX>
 static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int* ctl, float threshold,
-                            int64_t row_offset, float* ps, int32_t* pi, int64_t* out_rows, float* out_scores,
-                            uint8_t* out_accept, cudaStream_t st) {
+                            int64_t row_offset, float* ps, int32_t* pi, const XPush& push, int64_t* out_rows,
+                            float* out_scores, uint8_t* out_accept, cudaStream_t st) {
   const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
   if (a.master && a.metric == FRG_METRIC_EUCLIDEAN) {
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_EUCLIDEAN, KMAX, float>;
     FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
                            a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
-                           out_accept));
+                           out_accept, push));
   } else if (a.master) {
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float>;
     FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
                            a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
-                           out_accept));
+                           out_accept, push));
   } else {
     // bf16-only store: the exact re-do reads the scan plane (fp32 query x bf16 row, fp32 accumulation)
     auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, __nv_bfloat16>;
     FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.plane, a.tags, a.rows, a.qn,
                            a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
-                           out_accept));
+                           out_accept, push));
   }
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
@@ -378,18 +390,18 @@ static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int
 
 template <int NJ, int QB>
 static int launch_flagged_t(const ScanArgs& a, int grid, const int* flagged, int* ctl, float threshold,
-                            int64_t row_offset, float* ps, int32_t* pi, int64_t* out_rows, float* out_scores,
-                            uint8_t* out_accept, cudaStream_t st) {
-  if (a.k == 1) return launch_flagged_k<NJ, QB, 1>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
-  if (a.k <= 4) return launch_flagged_k<NJ, QB, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
-  if (a.k <= 8) return launch_flagged_k<NJ, QB, 8>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
-  return launch_flagged_k<NJ, QB, 16>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st);
+                            int64_t row_offset, float* ps, int32_t* pi, const XPush& push, int64_t* out_rows,
+                            float* out_scores, uint8_t* out_accept, cudaStream_t st) {
+  if (a.k == 1) return launch_flagged_k<NJ, QB, 1>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st);
+  if (a.k <= 4) return launch_flagged_k<NJ, QB, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st);
+  if (a.k <= 8) return launch_flagged_k<NJ, QB, 8>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st);
+  return launch_flagged_k<NJ, QB, 16>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st);
 }
 
 // ctl: device int[2] = {number of flagged queries, ticket counter (0)}
 int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, int* ctl, int64_t row_offset,
-                            float threshold, int64_t* out_rows, float* out_scores, uint8_t* out_accept,
-                            cudaStream_t st) {
+                            float threshold, const XPush& push, int64_t* out_rows, float* out_scores,
+                            uint8_t* out_accept, cudaStream_t st) {
   if (a.rows <= 0 || a.nq <= 0) return FRG_OK;
   const int grid = a.sm_count;       // partial lists are sized for the worst case (every query flagged)
   const size_t n_part = size_t(grid) * a.nq * a.k;
@@ -399,9 +411,9 @@ int launch_scan_f32_flagged(const ScanArgs& a, const int* flagged, int* ctl, int
   int32_t* pi = reinterpret_cast<int32_t*>(ps + n_part);
   int rc;
   switch (a.dim) {
-    case 128: rc = launch_flagged_t<1, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st); break;
-    case 256: rc = launch_flagged_t<2, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st); break;
-    case 512: rc = launch_flagged_t<4, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, out_rows, out_scores, out_accept, st); break;
+    case 128: rc = launch_flagged_t<1, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st); break;
+    case 256: rc = launch_flagged_t<2, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st); break;
+    case 512: rc = launch_flagged_t<4, 4>(a, grid, flagged, ctl, threshold, row_offset, ps, pi, push, out_rows, out_scores, out_accept, st); break;
     default: set_error("flagged scan: dim %d not built", a.dim); rc = FRG_ERR_UNSUPPORTED; break;
   }
   cudaError_t e = cudaFreeAsync(ws, st);

@@ -11,19 +11,32 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, float4 v) {
+// writes the bf16 image of v and returns ||v - bf16(v)||^2 of the four elements (each difference is exact in fp32)
+__device__ __forceinline__ float store_bf16x4(__nv_bfloat16* dst, float4 v) {
   __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
   __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
   uint2 packed;
   packed.x = *reinterpret_cast<uint32_t*>(&lo);
   packed.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(dst) = packed;
+  const float2 l = __bfloat1622float2(lo), h = __bfloat1622float2(hi);
+  const float a = v.x - l.x, b = v.y - l.y, c = v.z - h.x, d = v.w - h.y;
+  return fmaf(a, a, fmaf(b, b, fmaf(c, c, d * d)));
+}
+
+// The tensor-core filter's error bound is DATA-DEPENDENT and rigorous: |q^.g^ - q.g| <= ||q^|| ||g^ - g|| +
+// ||q^ - q|| ||g|| (q^, g^ the bf16 images).  bounds[1] keeps the largest ||g^ - g||^2 of any row ever stored
+// (non-negative floats order like their bit patterns); the query side is measured per query (queries.cu).
+// A NaN row (zero vector) is left out: it can never match either way.
+__device__ __forceinline__ void fold_residual(uint32_t* bounds, float rr, int lane) {
+  rr = warp_sum(rr);
+  if (bounds && lane == 0 && rr < INFINITY) atomicMax(bounds + 1, __float_as_uint(rr));
 }
 
 // Euclidean scan plane (raw stores): columns dim .. dim+15 of the row = [hi, mid, lo, 0 ...], the exact
 // three-term bf16 split of c = -0.5 * ||g||^2 (24 significand bits = 3 x 8), so that the tensor-core
 // product with a query image [q, 1, 1, 1, 0 ...] accumulates q.g - 0.5*||g||^2.  The largest ||g||^2
-// ever stored is folded into *gmax_bits (non-negative floats order like their bit patterns); it scales
+// ever stored is folded into gmax_bits[0] (non-negative floats order like their bit patterns); it scales
 // the filter's error bound.  Non-finite norms are left out: such rows can never match either way.
 __device__ __forceinline__ void store_bias_columns(__nv_bfloat16* row_aug, float ss, uint32_t* gmax_bits, int lane) {
   if (lane < kEuclidPad / 4) {
@@ -69,6 +82,7 @@ ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
     }
     float4* m = master ? reinterpret_cast<float4*>(master + dst * dim) : nullptr;   // null: bf16-only store
     float ss_stored = 0.f;                    // ||stored row||^2, for the Euclidean plane's bias columns
+    float rr = 0.f;                           // ||row - bf16(row)||^2
     for (int v = lane; v < nvec; v += 32) {
       float4 x = __ldg(src + v);
       if (normalise) {
@@ -78,8 +92,9 @@ ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
       ss_stored = fmaf(x.x, x.x, ss_stored); ss_stored = fmaf(x.y, x.y, ss_stored);
       ss_stored = fmaf(x.z, x.z, ss_stored); ss_stored = fmaf(x.w, x.w, ss_stored);
       if (m) m[v] = x;
-      if (plane) store_bf16x4(plane + dst * plane_dim + v * 4, x);
+      if (plane) rr += store_bf16x4(plane + dst * plane_dim + v * 4, x);
     }
+    if (plane) fold_residual(gmax_bits, rr, lane);
     if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), gmax_bits, lane);
     if (lane == 0) tag_out[dst] = tags ? tags[i] : 0;
   }
@@ -170,6 +185,7 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float norm = __fsqrt_rn(float(ss));
     float ss_stored = 0.f;
+    float rr = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int b = lane + 32 * j;
@@ -184,8 +200,8 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
           m[0] = lo; m[1] = hi;
         }
         if (plane) {
-          store_bf16x4(plane + dst * plane_dim + b * 8, lo);
-          store_bf16x4(plane + dst * plane_dim + b * 8 + 4, hi);
+          rr += store_bf16x4(plane + dst * plane_dim + b * 8, lo);
+          rr += store_bf16x4(plane + dst * plane_dim + b * 8 + 4, hi);
         }
         ss_stored = fmaf(lo.x, lo.x, ss_stored); ss_stored = fmaf(lo.y, lo.y, ss_stored);
         ss_stored = fmaf(lo.z, lo.z, ss_stored); ss_stored = fmaf(lo.w, lo.w, ss_stored);
@@ -193,6 +209,7 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
         ss_stored = fmaf(hi.z, hi.z, ss_stored); ss_stored = fmaf(hi.w, hi.w, ss_stored);
       }
     }
+    if (plane) fold_residual(gmax_bits, rr, lane);
     if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), gmax_bits, lane);
     if (lane == 0) tag_out[dst] = tag;
   }

@@ -13,6 +13,7 @@ reference's strict ``>`` scan resolves exact ties by that order (infrenceServer.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import json
 import struct
@@ -22,6 +23,61 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _native as N
+
+
+class StaleRows(RuntimeError):
+    """Row numbers of a match were looked up after ``compact()`` renumbered the gallery."""
+
+
+class _LayoutLock:
+    """Readers-writer lock between matches and ``compact()``.  A match and the row -> id translation of its
+    result form ONE read section (many may run at once - the native call releases the GIL); ``compact()``, which
+    renumbers rows, is the only writer: it waits for the read sections in flight and holds new ones off while it
+    runs.  Without it a match that straddles a compaction has its rows translated through the wrong table and a
+    whole batch of accepted faces is attributed to the wrong people.  Read sections nest per thread."""
+
+    def __init__(self):
+        self._c = threading.Condition()
+        self._readers = 0
+        self._writer = False
+        self._writers_waiting = 0
+        self._depth = threading.local()
+
+    @contextlib.contextmanager
+    def read(self):
+        d = getattr(self._depth, "n", 0)
+        if d == 0:
+            with self._c:
+                while self._writer or self._writers_waiting:
+                    self._c.wait()
+                self._readers += 1
+        self._depth.n = d + 1
+        try:
+            yield
+        finally:
+            self._depth.n = d
+            if d == 0:
+                with self._c:
+                    self._readers -= 1
+                    if not self._readers:
+                        self._c.notify_all()
+
+    @contextlib.contextmanager
+    def write(self):
+        if getattr(self._depth, "n", 0):
+            raise RuntimeError("compact() inside a read section of the same thread would wait for itself")
+        with self._c:
+            self._writers_waiting += 1
+            while self._writer or self._readers:
+                self._c.wait()
+            self._writers_waiting -= 1
+            self._writer = True
+        try:
+            yield
+        finally:
+            with self._c:
+                self._writer = False
+                self._c.notify_all()
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -48,8 +104,12 @@ class GalleryStore:
         self._id_of: Dict[int, str] = {}
         self._meta: Dict[str, Dict] = {}
         self._tenants: Dict[str, int] = {}
+        self._tenant_of: Dict[str, int] = {}         # id -> tenant code (company subset sizes without a device read)
+        self._anon_tags: Dict[int, int] = {}         # tenant code -> rows filled synthetically with it
         self._anon: List[Tuple[int, int, int]] = []  # (row0, n, global_row0) ranges filled synthetically
         self._rows = 0                               # mirror of stats.rows
+        self._layout = _LayoutLock()                 # matches + id lookups (readers) vs compact() (writer)
+        self.layout_version = 0                      # bumped by every compact(): row numbers of older results are void
 
     # ------------------------------------------------------------------ life-cycle
     def close(self):
@@ -131,6 +191,7 @@ class GalleryStore:
             N.check(N.lib.frg_store_fill_synthetic(self.handle, int(n), int(global_row0), int(seed), int(tag),
                                                    C.c_void_p(stream or 0)))
             self._anon.append((self._rows, int(n), int(global_row0)))
+            self._anon_tags[int(tag)] = self._anon_tags.get(int(tag), 0) + int(n)
             self._rows += int(n)
 
     # ------------------------------------------------------------------ id-level API (the dict)
@@ -165,8 +226,19 @@ class GalleryStore:
                 return "%024x" % (g0 + row - r0)
         return None
 
-    def ids_of(self, rows) -> List[List[Optional[str]]]:
-        """id_of over a whole [F, k] result (one pass over plain Python ints: ~0.1 us per slot)."""
+    def reading(self):
+        """Context manager: a match and the translation of its rows (``id_of`` / ``ids_of`` / ``metadata``) belong
+        in ONE ``with store.reading():`` block, so that ``compact()`` cannot renumber the rows in between.
+        ``Matcher.match(with_ids=True)`` and the two processors do this themselves."""
+        return self._layout.read()
+
+    def ids_of(self, rows, layout_version: Optional[int] = None) -> List[List[Optional[str]]]:
+        """id_of over a whole [F, k] result (one pass over plain Python ints: ~0.1 us per slot).
+        layout_version: the ``MatchResult.layout_version`` the rows belong to - raises :class:`StaleRows` when a
+        ``compact()`` has renumbered the gallery since (only possible outside a ``reading()`` block)."""
+        if layout_version is not None and layout_version != self.layout_version:
+            raise StaleRows("rows of layout %d looked up in layout %d: the gallery was compacted in between"
+                            % (layout_version, self.layout_version))
         get, anon = self._id_of.get, self._anon
 
         def one(r):
@@ -184,6 +256,13 @@ class GalleryStore:
 
     def metadata(self, pid: str) -> Optional[Dict]:
         return self._meta.get(str(pid))
+
+    def count_tenant(self, company_id: Optional[str]) -> int:
+        """Live ids of one company - `len(get_embeddings_for_company(c))` (infrenceServer.py:343-380) - from the
+        host-side id table, no device read.  (Synthetic fills count by the tag they were filled with.)"""
+        code = self.tenant_code(company_id, create=False)
+        with self._lock:
+            return sum(1 for c in self._tenant_of.values() if c == code) + self._anon_tags.get(code, 0)
 
     def upsert(self, ids: Sequence[str], vecs: np.ndarray, company_ids: Optional[Sequence[Optional[str]]] = None,
                meta: Optional[Sequence[Dict]] = None, prenormalised: bool = False):
@@ -209,6 +288,8 @@ class GalleryStore:
                     p = str(ids[i])
                     self._row_of[p] = first + j
                     self._id_of[first + j] = p
+            for i in old_i + new_i:
+                self._tenant_of[str(ids[i])] = int(tags[i])
             if meta is not None:
                 for p, m in zip(ids, meta):
                     self._meta[str(p)] = m
@@ -224,12 +305,14 @@ class GalleryStore:
                     rows.append(r)
                     self._id_of.pop(r, None)
                     self._meta.pop(p, None)
+                    self._tenant_of.pop(p, None)
             self.remove_rows(rows)
             return len(rows)
 
     def compact(self):
-        """Drop tombstones; order (hence tie behaviour) is unchanged."""
-        with self._lock:
+        """Drop tombstones; order (hence tie behaviour) is unchanged.  Rows are renumbered: waits for every
+        match / id lookup in flight (``reading()``), holds new ones off meanwhile, bumps ``layout_version``."""
+        with self._layout.write(), self._lock:
             n = self._rows
             mapping = np.empty(n, np.int64)
             N.check(N.lib.frg_store_compact(self.handle, _ptr(mapping)))
@@ -241,6 +324,7 @@ class GalleryStore:
             self._row_of, self._id_of = new_row_of, new_id_of
             self._anon = [(int(mapping[r0]), cnt, g0) for r0, cnt, g0 in self._anon if cnt and mapping[r0] >= 0]
             self._rows = int((mapping >= 0).sum())
+            self.layout_version += 1
 
     def snapshot_arrays(self):
         """(ids, G fp32[n, dim], tags) of the LIVE rows in gallery order - what get_all() returned
@@ -302,4 +386,5 @@ class GalleryStore:
         for r, pid in enumerate(ids):
             store._row_of[pid] = r
             store._id_of[r] = pid
+            store._tenant_of[pid] = int(tags[r])
         return store

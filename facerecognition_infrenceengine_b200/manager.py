@@ -13,6 +13,7 @@ under ``'embedding'``.
 """
 from __future__ import annotations
 
+import logging
 import threading
 import time
 from datetime import datetime, timezone
@@ -21,6 +22,8 @@ from typing import Dict, Iterable, List, Optional
 import numpy as np
 
 from .gallery import GalleryStore
+
+logger = logging.getLogger(__name__)
 
 
 # ---- eligibility filters: the Mongo queries of the loaders, restated on dict records ----------
@@ -105,9 +108,7 @@ class GalleryView:
             return len(self.store)
         if hasattr(self.store, "count_tenant"):          # sharded gallery: host-side table, no device read
             return self.store.count_tenant(self.company_id)
-        code = self.store.tenant_code(self.company_id, create=False)
-        _, _, tags = self.store.snapshot_arrays()
-        return int((tags == code).sum())
+        return self.store.count_tenant(self.company_id)     # host-side table: no device read
 
     def __bool__(self):
         return len(self.store) > 0
@@ -133,32 +134,62 @@ class EmbeddingManager:
         self.running = False
         self.sync_thread: Optional[threading.Thread] = None
         self._evicted_since_compaction = 0
+        self._compact_not_before = 0.0       # monotonic time before which a failed compaction is not retried
+        self.rejected_records = 0            # malformed documents skipped so far (logged, as the reference does)
         self._initial_load()
 
     # ---- loading ----------------------------------------------------------------------------
     def _initial_load(self):
-        """infrenceServer.py:62-91 / peopleCount.py:716-734."""
-        self._load_updated_embeddings(self.source.employee_docs(), self.source.visitor_docs())
-        self.last_sync_time = _utcnow()
-        self.is_initial_load = False
+        """infrenceServer.py:62-91 / peopleCount.py:716-734 - errors are logged, not raised (:89-91)."""
+        try:
+            self._load_updated_embeddings(self.source.employee_docs(), self.source.visitor_docs())
+            self.last_sync_time = _utcnow()
+            self.is_initial_load = False
+        except Exception as ex:                      # noqa: BLE001
+            logger.error("Error in initial load: %s", ex)
 
     def _load_updated_embeddings(self, employees: Iterable[Dict], visitors: Iterable[Dict]):
         """infrenceServer.py:260-341 / peopleCount.py:778-814: employees first, then visitors; each
         vector is divided by its norm on ingest (done on the device)."""
         ids, vecs, comps, meta = [], [], [], []
+        dim = getattr(self.store, "dim", None)
+
+        def vector_of(doc):
+            # the reference wraps every person in its own try/except and skips the bad ones
+            # (infrenceServer.py:264-341): one malformed document must not fail the batch, let alone every
+            # later sync.  What it would have stored is a float vector of the model's size.
+            v = np.asarray(doc["embedding"], dtype=np.float32)
+            if v.ndim != 1 or (dim is not None and v.shape[0] != dim):
+                raise ValueError("embedding of shape %s, expected (%s,)" % (v.shape, dim))
+            return v
+
         for e in employees:
-            ids.append(str(e["_id"]))
-            vecs.append(np.asarray(e["embedding"], dtype=np.float32))
+            try:
+                v = vector_of(e)
+                pid = str(e["_id"])
+            except Exception as ex:                  # noqa: BLE001 - skip and log, as the reference does
+                self.rejected_records += 1
+                logger.warning("Error loading embedding for employee %s: %s", e.get("_id") if isinstance(e, dict) else e, ex)
+                continue
+            ids.append(pid)
+            vecs.append(v)
             comps.append(None if e.get("companyId") is None else str(e["companyId"]))
             meta.append({"name": e.get("employeeName", "Unknown"), "employeeId": e.get("employeeId", "Unknown"),
                          "email": e.get("employeeEmail", ""), "mobile": e.get("employeeMobile", ""),
                          "type": "employee", "lastUpdated": e.get("lastUpdated")})
-        for v in visitors:
-            ids.append(str(v["_id"]))
-            vecs.append(np.asarray(v["embedding"], dtype=np.float32))
-            comps.append(None if v.get("companyId") is None else str(v["companyId"]))
-            meta.append({"name": v.get("visitorName", "Unknown"), "type": "visitor",
-                         "lastUpdated": v.get("lastUpdated")})
+        for d in visitors:
+            try:
+                v = vector_of(d)
+                pid = str(d["_id"])
+            except Exception as ex:                  # noqa: BLE001
+                self.rejected_records += 1
+                logger.warning("Error loading embedding for visitor %s: %s", d.get("_id") if isinstance(d, dict) else d, ex)
+                continue
+            ids.append(pid)
+            vecs.append(v)
+            comps.append(None if d.get("companyId") is None else str(d["companyId"]))
+            meta.append({"name": d.get("visitorName", "Unknown"), "type": "visitor",
+                         "lastUpdated": d.get("lastUpdated")})
         if ids:
             with self.embeddings_lock:
                 self.store.upsert(ids, np.stack(vecs), comps, meta)
@@ -176,6 +207,7 @@ class EmbeddingManager:
     # both many and a sizeable share of the gallery - never for the odd eviction.
     COMPACT_MIN_DEAD = 1024
     COMPACT_DEAD_SHARE = 0.25
+    COMPACT_RETRY_S = 600
 
     def _maybe_compact(self):
         if self._evicted_since_compaction < self.COMPACT_MIN_DEAD or not hasattr(self.store, "compact"):
@@ -183,7 +215,16 @@ class EmbeddingManager:
         st = self.store.stats()
         dead = int(st.rows) - int(st.live)
         if dead >= self.COMPACT_MIN_DEAD and dead >= self.COMPACT_DEAD_SHARE * int(st.rows):
-            self.store.compact()
+            if time.monotonic() < self._compact_not_before:
+                return False
+            try:
+                self.store.compact()
+            except Exception as ex:                  # noqa: BLE001 - e.g. no device memory for the bounce chunk
+                # compaction is an optimisation: the gallery is intact (frg_store_compact changes nothing
+                # unless it succeeds), the sync goes on, and it is not retried every cycle
+                self._compact_not_before = time.monotonic() + self.COMPACT_RETRY_S
+                logger.warning("gallery compaction failed, next attempt in %d s: %s", self.COMPACT_RETRY_S, ex)
+                return False
             self._evicted_since_compaction = 0
             return True
         return False

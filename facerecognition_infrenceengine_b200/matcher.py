@@ -8,6 +8,7 @@ result shapes so a call site can be switched over line for line
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
@@ -30,11 +31,19 @@ class MatchResult:
     ids: Optional[List[List[Optional[str]]]] = None
     variant: str = ""
     launches: int = 0
+    layout_version: int = 0      # GalleryStore.layout_version the rows belong to (compact() renumbers rows)
 
 
 def _params(metric: str, variant: str, threshold: float, tenant: int, row_offset: int) -> N.MatchParams:
     return N.MatchParams(N.METRICS[metric], N.VARIANTS[variant], float(np.float32(threshold)),
                          int(tenant), int(row_offset), 0, 0)
+
+
+def _reading(store):
+    """The store's read section (GalleryStore.reading): match + row -> id translation are atomic with respect to
+    compact().  Stores without one (sharded galleries never renumber rows; test doubles) need none."""
+    fn = getattr(store, "reading", None)
+    return fn() if fn is not None else contextlib.nullcontext()
 
 
 class Matcher:
@@ -54,14 +63,19 @@ class Matcher:
             out = MatchResult(np.empty((F, k), np.int64), np.empty((F, k), np.float32), np.zeros(F, np.uint8))
         tenant = -1 if company_id is None else self.store.tenant_code(company_id, create=False)
         p = _params(self.metric, variant, threshold, tenant, row_offset)
-        N.check(N.lib.frg_match_host(self.store.handle, Q.ctypes.data, F, int(k), C.byref(p),
-                                     out.rows.ctypes.data, out.scores.ctypes.data,
-                                     out.accept.ctypes.data))
-        out.variant, out.launches = N.last_variant(), N.last_launch_count()
-        if out.accept.dtype != np.bool_:
-            out.accept = out.accept.view(np.bool_)
-        if with_ids:
-            out.ids = self.store.ids_of(out.rows)
+        # one read section: a compaction cannot renumber the rows between the match and their translation.
+        # With with_ids=False the caller translates later - inside its own `with store.reading():` around this
+        # call (the processors below), or checked through `ids_of(rows, layout_version=out.layout_version)`.
+        with _reading(self.store):
+            out.layout_version = getattr(self.store, "layout_version", 0)
+            N.check(N.lib.frg_match_host(self.store.handle, Q.ctypes.data, F, int(k), C.byref(p),
+                                         out.rows.ctypes.data, out.scores.ctypes.data,
+                                         out.accept.ctypes.data))
+            out.variant, out.launches = N.last_variant(), N.last_launch_count()
+            if out.accept.dtype != np.bool_:
+                out.accept = out.accept.view(np.bool_)
+            if with_ids:
+                out.ids = self.store.ids_of(out.rows)
         return out
 
     # ---- device tensors in/out, enqueued on the caller's stream (torch is only the allocator here)
@@ -124,16 +138,17 @@ class FaceRecognitionProcessor:
         store = self.store
         if len(embeddings) == 0 or len(store) == 0:      # `if not embeddings: return frame` (:523-525)
             return []
-        r = self._match(embeddings, 1, self.recognition_threshold, company_id, with_ids=False)
         out = []
-        for f in range(len(embeddings)):
-            if r.accept[f]:
-                pid = store.id_of(r.rows[f, 0])            # ids only for the faces that matched
-                info = store.metadata(pid) or {"name": pid, "type": "employee"}
-                out.append({"person_id": pid, "person_info": info, "recognition_score": r.scores[f, 0]})
-            else:
-                out.append({"person_id": None, "person_info": {"name": "Unknown", "type": "unknown"},
-                            "recognition_score": 0})
+        with _reading(store):        # match + id lookup are one read section (compact() renumbers rows)
+            r = self._match(embeddings, 1, self.recognition_threshold, company_id, with_ids=False)
+            for f in range(len(embeddings)):
+                if r.accept[f]:
+                    pid = store.id_of(r.rows[f, 0])            # ids only for the faces that matched
+                    info = store.metadata(pid) or {"name": pid, "type": "employee"}
+                    out.append({"person_id": pid, "person_info": info, "recognition_score": r.scores[f, 0]})
+                else:
+                    out.append({"person_id": None, "person_info": {"name": "Unknown", "type": "unknown"},
+                                "recognition_score": 0})
         return out
 
 
@@ -159,19 +174,20 @@ class CameraProcessor:
         stats["faces"] = len(embeddings)
         if len(embeddings) == 0:
             return [], stats
-        r = self._match(embeddings, 1, self.recognition_threshold, with_ids=False)
-        # three-way decision in fp32 (peopleCount.py:876-887); ids are looked up only for recognised faces
-        accept = r.accept.tolist()
-        below = (r.scores[:, 0] < np.float32(self.unknown_threshold)).tolist()   # best_score stays -1 when nothing matched
-        rows, scores = r.rows[:, 0].tolist(), r.scores[:, 0].tolist()
         events = []
-        for f in range(len(accept)):
-            if accept[f]:
-                events.append(("recognized", store.id_of(rows[f]), scores[f]))
-            elif below[f]:
-                events.append(("unknown", None, None))
-            else:
-                events.append(("ignored", None, None))
+        with _reading(store):        # match + id lookup are one read section (compact() renumbers rows)
+            r = self._match(embeddings, 1, self.recognition_threshold, with_ids=False)
+            # three-way decision in fp32 (peopleCount.py:876-887); ids are looked up only for recognised faces
+            accept = r.accept.tolist()
+            below = (r.scores[:, 0] < np.float32(self.unknown_threshold)).tolist()   # best_score stays -1 when nothing matched
+            rows, scores = r.rows[:, 0].tolist(), r.scores[:, 0].tolist()
+            for f in range(len(accept)):
+                if accept[f]:
+                    events.append(("recognized", store.id_of(rows[f]), scores[f]))
+                elif below[f]:
+                    events.append(("unknown", None, None))
+                else:
+                    events.append(("ignored", None, None))
         stats["recognized"] = sum(accept)
         stats["unknown"] = sum(1 for a, b in zip(accept, below) if b and not a)
         return events, stats

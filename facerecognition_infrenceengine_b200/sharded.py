@@ -345,7 +345,7 @@ class ShardedMatcher:
         rows, scores, accept = out
         self._epoch += 1
         x = N.Exchange(rank=self.g.rank, world=self.g.world, peer_bufs=int(hdl.buffer_ptrs_dev), block_cap=cap,
-                       epoch=((self._epoch - 1) % 0xFFFFFFFF) + 1, reserved=0)
+                       epoch=((self._epoch - 1) % 0xFFFFFFFF) + 1, flags=0)
         p = N.MatchParams(metric=N.METRICS[self.metric], variant=N.VARIANTS[variant],
                           threshold=float(np.float32(threshold)), tenant=int(tenant), row_offset=int(self.g.offset),
                           flags=0, reserved=0)
@@ -354,6 +354,26 @@ class ShardedMatcher:
             self.g.store.handle, C.c_void_p(Q.data_ptr()), F, k, C.byref(p), C.byref(x),
             C.c_void_p(rows_l.data_ptr()), C.c_void_p(scores_l.data_ptr()), C.c_void_p(rows.data_ptr()),
             C.c_void_p(scores.data_ptr()), C.c_void_p(accept.data_ptr()), C.c_void_p(stream)))
+
+    def check_exchange(self, clear: bool = False):
+        """Host-side health check of the peer-memory exchange; call it wherever the results of earlier
+        ``match`` calls are about to be trusted (it synchronises the current stream).  The poll kernel never
+        hangs or traps: when a rank did not take part in a call (the ranks made different numbers of
+        collective calls), passed another (F, k), or died, it gives up after FRG_EXCHANGE_TIMEOUT_MS (default
+        2000), returns "no match" everywhere and leaves a status record - raised here as ``NativeError``
+        (code ``ERR_STATE``) naming the call, the rank and the shapes.  After a failure the exchange buffer
+        is dropped; the next ``match`` sets it up again (collective)."""
+        if self._x is None:
+            return
+        import torch
+        t = self._x[0]
+        st = N.ExchangeStatus()
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        rc = N.lib.frg_exchange_status(t.device.index, C.c_void_p(t.data_ptr()), 1 if clear else 0,
+                                       C.c_void_p(stream), C.byref(st))
+        if rc != N.OK:
+            self._x = None
+            N.check(rc)
 
     # ---- CUDA pieces ------------------------------------------------------------------------------
     def _local_cuda(self, Q, k, threshold, variant, rows_out, scores_out, tenant=-1):
@@ -425,6 +445,8 @@ class ShardedMatcher:
         dev = torch.device("cuda", self.g.store.device if self.g.device is None else self.g.device)
         Qd = torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.g.dim)).to(dev)
         rows, scores, acc = self.match(Qd, k, threshold, variant, company_id=company_id)
+        if self.exchange == "p2p":
+            self.check_exchange()                      # results are about to be read: a void call raises here
         out = MatchResult(rows.cpu().numpy(), scores.cpu().numpy(), acc.cpu().numpy().astype(np.bool_))
         if with_ids:
             out.ids = self.ids_of(out.rows)

@@ -187,17 +187,23 @@ FRG_API int frg_merge_topk_strided(int32_t device, const float* scores, int64_t 
  * local top-k travels as 8-byte {payload, epoch} packets written straight into slot `rank` of every rank's
  * buffer; a packet is valid when its epoch word matches, so there is no fence, flag or rendezvous.
  * Collective: every rank makes the same call with the same nq, k and epoch = 1, 2, 3, ... */
+#define FRG_XCHG_PUSH_ONLY  1u   /* run the local match and push its result; merge later (same epoch) */
+#define FRG_XCHG_MERGE_ONLY 2u   /* the result of this epoch went out earlier: only wait for all ranks and merge */
+#define FRG_XCHG_TIMEOUT_MS(ms) ((uint32_t)(ms) << 8)   /* per-call bound of the merge kernel's waits, 1 .. 2^24-1 ms
+                                                          (0 = FRG_EXCHANGE_TIMEOUT_MS from the environment, else 2000) */
 typedef struct frg_exchange_t {
-  int32_t rank, world;
+  int32_t rank, world;     /* world <= 32 */
   void* const* peer_bufs;  /* DEVICE array of `world` device pointers */
   int64_t block_cap;       /* from frg_exchange_bytes() */
   uint32_t epoch;          /* one more per call, never 0 */
-  uint32_t reserved;
+  uint32_t flags;          /* 0, or FRG_XCHG_PUSH_ONLY / FRG_XCHG_MERGE_ONLY: the two halves of a call, issued
+                              separately (e.g. ranks emulated one after the other on a single device);
+                              | FRG_XCHG_TIMEOUT_MS(ms) */
 } frg_exchange_t;
-FRG_API int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap, int64_t* total);
+FRG_API int frg_exchange_bytes(int32_t world, int32_t nq, int32_t k, int64_t* block_cap, int64_t* total);   /* world <= 32 */
 /* frg_match on this rank's shard + exchange + merge in one enqueue: the select stage pushes every query's
- * top-k to all ranks the moment it is final; a last kernel pushes the stragglers (queries redone by the
- * exact fallback) and merges each query's `world` lists as their packets arrive.  local_rows / local_scores:
+ * top-k to all ranks the moment it is final (the exact fallback pushes the queries it redoes); a last kernel,
+ * which only waits, merges each query's `world` lists as their packets arrive.  local_rows / local_scores:
  * [nq][k] device scratch for this shard's own result (global rows: params->row_offset).  out_*: the merged
  * result, identical on every rank. */
 FRG_API int frg_match_exchange(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
@@ -207,6 +213,25 @@ FRG_API int frg_match_exchange(frg_store* s, const float* q, int32_t nq, int32_t
 FRG_API int frg_exchange_merge_topk(int32_t device, const frg_exchange_t* x, const int64_t* local_rows,
                             const float* local_scores, int32_t nq, int32_t k, int32_t metric, float threshold,
                             int64_t* out_rows, float* out_scores, uint8_t* out_accept, void* stream);
+
+/* Waits are bounded (FRG_EXCHANGE_TIMEOUT_MS, default 2000): when a rank never announces the call (the ranks made
+ * different numbers of collective calls; a rank died), announces a different (nq, k), or a packet never arrives,
+ * the merge kernel gives up, writes "no match" results and a status record into the header of this rank's
+ * buffer - it never traps, never hangs.  frg_exchange_status copies that record out (own_buf = this rank's
+ * buffer, device pointer; synchronises `stream`): FRG_OK, or FRG_ERR_STATE with frg_last_error() naming call,
+ * rank and shapes.  The record is sticky until cleared (clear != 0) or the buffer is zeroed again. */
+typedef struct frg_exchange_status_t {
+  int32_t code;            /* 0 ok, 1 a rank never announced the call, 2 (nq, k) mismatch, 3 a packet never arrived */
+  int32_t peer;            /* the rank concerned */
+  uint32_t epoch;          /* the failing call on this rank */
+  uint32_t peer_epoch;     /* what that rank's header slot / packet carried instead */
+  int32_t nq, k;           /* this rank's shape */
+  int32_t peer_nq, peer_k; /* code 2: the peer's */
+  int32_t slot;            /* code 3: nq*k slot that never arrived */
+  int32_t reserved;
+} frg_exchange_status_t;
+FRG_API int frg_exchange_status(int32_t device, const void* own_buf, int32_t clear, void* stream,
+                                frg_exchange_status_t* out);
 
 /* ---- introspection for tests / bench: name and launch count of the kernels the LAST frg_match /
  * frg_match_host on this thread enqueued (bench.py reports it as gpu_launches). */

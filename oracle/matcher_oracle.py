@@ -171,6 +171,41 @@ def match_topk(Q: np.ndarray, G: np.ndarray, k: int = 1, threshold: float = LIVE
     return rows, scores, accept_fp32(scores[:, 0], rows[:, 0], threshold)
 
 
+def match_topk_fast(Q: np.ndarray, G: np.ndarray, k: int = 1, threshold: float = LIVE_THRESHOLD,
+                    tags: Optional[np.ndarray] = None, tenant: Optional[int] = None, chunk: int = 128):
+    """:func:`match_topk` for LARGE inputs (1024 x 1 M): same definition, same results (checked against it in
+    tests/test_oracle_properties.py), but the score matrix is produced in query chunks and the k best of a row are
+    found with a partial selection instead of a full stable sort: everything >= the k-th largest score is kept
+    (ties included), then ordered by (score desc, row asc) - which IS the stable descending sort's prefix."""
+    Q = np.asarray(Q, dtype=np.float32)
+    G = np.asarray(G, dtype=np.float32)
+    F, N = len(Q), len(G)
+    rows = np.full((F, k), NO_ROW, dtype=np.int64)
+    scores = np.full((F, k), NO_SCORE, dtype=np.float32)
+    if N == 0:
+        return rows, scores, np.zeros(F, bool)
+    mask = None
+    if tags is not None:
+        tags = np.asarray(tags)
+        mask = tags >= 0
+        if tenant is not None and tenant >= 0:
+            mask &= tags == tenant
+    for a in range(0, F, chunk):
+        S = cosine_scores(Q[a:a + chunk], G)
+        S[~(S > np.float32(-1))] = -np.inf                 # scores <= -1 and NaN never match
+        if mask is not None:
+            S[:, ~mask] = -np.inf
+        kk = min(k, N)
+        part = np.partition(S, N - kk, axis=1)[:, N - kk]  # k-th largest per row
+        for f in range(S.shape[0]):
+            s = S[f]
+            cand = np.nonzero((s >= part[f]) & (s > -np.inf))[0]
+            order = cand[np.lexsort((cand, -s[cand]))][:k]
+            rows[a + f, :order.size] = order
+            scores[a + f, :order.size] = s[order]
+    return rows, scores, accept_fp32(scores[:, 0], rows[:, 0], threshold)
+
+
 def euclidean_topk(Q: np.ndarray, G: np.ndarray, k: int = 1, tolerance: float = 0.6,
                    tags: Optional[np.ndarray] = None, tenant: Optional[int] = None):
     """Config 3 (128-d Euclidean).  NOT in the reference - OUR definition, parity unpinned:

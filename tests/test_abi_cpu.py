@@ -41,6 +41,8 @@ def test_library_exports_every_declared_symbol(native):
 def test_struct_layouts_match_header(native):
     assert ctypes.sizeof(native.StoreStats) == 56
     assert ctypes.sizeof(native.MatchParams) == 32
+    assert ctypes.sizeof(native.Exchange) == 32
+    assert ctypes.sizeof(native.ExchangeStatus) == 40
     assert native.lib.frg_abi_version() == 1
 
 
@@ -84,8 +86,8 @@ int main(void) {
   int rc;
   memset(&p, 0, sizeof p);
   memset(&x, 0, sizeof x);
-  printf("abi=%d params=%u stats=%u exchange=%u\n", frg_abi_version(), (unsigned)sizeof p,
-         (unsigned)sizeof(frg_store_stats_t), (unsigned)sizeof x);
+  printf("abi=%d params=%u stats=%u exchange=%u xstatus=%u\n", frg_abi_version(), (unsigned)sizeof p,
+         (unsigned)sizeof(frg_store_stats_t), (unsigned)sizeof x, (unsigned)sizeof(frg_exchange_status_t));
   rc = frg_device_count(&n);                 /* no GPU here: an error code and a message, not a crash */
   printf("device_count rc=%d n=%d err=%s\n", rc, (int)n, frg_last_error());
   rc = frg_store_create(0, 512, 16, FRG_STORE_BF16_PLANE, &s);
@@ -109,7 +111,7 @@ def test_header_is_plain_c_and_links_from_c(native, tmp_path):
     assert r.returncode == 0, r.stderr
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
-    assert "abi=1 params=32 stats=56 exchange=32" in out.stdout
+    assert "abi=1 params=32 stats=56 exchange=32 xstatus=40" in out.stdout
     import torch
     if not torch.cuda.is_available():
         assert "device_count rc=2" in out.stdout and "store_create rc=0" not in out.stdout

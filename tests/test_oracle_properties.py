@@ -78,3 +78,43 @@ def test_reference_arm_emits_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["gallery_rows"] == 20000 and line["gpu_launches"] == 0
+
+
+def test_adversarial_rounding_case_really_breaks_a_4e3_margin():
+    """Premises of tests/rounding_case.py, checked in numpy: exact scores put A ahead of B by more than the 1e-4 id
+    tolerance, the bf16 images put B ahead of A by more than 2 * 4e-3 - so a filter margin derived from a 2^-9
+    unit roundoff would drop the true best row, while |error| stays within the rigorous 2^-7 + 2^-16."""
+    from rounding_case import adversarial_pair, bf16_rn
+    for seed in range(4):
+        A, B, q = adversarial_pair(seed)
+        n32 = np.sqrt(np.sum(q * q, dtype=np.float32))
+        assert abs(float(n32) - 1.0) < 1e-6
+        qn = (q / n32).astype(np.float32)
+        sA, sB = float(qn.astype(np.float64) @ A), float(qn.astype(np.float64) @ B)
+        SA = float(bf16_rn(qn).astype(np.float64) @ bf16_rn(A))
+        SB = float(bf16_rn(qn).astype(np.float64) @ bf16_rn(B))
+        assert sA - sB > 2e-4 and SB - SA > 8.2e-3
+        assert abs(SA - sA) <= (2.0 ** -7 + 2.0 ** -16) * 1.005 and abs(SB - sB) <= (2.0 ** -7 + 2.0 ** -16) * 1.005
+
+
+def test_fast_topk_oracle_equals_the_stable_sort_oracle():
+    """match_topk_fast (partial selection, chunked) == match_topk (full stable sort) on data with exact ties, a NaN
+    row, a zero query, removed rows and a tenant filter."""
+    from oracle import matcher_oracle as mo
+    rng = np.random.default_rng(11)
+    n, d = 3000, 64
+    G = mo.normalise_rows(rng.standard_normal((n, d)).astype(np.float32))
+    G[100:140] = G[7]                       # exact ties
+    G[500] = np.nan
+    tags = rng.integers(0, 3, n).astype(np.int32)
+    tags[rng.integers(0, n, 200)] = -1
+    Q = rng.standard_normal((70, d)).astype(np.float32)
+    Q[3] = G[7] * 2.5
+    Q[5] = 0
+    Q[6, 2] = np.nan
+    for k in (1, 5, 16):
+        for tg, tn in ((None, None), (tags, None), (tags, 1), (tags, 7)):
+            a = mo.match_topk(Q, G, k, 0.45, tg, tn)
+            b = mo.match_topk_fast(Q, G, k, 0.45, tg, tn, chunk=32)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)

@@ -133,3 +133,127 @@ def test_manager_compacts_after_heavy_eviction_only():
     assert st.live == 4000 and st.compactions == 1 and st.rows == 4000
     m._remove_inactive_employees()                  # nothing new: nothing happens
     assert st.compactions == 1
+
+
+def _counting_store(dim=8, fail_compact=False):
+    from types import SimpleNamespace
+
+    class Store:
+        def __init__(self):
+            self.dim, self.rows, self.live, self.compactions, self.ids_ = dim, 0, 0, 0, {}
+
+        def upsert(self, ids, vecs, comps=None, meta=None):
+            assert vecs.shape == (len(ids), dim)
+            for i in ids:
+                if i not in self.ids_:
+                    self.rows += 1; self.live += 1
+                self.ids_[i] = True
+
+        def remove(self, ids):
+            gone = [i for i in ids if i in self.ids_]
+            for i in gone:
+                del self.ids_[i]
+            self.live -= len(gone)
+            return len(gone)
+
+        def stats(self):
+            return SimpleNamespace(rows=self.rows, live=self.live, capacity=self.rows, bytes=0, version=0)
+
+        def compact(self):
+            self.compactions += 1
+            if fail_compact:
+                raise RuntimeError("libfrg error 3: out of device memory")
+            self.rows = self.live
+
+    return Store()
+
+
+def test_one_malformed_document_does_not_stop_the_sync():
+    """The reference wraps every person in its own try/except and skips the bad ones (infrenceServer.py:264-341).
+    Here a wrong-sized, a None and a ragged embedding are skipped and logged; the good documents of the same batch
+    are enrolled, the constructor does not raise, and last_sync_time advances so the bad document is not refetched
+    for ever."""
+    from datetime import datetime
+    from facerecognition_infrenceengine_b200.manager import EmbeddingManager, ListSource
+
+    def emp(i, emb):
+        return {"_id": "%024x" % i, "embedding": emb, "companyId": "c", "status": "active", "blacklisted": False,
+                "lastUpdated": datetime(2026, 1, 1)}
+
+    good = np.ones(8, np.float32)
+    E = [emp(0, good), emp(1, np.ones(7, np.float32)), emp(2, good), emp(3, [[1.0, 2.0], [3.0]]), emp(4, "not a vector")]
+    V = [{"_id": "%024x" % 100, "embedding": np.ones((2, 4), np.float32), "companyId": "c", "lastUpdated": datetime(2026, 1, 1)},
+         {"_id": "%024x" % 101, "embedding": good, "companyId": "c", "lastUpdated": datetime(2026, 1, 1)}]
+    st = _counting_store()
+    m = EmbeddingManager(ListSource(E, V), mode="live", store=st)
+    assert sorted(st.ids_) == ["%024x" % i for i in (0, 2, 101)]
+    assert m.rejected_records == 4 and not m.is_initial_load and m.last_sync_time is not None
+    before = m.last_sync_time
+    E.append(emp(5, good)); E[-1]["lastUpdated"] = datetime(2999, 1, 1)
+    E.append(emp(6, np.ones(3, np.float32))); E[-1]["lastUpdated"] = datetime(2999, 1, 1)
+    m.force_sync()
+    assert "%024x" % 5 in st.ids_ and "%024x" % 6 not in st.ids_
+    assert m.last_sync_time >= before and m.rejected_records == 5
+
+
+def test_failed_compaction_is_logged_backed_off_and_the_sync_goes_on():
+    from datetime import datetime
+    from facerecognition_infrenceengine_b200.manager import EmbeddingManager, ListSource
+
+    def emp(i, status="active"):
+        return {"_id": "%024x" % i, "embedding": np.ones(8, np.float32), "companyId": "c", "status": status,
+                "blacklisted": False, "lastUpdated": datetime(2026, 1, 1)}
+
+    E = [emp(i) for i in range(4000)]
+    st = _counting_store(fail_compact=True)
+    m = EmbeddingManager(ListSource(E, []), mode="live", store=st)
+    for e in E[:2000]:
+        e["status"] = "inactive"
+    E.append(dict(emp(9000), lastUpdated=datetime(2999, 1, 1)))
+    m.force_sync()                                   # eviction -> compaction fails inside: must not abort the cycle
+    assert st.compactions == 1 and st.live == 2001 and "%024x" % 9000 in st.ids_
+    t = m.last_sync_time
+    m.force_sync()                                   # not retried every cycle
+    assert st.compactions == 1 and m.last_sync_time >= t
+
+
+def test_layout_lock_orders_compaction_against_read_sections():
+    """gallery._LayoutLock: read sections run together and nest; a writer waits for them and holds new ones off."""
+    import threading
+    import time
+    from facerecognition_infrenceengine_b200.gallery import _LayoutLock
+    lk = _LayoutLock()
+    log, in_read, go = [], threading.Event(), threading.Event()
+
+    def reader():
+        with lk.read():
+            with lk.read():                          # nested (Matcher.match inside a processor's section)
+                in_read.set()
+                go.wait(5)
+                log.append("read-done")
+
+    def writer():
+        with lk.write():
+            log.append("write")
+
+    def late_reader():
+        with lk.read():
+            log.append("late-read")
+
+    tr = threading.Thread(target=reader); tr.start()
+    assert in_read.wait(5)
+    tw = threading.Thread(target=writer); tw.start()
+    time.sleep(0.1)
+    tl = threading.Thread(target=late_reader); tl.start()      # arrives while the writer waits: queues behind it
+    time.sleep(0.1)
+    assert log == []
+    go.set()
+    for t in (tr, tw, tl):
+        t.join(5)
+    assert log == ["read-done", "write", "late-read"]
+    with lk.read():
+        try:
+            with lk.write():
+                raise AssertionError("write inside read must be refused")
+        except RuntimeError:
+            pass
