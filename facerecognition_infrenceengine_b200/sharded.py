@@ -375,6 +375,12 @@ class ShardedMatcher:
             self._x = None
             N.check(rc)
 
+    def reset_exchange(self):
+        """Collective: drop the exchange buffer on every rank; the next ``match`` allocates and zeroes a fresh one
+        (epochs restart at 1).  The way back after ``check_exchange`` raised on ANY rank."""
+        self._x = None
+        self._epoch = 0
+
     # ---- CUDA pieces ------------------------------------------------------------------------------
     def _local_cuda(self, Q, k, threshold, variant, rows_out, scores_out, tenant=-1):
         acc = self._accept_scratch(Q)

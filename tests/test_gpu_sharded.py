@@ -248,6 +248,42 @@ _manager_scenario(frg, g3, ShardedMatcher(g3),
                   gm, rank=dist.get_rank())
 if dist.get_rank() == 0:
     print("MANAGER_OK world=%%d" %% dist.get_world_size())
+# soak: 200 collective calls with random per-rank HOST jitter (the ranks enqueue at different times, sometimes
+# 50 ms apart) - p2p against NCCL every time.  Then the round-1 scaling crash on purpose: rank 1 skips a call.
+import random, time
+rnd = random.Random(1000 + dist.get_rank())
+shapes = random.Random(7)
+Qs = torch.from_numpy(synth.queries(320, n, d, seed=99)[0]).cuda()
+for it in range(200):
+    ff, kk = shapes.randint(1, 320), shapes.choice([1, 5, 10, 16])
+    time.sleep(rnd.random() * (0.05 if rnd.random() < 0.05 else 0.002))
+    a = m_p2p.match(Qs[:ff], kk, 0.45)
+    if it %% 10 == 0:
+        b = m_nccl.match(Qs[:ff], kk, 0.45)
+        torch.cuda.synchronize()
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), (it, ff, kk)
+torch.cuda.synchronize()
+m_p2p.check_exchange()
+dist.barrier()
+if dist.get_rank() == 0:
+    a = m_p2p.match(Qs[:32], 5, 0.45)              # rank 1 does not take part: bounded wait, status, no trap
+    t0 = time.perf_counter()
+    try:
+        m_p2p.check_exchange()
+        raise SystemExit("a missing rank went unnoticed")
+    except frg.NativeError as ex:
+        assert ex.code == frg._native.ERR_STATE and "rank 1 never announced" in str(ex), str(ex)
+    assert time.perf_counter() - t0 < 10 and (a[0] == -1).all()
+dist.barrier()
+m_p2p.reset_exchange()                             # collective recovery: fresh buffer, epochs restart
+a = m_p2p.match(Qd, 5, 0.45); b = m_nccl.match(Qd, 5, 0.45)
+torch.cuda.synchronize()
+m_p2p.check_exchange()
+for x, y in zip(a, b):
+    assert torch.equal(x, y)
+if dist.get_rank() == 0:
+    print("SOAK_OK world=%%d" %% dist.get_world_size())
 # every rank holds the same merged result
 chk = a[0].clone()
 dist.broadcast(chk, src=0)
@@ -266,9 +302,11 @@ def test_sharded_two_ranks_nccl(tmp_path):
     script.write_text(WORKER % (ROOT, ROOT, ROOT))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, FRG_EXCHANGE_TIMEOUT_MS="500"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK world=2" in r.stdout
     assert "P2P_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ENROL_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MANAGER_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SOAK_OK world=2" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
