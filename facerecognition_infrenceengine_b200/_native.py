@@ -35,7 +35,7 @@ class NativeError(RuntimeError):
 class StoreStats(C.Structure):
     _fields_ = [("rows", C.c_int64), ("live", C.c_int64), ("capacity", C.c_int64),
                 ("version", C.c_int64), ("bytes", C.c_int64), ("dim", C.c_int32),
-                ("device", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("device", C.c_int32), ("flags", C.c_uint32), ("faults", C.c_uint32)]
 
 
 class MatchParams(C.Structure):

@@ -110,6 +110,15 @@ int store_begin_read(frg_store* s, cudaStream_t stream) {
   return FRG_OK;
 }
 
+// after a stream synchronisation: has a kernel of this store reported a broken pipeline?
+static int store_fault(const frg_store* s) {
+  const uint32_t f = s->fault_host ? *static_cast<volatile uint32_t*>(s->fault_host) : 0u;
+  if (!f) return FRG_OK;
+  set_error("a tensor-core pipeline barrier of this store's match kernels timed out (code %u): results since are "
+            "void; destroy the store and create it again", f);
+  return FRG_ERR_CUDA;
+}
+
 static bool has_master(const frg_store* s) { return !(s->flags & FRG_STORE_BF16_ONLY); }
 static bool has_plane(const frg_store* s) { return (s->flags & (FRG_STORE_BF16_PLANE | FRG_STORE_BF16_ONLY)) != 0; }
 
@@ -204,7 +213,7 @@ static void extents_note_upsert(frg_store* s, const int64_t* hrows, const int32_
 // tenant's rows can sit in (FRG_TENANT_WINDOW=0 turns the window off)
 static GalleryWindow window_of(const frg_store* s, int32_t tenant) {
   GalleryWindow w;
-  w.master = s->master; w.plane = s->plane; w.tags = s->tags; w.gmax_bits = s->gmax_bits;
+  w.master = s->master; w.plane = s->plane; w.tags = s->tags; w.gmax_bits = s->gmax_bits; w.fault = s->fault_dev;
   w.rows = s->rows; w.row0 = 0; w.dim = s->dim; w.plane_dim = s->plane_dim; w.flags = s->flags;
   w.maybe_dead = s->maybe_dead;
   static const bool on = []() { const char* e = getenv("FRG_TENANT_WINDOW"); return !e || atoi(e) != 0; }();
@@ -304,6 +313,18 @@ int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t fla
       rc = cuda_fail(eg, "cudaMalloc(gmax)", __FILE__, __LINE__);
     }
   }
+  if (rc == FRG_OK) {
+    cudaError_t ef = cudaHostAlloc(reinterpret_cast<void**>(&s->fault_host), sizeof(uint32_t), cudaHostAllocMapped);
+    if (ef == cudaSuccess) {
+      *s->fault_host = 0;
+      ef = cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->fault_dev), s->fault_host, 0);
+    }
+    if (ef != cudaSuccess) {
+      cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
+      if (s->fault_host) cudaFreeHost(s->fault_host);
+      rc = cuda_fail(ef, "cudaHostAlloc(fault word)", __FILE__, __LINE__);
+    }
+  }
   if (rc != FRG_OK) { delete s; return rc; }
   s->capacity = capacity > 0 ? capacity : 1;
   cudaError_t e = cudaEventCreateWithFlags(&s->last_write, cudaEventDisableTiming);
@@ -324,6 +345,7 @@ int frg_store_destroy(frg_store* s) {
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();
     cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
+    if (s->fault_host) cudaFreeHost(s->fault_host);
     if (s->last_write) cudaEventDestroy(s->last_write);
   }
   delete s;
@@ -346,6 +368,7 @@ int frg_store_stats(frg_store* s, frg_store_stats_t* out) {
   out->rows = s->rows; out->live = s->live; out->capacity = s->capacity; out->version = s->version;
   out->bytes = int64_t(row_bytes(s)) * s->capacity;
   out->dim = s->dim; out->device = s->device; out->flags = s->flags;
+  out->faults = s->fault_host ? *s->fault_host : 0u;
   return FRG_OK;
 }
 
@@ -911,6 +934,7 @@ int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const fr
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     }
     if (e != cudaSuccess) rc = cuda_fail(e, "D2H results", __FILE__, __LINE__);
+    else rc = store_fault(s);
   }
   cudaFreeAsync(d, st);
   return rc;

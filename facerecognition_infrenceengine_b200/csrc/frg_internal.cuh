@@ -124,6 +124,11 @@ struct frg_store {
   uint32_t* gmax_bits = nullptr;      // device uint32[2], float bits: [0] max ||g||^2 ever ingested (raw stores with a
                                       // Euclidean plane), [1] max ||g - bf16(g)||^2 (any store with a plane)
   int32_t* tags = nullptr;            // [capacity]
+  // Fault word in pinned, device-mapped host memory: a kernel whose TMA / MMA pipeline barrier timed out sets it
+  // instead of trapping (a trap would kill the CUDA context of the whole service).  Sticky; reported by
+  // frg_store_stats (faults) and by every *_host call as FRG_ERR_CUDA.
+  uint32_t* fault_host = nullptr;
+  uint32_t* fault_dev = nullptr;
   std::mutex mu;                      // guards the fields above and the stream bookkeeping
   cudaEvent_t last_write = nullptr;   // recorded after every mutation
   bool has_write = false;
@@ -144,6 +149,7 @@ struct GalleryWindow {
   const __nv_bfloat16* plane = nullptr;
   const int32_t* tags = nullptr;
   uint32_t* gmax_bits = nullptr;
+  uint32_t* fault = nullptr;          // frg_store::fault_dev
   int64_t rows = 0;       // rows in the window
   int64_t row0 = 0;       // store row of the window's first row (added to every returned row)
   int dim = 0, plane_dim = 0;

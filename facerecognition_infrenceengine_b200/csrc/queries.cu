@@ -13,6 +13,10 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
                          float* __restrict__ qn, __nv_bfloat16* __restrict__ qb,
                          uint32_t* __restrict__ group_keys, int* __restrict__ cand_total,
                          int* __restrict__ n_flagged, float* __restrict__ eps, const uint32_t* __restrict__ bounds) {
+  // launched with the programmatic-serialization attribute: the launch overlaps the tail of whatever kernel
+  // precedes it in the stream (the previous match of a back-to-back caller); nothing is read or written before
+  // that kernel has completed
+  pdl_wait();
   pdl_trigger();          // the next kernel of the match may be scheduled now (it waits before reading)
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -80,6 +84,7 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
                               float* __restrict__ qn, __nv_bfloat16* __restrict__ q_aug, float* __restrict__ eps,
                               uint32_t* __restrict__ group_keys, uint32_t none_key, int* __restrict__ cand_total,
                               int* __restrict__ n_flagged) {
+  pdl_wait();
   pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -135,8 +140,8 @@ int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_
   const float none = kEuclidNone;
   memcpy(&none_bits, &none, sizeof(none_bits));
   const uint32_t none_key = ~none_bits;        // float_key() of a negative value: all bits complemented
-  prepare_queries_euclid_kernel<<<(nq + 3) / 4, 128, 0, st>>>(q, nq, dim, gmax_bits, qn, q_aug, eps, group_keys,
-                                                               none_key, cand_total, n_flagged);
+  FRG_CUDA(launch_kernel(prepare_queries_euclid_kernel, dim3((nq + 3) / 4), dim3(128), 0, st, true, q, nq, dim, gmax_bits,
+                         qn, q_aug, eps, group_keys, none_key, cand_total, n_flagged));
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;
@@ -149,8 +154,8 @@ int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, fl
   const int warps_per_block = 4;
   // same smem/L1 split as the tensor-core kernels that follow: no carve-out switch between launches
   FRG_CUDA(func_attr_once(normalise_queries_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  normalise_queries_kernel<<<(nq + warps_per_block - 1) / warps_per_block, 128, 0, st>>>(
-      q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, cand_total, n_flagged, eps, bounds);
+  FRG_CUDA(launch_kernel(normalise_queries_kernel, dim3((nq + warps_per_block - 1) / warps_per_block), dim3(128), 0, st,
+                         true, q, nq, dim, normalise ? 1 : 0, qn, qn_bf16, group_keys, cand_total, n_flagged, eps, bounds));
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;

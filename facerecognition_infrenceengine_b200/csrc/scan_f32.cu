@@ -106,12 +106,16 @@ __device__ __forceinline__ void list_insert(float* sc, int32_t* ix, int K, float
 
 // One pass over the gallery for the queries q_of[0..nq_pass): fills part_[sc|ix][(block*part_stride + part_q0 + b)*K ..].
 // ROW = float: fp32 master rows.  ROW = __nv_bfloat16: rows of the bf16 scan plane, widened exactly.
-template <int NJ, int QB, int METRIC, typename ROW = float>
+// SPARSE: few rows of the window can take part (a tenant whose row window was stretched by one late
+// re-enrolment; a gallery full of tombstones).  Tags are read FIRST - 32 per warp and step, one coalesced load,
+// the next step's prefetched - and only the rows that can match are fetched at all: a 10 000-row company inside
+// a 1 M-row window costs 4 MB of tags + 20 MB of rows per pass instead of 2 GB.
+template <int NJ, int QB, int METRIC, typename ROW = float, bool SPARSE = false>
 __device__ __forceinline__ void scan_pass(const ROW* __restrict__ master, const int32_t* __restrict__ tags,
                                           int64_t rows, const float* __restrict__ qn, const int (&q_of)[QB],
                                           int nq_pass, int part_stride, int part_q0, int K, int32_t tenant,
                                           float* __restrict__ part_sc, int32_t* __restrict__ part_ix,
-                                          float* l_sc, int32_t* l_ix) {
+                                          float* l_sc, int32_t* l_ix, const int32_t* w_list = nullptr, int w_n = -1) {
   constexpr int DIM = NJ * 128;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -140,10 +144,68 @@ __device__ __forceinline__ void scan_pass(const ROW* __restrict__ master, const 
   const int64_t gw = int64_t(blockIdx.x) * kScanWarps + warp;
   const int64_t tw = int64_t(gridDim.x) * kScanWarps;
 
+  auto load_row = [&](int64_t r, float4 (&g)[NJ]) {
+    if constexpr (sizeof(ROW) == 4) {
+      const float4* pr = reinterpret_cast<const float4*>(master + r * DIM) + lane;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) g[j] = ldg_stream(pr + j * 32);
+    } else {
+      const uint2* pr = reinterpret_cast<const uint2*>(master + r * DIM) + lane;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) g[j] = ldg_stream_bf16(pr + j * 32);
+    }
+  };
+  auto consume = [&](const float4 (&g)[NJ], int64_t r) {
+    float a[QB];
+    row_dots<NJ, QB, METRIC>(g, q, a);
+    float sdot = butterfly<QB>(a, lane);
+    if (METRIC == FRG_METRIC_EUCLIDEAN) sdot = -sdot;
+    const bool ins = sdot > kth;                     // false for NaN
+    if (__any_sync(0xffffffffu, ins)) {
+      if (ins && rep) list_insert(my_sc, my_ix, K, sdot, int32_t(r));
+      __syncwarp();
+      kth = my_sc[K - 1];
+    }
+  };
+  if (SPARSE && w_n >= 0) {
+    // this warp's valid rows were listed once for the whole kernel (sparse_row_list): two in flight
+    for (int i = 0; i < w_n; i += 2) {
+      const bool two = i + 1 < w_n;
+      const int64_t r0 = w_list[i], r1 = two ? w_list[i + 1] : r0;
+      float4 g0[NJ], g1[NJ];
+      load_row(r0, g0);
+      if (two) load_row(r1, g1);
+      consume(g0, r0);
+      if (two) consume(g1, r1);
+    }
+  } else if constexpr (SPARSE) {
+    const int64_t nblk = (rows + 31) >> 5;
+    auto tag_of = [&](int64_t b) {
+      const int64_t r = b * 32 + lane;
+      return (b < nblk && r < rows) ? __ldg(tags + r) : int32_t(-1);
+    };
+    int32_t tg_next = tag_of(gw);
+    for (int64_t b = gw; b < nblk; b += tw) {
+      const int32_t tg = tg_next;
+      tg_next = tag_of(b + tw);
+      unsigned vm = __ballot_sync(0xffffffffu, tg >= 0 && (tenant < 0 || tg == tenant));
+      while (vm) {                                   // valid rows of the block, in row order, two in flight
+        const int j0 = __ffs(vm) - 1;
+        vm &= vm - 1;
+        const int j1 = vm ? __ffs(vm) - 1 : -1;
+        if (j1 >= 0) vm &= vm - 1;
+        float4 g0[NJ], g1[NJ];
+        load_row(b * 32 + j0, g0);
+        if (j1 >= 0) load_row(b * 32 + j1, g1);
+        consume(g0, b * 32 + j0);
+        if (j1 >= 0) consume(g1, b * 32 + j1);
+      }
+    }
+  }
   // R rows in flight per warp (R * NJ 16-byte loads per lane): enough bytes in flight per SM to
   // cover the HBM latency even for short rows
   constexpr int R = NJ >= 4 ? 2 : (NJ == 2 ? 4 : 8);
-  for (int64_t rb = gw; rb < rows; rb += int64_t(R) * tw) {
+  for (int64_t rb = SPARSE ? rows : gw; rb < rows; rb += int64_t(R) * tw) {
     float4 g[R][NJ];
     int32_t tg[R];
 #pragma unroll
@@ -220,11 +282,42 @@ scan_f32_kernel(const float* __restrict__ master, const int32_t* __restrict__ ta
                             l_sc, l_ix);
 }
 
+// SPARSE fallback: the rows that can take part are the same for every pass of the kernel - each warp lists ITS
+// valid rows once (tags read 32 at a time, ascending), up to kSparseCap; a warp with more keeps sweeping the tags
+// in every pass (returns -1).
+constexpr int kSparseCap = 96;
+__device__ __forceinline__ int sparse_row_list(const int32_t* __restrict__ tags, int64_t rows, int32_t tenant,
+                                               int32_t* list) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = int64_t(blockIdx.x) * kScanWarps + (threadIdx.x >> 5);
+  const int64_t tw = int64_t(gridDim.x) * kScanWarps;
+  const int64_t nblk = (rows + 31) >> 5;
+  int n = 0;
+  for (int64_t b0 = gw; b0 < nblk; b0 += 4 * tw) {           // four independent tag loads per round
+    int32_t tg[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = (b0 + u * tw) * 32 + lane;
+      tg[u] = (b0 + u * tw < nblk && r < rows) ? __ldg(tags + r) : int32_t(-1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = tg[u] >= 0 && (tenant < 0 || tg[u] == tenant);
+      const unsigned vm = __ballot_sync(0xffffffffu, ok);
+      const int pos = n + __popc(vm & ((1u << lane) - 1u));
+      if (ok && pos < kSparseCap) list[pos] = int32_t((b0 + u * tw) * 32 + lane);
+      n += __popc(vm);
+    }
+  }
+  __syncwarp();
+  return n <= kSparseCap ? n : -1;
+}
+
 // Exact re-do of the queries a tensor-core pass could not settle (candidate overflow).  The list
 // and its length live on the device; the kernel loops over it, so nothing waits for the host, and
 // the CTA that finishes last folds the per-CTA lists into the final results (ticket counter), so an
 // empty list costs ONE idle launch.  ctl[0] = number of flagged queries, ctl[1] = ticket (starts 0).
-template <int NJ, int QB, int METRIC, int KMAX, typename ROW>
+template <int NJ, int QB, int METRIC, int KMAX, typename ROW, bool SPARSE>
 __global__ void __launch_bounds__(kScanWarps * 32, 2)
 scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restrict__ tags, int64_t rows,
                         const float* __restrict__ qn, int nq_total, const int* __restrict__ flagged,
@@ -236,16 +329,20 @@ scan_f32_flagged_kernel(const ROW* __restrict__ master, const int32_t* __restric
   float* l_sc = reinterpret_cast<float*>(smem_raw);
   int32_t* l_ix = reinterpret_cast<int32_t*>(l_sc + kScanWarps * QB * K);
   __shared__ int is_last;
+  __shared__ int32_t s_list[SPARSE ? kScanWarps : 1][SPARSE ? kSparseCap : 1];
   pdl_wait();             // the select kernel's list of flagged queries
   pdl_trigger();
   const int nf = ctl[0];
+  int w_n = -1;
+  const int32_t* w_list = s_list[SPARSE ? (threadIdx.x >> 5) : 0];
+  if (SPARSE && nf > 0) w_n = sparse_row_list(tags, rows, tenant, s_list[SPARSE ? (threadIdx.x >> 5) : 0]);
   for (int q0 = 0; q0 < nf; q0 += QB) {
     const int nq_pass = nf - q0 < QB ? nf - q0 : QB;
     int q_of[QB];
 #pragma unroll
     for (int b = 0; b < QB; ++b) q_of[b] = b < nq_pass ? flagged[q0 + b] : 0;
-    scan_pass<NJ, QB, METRIC, ROW>(master, tags, rows, qn, q_of, nq_pass, nq_total, q0, K, tenant, part_sc,
-                                   part_ix, l_sc, l_ix);
+    scan_pass<NJ, QB, METRIC, ROW, SPARSE>(master, tags, rows, qn, q_of, nq_pass, nq_total, q0, K, tenant, part_sc,
+                                           part_ix, l_sc, l_ix, w_list, w_n);
     __syncthreads();
   }
   if (nf == 0) return;
@@ -363,21 +460,29 @@ static int launch_flagged_k(const ScanArgs& a, int grid, const int* flagged, int
                             int64_t row_offset, float* ps, int32_t* pi, const XPush& push, int64_t* out_rows,
                             float* out_scores, uint8_t* out_accept, cudaStream_t st) {
   const size_t smem = size_t(kScanWarps) * QB * a.k * (sizeof(float) + sizeof(int32_t));
-  if (a.master && a.metric == FRG_METRIC_EUCLIDEAN) {
-    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_EUCLIDEAN, KMAX, float>;
+  // a tenant-filtered call whose queries overflowed: the tenant's rows are concentrated inside a wide window
+  //  - read the tags first and fetch only that tenant's rows
+  if (a.master && a.metric == FRG_METRIC_COSINE && a.tenant >= 0) {
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float, true>;
+    FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
+                           a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
+                           out_accept, push));
+  } else if (a.master && a.metric == FRG_METRIC_EUCLIDEAN) {
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_EUCLIDEAN, KMAX, float, false>;
     FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
                            a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
                            out_accept, push));
   } else if (a.master) {
-    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float>;
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, float, false>;
     FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.master, a.tags, a.rows, a.qn,
                            a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,
                            out_accept, push));
   } else {
     // bf16-only store: the exact re-do reads the scan plane (fp32 query x bf16 row, fp32 accumulation)
-    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, __nv_bfloat16>;
+    auto kern = scan_f32_flagged_kernel<NJ, QB, FRG_METRIC_COSINE, KMAX, __nv_bfloat16, false>;
     FRG_CUDA(func_attr_once(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     FRG_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanWarps * 32), smem, st, true, a.plane, a.tags, a.rows, a.qn,
                            a.nq, flagged, ctl, a.k, a.tenant, threshold, row_offset, ps, pi, out_rows, out_scores,

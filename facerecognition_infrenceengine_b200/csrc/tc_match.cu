@@ -65,11 +65,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// A broken pipeline must abort the kernel, not hang the GPU: bounded spin, then trap.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// A broken pipeline must neither hang the GPU nor kill the CUDA context of a long-running service (a trap
+// would): bounded spin, then the CTA's abort flag is raised.  Every role loop leaves at its next iteration, the
+// CTA tears down normally, the store's fault word is set (frg_store_stats / the *_host calls report it as a
+// status code) and the results of that call are void.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 1023u) == 0u) {
+      if (*abort_flag) return;
+      if (spins > (1u << 24)) { *abort_flag = 1; return; }
+    }
   }
 }
 // one lane of a converged warp (PTX elect.sync): lets the rest of the warp stay on the uniform datapath
@@ -265,6 +271,7 @@ struct TcScanParams {
   // box 16 x 128 rows, 32B swizzle, 4 KB per stage) with ONE K = 16 MMA instead of four
   int pad;
   int stages;              // depth of the TMA ring (tc_stages)
+  uint32_t* fault;         // the store's fault word (host-mapped): set when a pipeline barrier timed out
 };
 
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
@@ -304,6 +311,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   // landed, not all 128 KB
   auto bar_q = [&](int kb) { return bar0 + 8u * (2 * kMaxStages + 4 + kb); };
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + kMaxKBlocks);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_holder + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -324,6 +332,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   auto tile_of = [&](int it) { return it < n_tiles ? tile_begin + it : tile_begin + (it - n_tiles); };
 
   if (threadIdx.x == 0) {
+    *abort_flag = 0;
     for (int s = 0; s < nstages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), PAIR ? 2 * kEpiWarps : kEpiWarps); }
     for (int kb = 0; kb < kblocks; ++kb) mbar_init(bar_q(kb), 1);
@@ -352,7 +361,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       const uint64_t g_hint = gridDim.x > (PAIR ? 2 : 1) ? kEvictLast : kEvictFirst;
       constexpr uint32_t kQBlockBytes = kTileQ * kBlockK * 2;
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < n_iter; ++it) {
+      for (int it = 0; it < n_iter && !*abort_flag; ++it) {
         const int t = tile_of(it);
         const int row0 = t * p.tile_scale * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -366,7 +375,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
               tma_load_2d(q_smem + kb * kQBlockBytes, &q_map, bar_q(kb), kb * kBlockK, qtile * kTileQ, kEvictLast);
             }
           }
-          mbar_wait(bar_empty(stage), phase ^ 1);
+          mbar_wait(bar_empty(stage), phase ^ 1, abort_flag);
           const bool padkb = p.pad && kb == kblocks - 1;
           const CUtensorMap* map = padkb ? &pad_map : &g_map;
           const uint32_t bytes = padkb ? kPadStageBytes : kStageBytes;
@@ -394,13 +403,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       const uint64_t a_base = umma_desc_sw128(q_smem);
       const uint64_t b_base = umma_desc_sw128(stage_smem);
       const uint64_t pad_base = umma_desc_sw32(stage_smem);
-      for (int it = 0; it < n_iter; ++it) {
-        mbar_wait(bar_tempty(buf), tphase ^ 1);
+      for (int it = 0; it < n_iter && !*abort_flag; ++it) {
+        mbar_wait(bar_tempty(buf), tphase ^ 1, abort_flag);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(buf * kAccN);
         for (int kb = 0; kb < kblocks; ++kb) {
-          if (it == 0) mbar_wait(bar_q(kb), 0);          // first tile: the query k-block must have landed
-          mbar_wait(bar_full(stage), phase);
+          if (it == 0) mbar_wait(bar_q(kb), 0, abort_flag);          // first tile: the query k-block must have landed
+          mbar_wait(bar_full(stage), phase, abort_flag);
           tc_fence_after();
           // descriptor start-address field is (addr >> 4): a k-block of A is 16 KB, a stage of B 16 KB
           const uint64_t a0 = a_base + uint64_t(kb * ((kTileQ * kBlockK * 2) >> 4));
@@ -499,11 +508,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     }
 
     int buf = 0; uint32_t tphase = 0;
-    for (int it = 0; it < n_iter; ++it) {
+    for (int it = 0; it < n_iter && !*abort_flag; ++it) {
       const int t = tile_of(it);
       const bool probe = MODE == kModeGroupMax || (MODE == kModeFused && it < n_probe);
       if (idle) {
-        mbar_wait(bar_tfull(buf), tphase);
+        mbar_wait(bar_tfull(buf), tphase, abort_flag);
         if (lane == 0) {
           if (PAIR) mbar_arrive_remote(bar_tempty(buf), 0);
           else mbar_arrive(bar_tempty(buf));
@@ -523,7 +532,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
         }
         vmask[b] = __ballot_sync(0xffffffffu, ok);
       }
-      mbar_wait(bar_tfull(buf), tphase);
+      mbar_wait(bar_tfull(buf), tphase, abort_flag);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) +
                              uint32_t(buf * kAccN + half * kBlocksPerWarp * 32);
@@ -628,6 +637,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   tc_fence_before();
   if (PAIR) cluster_sync_all();        // the leader's MMAs read the peer's shared memory until the very end
   else __syncthreads();
+  if (threadIdx.x == 0 && *abort_flag && p.fault)      // zero-copy word in pinned host memory: only ever written here
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.fault), "r"(uint32_t(1 + MODE)) : "memory");
   if (warp == 1) {
     __syncwarp();
     if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
@@ -1104,6 +1115,7 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
   else pm = gm_full;                                                          // never dereferenced (p.pad == 0)
 
   TcScanParams p{};
+  p.fault = s->fault;
   p.eps = eps; p.none_score = euclid ? kEuclidNone : kNoScore; p.pad = euclid ? 1 : 0; p.stages = tc_stages(kdim);
   p.dim = kdim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   p.n_rows = int(s->rows); p.group_key = keys; p.k = k;

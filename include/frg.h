@@ -82,7 +82,9 @@ typedef struct frg_store_stats_t {
   int32_t dim;
   int32_t device;
   uint32_t flags;
-  uint32_t reserved;
+  uint32_t faults;     /* != 0: a match kernel's internal pipeline barrier timed out (never a trap: the context
+                          stays usable); sticky - results since are void, recreate the store.  The *_host entry
+                          points return FRG_ERR_CUDA once it is set. */
 } frg_store_stats_t;
 
 typedef struct frg_match_params_t {

@@ -217,3 +217,33 @@ def test_threads_match_while_the_gallery_is_compacted(frg):
     with pytest.raises(frg.StaleRows):
         store.ids_of(r.rows, layout_version=r.layout_version)
     store.close()
+
+
+def test_stretched_tenant_window_takes_the_sparse_fallback(frg):
+    """A company enrolled as one block, then ONE person re-enrolled at the end of the gallery: the company's row
+    window now spans almost everything while its rows stay concentrated in one CTA's chunk, whose private
+    candidate segments overflow.  Those queries are redone exactly by the tag-first
+    ("sparse") fallback scan, which fetches only the company's rows.  Results against the oracle's masked scan;
+    F = 64 (single-CTA kernels) and F = 300 (CTA pairs)."""
+    n, d, T = 400_000, 512, 8_000
+    G = synth.gallery(n, d, 41)
+    tags = (1 + np.arange(n) // T).astype(np.int32)
+    tenant = 7
+    lo = (tenant - 1) * T
+    tags[n - 1] = tenant                                 # the late re-enrolment
+    store = frg.GalleryStore(dim=d, capacity=n)
+    store.append_rows(G, tags, prenormalised=True)
+    store._tenants = {"c%d" % i: i for i in range(1, n // T + 2)}
+    rng = np.random.default_rng(3)
+    m = frg.Matcher(store)
+    for F in (64, 300):
+        pick = rng.integers(lo, lo + T, size=F)
+        pick[0] = n - 1
+        Q = G[pick] + np.float32(0.03) * rng.standard_normal((F, d)).astype(np.float32)
+        Q[F // 2:] = rng.standard_normal((F - F // 2, d)).astype(np.float32)
+        ref = mo.match_topk_fast(Q, G, 6, 0.4, tags, tenant)
+        r = m.match(Q, 5, 0.4, company_id="c%d" % tenant, with_ids=False)
+        compare(r.rows, r.scores, r.accept, ref, 5, 0.4)
+        assert r.rows[0, 0] == n - 1
+        assert r.launches >= 5
+    store.close()
