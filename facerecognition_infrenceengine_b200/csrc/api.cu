@@ -189,8 +189,40 @@ static void extent_add(frg_store* s, int32_t tag, int64_t lo, int64_t hi) {
   if (hi > it->second.hi) it->second.hi = hi;
 }
 
+// interval [lo, hi) of tag -> its span set (merged with what it touches)
+static void span_add(frg_store* s, int32_t tag, int64_t lo, int64_t hi) {
+  if (tag < 0 || hi <= lo) return;
+  frg_store::Spans& sp = s->spans[tag];
+  if (sp.scattered) return;
+  auto it = sp.iv.upper_bound(lo);
+  if (it != sp.iv.begin()) {
+    auto pv = std::prev(it);
+    if (pv->second >= lo) { lo = pv->first; if (pv->second > hi) hi = pv->second; sp.covered -= pv->second - pv->first; it = sp.iv.erase(pv); }
+  }
+  while (it != sp.iv.end() && it->first <= hi) {
+    if (it->second > hi) hi = it->second;
+    sp.covered -= it->second - it->first;
+    it = sp.iv.erase(it);
+  }
+  sp.iv.emplace(lo, hi);
+  sp.covered += hi - lo;
+  if (sp.iv.size() > frg_store::kMaxSpans) { sp.scattered = true; sp.iv.clear(); }
+}
+
 // rows / tags are HOST arrays (or null: append at `base` / tag 0)
 static void extents_note_upsert(frg_store* s, const int64_t* hrows, const int32_t* htags, int64_t n, int64_t base) {
+  {
+    // exact runs of consecutive rows with one tag -> span intervals
+    int64_t i = 0;
+    while (i < n) {
+      const int32_t tag = htags ? htags[i] : 0;
+      const int64_t lo = hrows ? hrows[i] : base + i;
+      int64_t j = i + 1;
+      while (j < n && (htags ? htags[j] : 0) == tag && (hrows ? hrows[j] : base + j) == lo + (j - i)) ++j;
+      span_add(s, tag, lo, lo + (j - i));
+      i = j;
+    }
+  }
   if (!htags && !hrows) { extent_add(s, 0, base, base + n); return; }
   // runs of equal tags over consecutive rows (bulk loads) cost one map update each
   int64_t i = 0;
@@ -211,7 +243,7 @@ static void extents_note_upsert(frg_store* s, const int64_t* hrows, const int32_
 
 // the whole gallery, or - for a tenant-filtered call whose tag extents are known - only the row window that
 // tenant's rows can sit in (FRG_TENANT_WINDOW=0 turns the window off)
-static GalleryWindow window_of(const frg_store* s, int32_t tenant) {
+static GalleryWindow window_of(const frg_store* s, int32_t tenant, bool for_tc = false) {
   GalleryWindow w;
   w.master = s->master; w.plane = s->plane; w.tags = s->tags; w.gmax_bits = s->gmax_bits; w.fault = s->fault_dev;
   w.rows = s->rows; w.row0 = 0; w.dim = s->dim; w.plane_dim = s->plane_dim; w.flags = s->flags;
@@ -222,12 +254,68 @@ static GalleryWindow window_of(const frg_store* s, int32_t tenant) {
     auto it = s->extents.find(tenant);
     if (it != s->extents.end()) { lo = it->second.lo; hi = it->second.hi < s->rows ? it->second.hi : s->rows; }
     if (hi < lo) hi = lo;
+    // A window that is mostly other tenants' rows (a company's block + one person re-enrolled at the far end):
+    // keep the WHOLE store as the window and let the tensor-core kernels walk only the tiles of the tenant's
+    // intervals.  (The exact scan and first_match still take the bounding window.)
+    static const bool lists_on = []() { const char* e = getenv("FRG_TILE_LIST"); return !e || atoi(e) != 0; }();
+    auto sp = s->spans.find(tenant);
+    if (lists_on && for_tc && sp != s->spans.end() && !sp->second.scattered && hi - lo >= 32768 &&
+        sp->second.covered * 4 <= hi - lo) {
+      w.owner = const_cast<frg_store*>(s);
+      w.want_tile_list = true;
+      w.list_tenant = tenant;
+      return w;                             // row0 = 0, rows = s->rows: tile indices are absolute
+    }
     w.row0 = lo; w.rows = hi - lo;
     if (w.master) w.master += lo * s->dim;
     if (w.plane) w.plane += lo * s->plane_dim;
     w.tags += lo;
   }
   return w;
+}
+
+int store_tile_list(frg_store* s, int32_t tenant, int gran, cudaStream_t st, const int32_t** list, int* n) {
+  *list = nullptr; *n = 0;
+  auto sp = s->spans.find(tenant);
+  if (sp == s->spans.end() || sp->second.scattered || !s->extents_known) return FRG_OK;
+  frg_store::TileList& tl = s->tile_lists[std::make_pair(tenant, gran)];
+  if (tl.version != s->version) {
+    // rebuild: tiles touched by the intervals, ascending, clipped to the rows in use
+    std::vector<int32_t> tiles;
+    int64_t last = -1;
+    for (const auto& iv : sp->second.iv) {
+      const int64_t hi = iv.second < s->rows ? iv.second : s->rows;
+      if (hi <= iv.first) continue;
+      int64_t t0 = iv.first / gran;
+      const int64_t t1 = (hi - 1) / gran;
+      if (t0 <= last) t0 = last + 1;
+      for (int64_t t = t0; t <= t1; ++t) tiles.push_back(int32_t(t));
+      if (t1 > last) last = t1;
+    }
+    const int64_t all_tiles = (s->rows + gran - 1) / gran;
+    tl.version = s->version;
+    tl.n = int(tiles.size());
+    tl.use = !tiles.empty() && int64_t(tiles.size()) * 2 <= all_tiles;
+    if (tl.use) {
+      if (int64_t(tiles.size()) > tl.cap) {
+        // a bigger buffer; the old one may still be read by matches in flight: freed with the store
+        if (tl.dev) s->retired.push_back(tl.dev);
+        tl.cap = int64_t(tiles.size()) * 2 + 64;
+        tl.dev = nullptr;
+        FRG_CUDA(cudaMalloc(reinterpret_cast<void**>(&tl.dev), size_t(tl.cap) * sizeof(int32_t)));
+      }
+      if (!tl.ready) FRG_CUDA(cudaEventCreateWithFlags(&tl.ready, cudaEventDisableTiming));
+      // Overwriting in place is safe: this match was ordered (store_begin_read) after the mutation that bumped
+      // the version, and that mutation after every match that read the previous list.  Pageable source: the
+      // call returns once the vector has been staged.
+      FRG_CUDA(cudaMemcpyAsync(tl.dev, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      FRG_CUDA(cudaEventRecord(tl.ready, st));
+    }
+  }
+  if (!tl.use) return FRG_OK;
+  FRG_CUDA(cudaStreamWaitEvent(st, tl.ready, 0));        // another stream may have uploaded it
+  *list = tl.dev; *n = tl.n;
+  return FRG_OK;
 }
 
 }  // namespace frg
@@ -346,6 +434,8 @@ int frg_store_destroy(frg_store* s) {
     cudaDeviceSynchronize();
     cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags); cudaFree(s->gmax_bits);
     if (s->fault_host) cudaFreeHost(s->fault_host);
+    for (auto& kv : s->tile_lists) { cudaFree(kv.second.dev); if (kv.second.ready) cudaEventDestroy(kv.second.ready); }
+    for (void* p : s->retired) cudaFree(p);
     if (s->last_write) cudaEventDestroy(s->last_write);
   }
   delete s;
@@ -613,6 +703,14 @@ int frg_store_compact(frg_store* s, int64_t* old_to_new) {
   }
   s->extents.swap(fresh);
   s->extents_known = true;
+  s->spans.clear();
+  for (int64_t i = 0; i < m;) {                       // exact runs at the rows' new positions
+    const int32_t tag = t[size_t(src[size_t(i)])];
+    int64_t j = i + 1;
+    while (j < m && t[size_t(src[size_t(j)])] == tag) ++j;
+    span_add(s, tag, i, j);
+    i = j;
+  }
   s->live = m; s->maybe_dead = false;
   if (m != n) { s->rows = m; s->version++; }
   return FRG_OK;
@@ -653,6 +751,7 @@ int frg_store_fill_synthetic(frg_store* s, int64_t n, int64_t global_row0, uint6
   FRG_CHECK(launch_synth(n, s->rows, global_row0, seed, tag, s->dim, s->master, s->plane, s->plane_dim,
                          s->gmax_bits, s->tags, st));
   extent_add(s, tag, s->rows, s->rows + n);
+  span_add(s, tag, s->rows, s->rows + n);
   s->rows += n;
   if (s->live >= 0 && tag >= 0) s->live += n;
   if (tag < 0) s->maybe_dead = true;
@@ -749,7 +848,11 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
   const size_t qb_bytes = (size_t(nq) * (s->dim + (euclid ? kEuclidQPad : 0)) * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
   const size_t eps_bytes = (size_t(nq) * sizeof(float) + 255) & ~size_t(255);     // per-query filter error bound
-  const size_t tc_bytes = tc_workspace_bytes(s->rows, s->dim, nq, k, sm_count);
+  const int32_t* tile_list = nullptr;
+  int n_list = 0;
+  const int64_t plan_rows = tc_effective_rows(s, nq, st, &tile_list, &n_list);
+  if (plan_rows < 0) return FRG_ERR_CUDA;
+  const size_t tc_bytes = tc_workspace_bytes(plan_rows, s->dim, nq, k, sm_count);
   unsigned char* ws = nullptr;
   FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + eps_bytes + tc_bytes, st));
   float* qn = reinterpret_cast<float*>(ws);
@@ -758,7 +861,7 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
   unsigned char* tc_ws = ws + qn_bytes + qb_bytes + eps_bytes;
   int* flagged = nullptr; int* n_flagged = nullptr;
   uint32_t* keys = nullptr; int* ct0 = nullptr; int* nf0 = nullptr;
-  tc_workspace_init_targets(s->rows, s->dim, nq, k, sm_count, tc_ws, &keys, &ct0, &nf0);
+  tc_workspace_init_targets(plan_rows, s->dim, nq, k, sm_count, tc_ws, &keys, &ct0, &nf0);
   profile_begin(st, kStagePrep);
   int rc = euclid ? launch_prepare_queries_euclid(q, nq, s->dim, s->gmax_bits, qn, qb, eps, keys, ct0, nf0, st)
                   : launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, qb, keys, ct0,
@@ -767,7 +870,7 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
   if (rc == FRG_OK)
     rc = launch_tc_match(s, p->metric, qn, qb, eps, nq, k, p->tenant, rescore, p->threshold, p->row_offset, tc_ws,
                          sm_count, tail.active ? tail.x : XPush(), out_rows, out_scores, out_accept, &flagged,
-                         &n_flagged, st);
+                         &n_flagged, st, plan_rows, tile_list, n_list);
   if (rc == FRG_OK) {
     // queries whose candidate lists overflowed are redone exactly, inside the same enqueue
     ScanArgs a;
@@ -808,10 +911,11 @@ static int match_impl(frg_store* s, const float* q, int32_t nq, int32_t k, const
   FRG_CHECK(store_begin_read(s, st));
   struct SeqBump { ~SeqBump() { ++g_match_seq; } } bump;      // sampled profiling: every 4th match is bracketed
   // a tenant-filtered call scans only the rows that tenant can sit in (the whole gallery otherwise)
-  const GalleryWindow w = window_of(s, p->tenant);
+  const int variant = pick_variant(s, p, nq);
+  const GalleryWindow w = window_of(s, p->tenant, variant == FRG_VARIANT_TC_EXACT || variant == FRG_VARIANT_TC_BF16);
   frg_match_params_t pw = *p;
   pw.row_offset += w.row0;
-  switch (pick_variant(s, p, nq)) {
+  switch (variant) {
     case FRG_VARIANT_SCAN_F32:
       return match_scan(&w, q, nq, k, &pw, di.sm_count, out_rows, out_scores, out_accept, st, tail);
     case FRG_VARIANT_TC_EXACT:

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -140,6 +141,18 @@ struct frg_store {
   struct Extent { int64_t lo, hi; };
   std::unordered_map<int32_t, Extent> extents;
   bool extents_known = true;
+  // ... and, finer, the disjoint row intervals [lo, hi) of every tag (same provenance, same superset rule).  When
+  // a tenant's window is mostly other tenants' rows - one person re-enrolled at the end of the gallery stretches it
+  // over everything - the tensor-core kernels walk only the TILES these intervals touch (tile list, cached per
+  // store version and tile size).  A tag with more than kMaxSpans intervals (interleaved companies) is "scattered":
+  // no list, the masked scan of the window as before.
+  static constexpr size_t kMaxSpans = 4096;
+  struct Spans { std::map<int64_t, int64_t> iv; int64_t covered = 0; bool scattered = false; };
+  std::unordered_map<int32_t, Spans> spans;
+  struct TileList { int64_t version = -1; int32_t* dev = nullptr; int64_t cap = 0; int n = 0; bool use = false;
+                    cudaEvent_t ready = nullptr; };
+  std::map<std::pair<int32_t, int>, TileList> tile_lists;       // (tenant, rows per tile)
+  std::vector<void*> retired;                                   // outgrown list buffers, freed with the store
 };
 
 namespace frg {
@@ -155,6 +168,11 @@ struct GalleryWindow {
   int dim = 0, plane_dim = 0;
   uint32_t flags = 0;
   bool maybe_dead = false;
+  // tenant-filtered call over a window that is mostly other tenants' rows: the tensor-core kernels may ask the
+  // store for the tenant's tile list (store_tile_list; the caller holds owner->mu)
+  frg_store* owner = nullptr;
+  bool want_tile_list = false;
+  int32_t list_tenant = -1;
 };
 }  // namespace frg
 
@@ -165,6 +183,13 @@ int store_begin_write(frg_store* s, cudaStream_t stream);
 int store_end_write(frg_store* s, cudaStream_t stream);
 // order a match on `stream` after the last mutation; call with s->mu held
 int store_begin_read(frg_store* s, cudaStream_t stream);
+
+// api.cu: device-resident list of the tiles (`gran` rows each, absolute tile indices, ascending) that hold rows of
+// `tenant`, rebuilt when the store's version changed; *list == nullptr: not worth it.  s->mu held; the list is
+// valid for work enqueued on `st` after the call.
+int store_tile_list(frg_store* s, int32_t tenant, int gran, cudaStream_t st, const int32_t** list, int* n);
+// tc_match.cu
+int64_t tc_effective_rows(const GalleryWindow* s, int nq, cudaStream_t st, const int32_t** list, int* n_list);
 
 // ---- kernels' host launchers (defined in the .cu named in the comment) ----------------------
 // queries.cu: qn[f] = q[f] / ||q[f]|| (fp32), optional bf16 image
@@ -272,7 +297,8 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
 int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
-                    uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st);
+                    uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st,
+                    int64_t plan_rows, const int32_t* tile_list, int n_list);
 
 // first_match.cu
 int launch_first_match(const float* master, const int32_t* tags, int64_t rows, int dim, const float* qn, int nq,

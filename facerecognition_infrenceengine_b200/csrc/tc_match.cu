@@ -272,6 +272,10 @@ struct TcScanParams {
   int pad;
   int stages;              // depth of the TMA ring (tc_stages)
   uint32_t* fault;         // the store's fault word (host-mapped): set when a pipeline barrier timed out
+  // Tile list (tenant-filtered calls over a window that is mostly other tenants' rows): the kernel walks
+  // n_list listed tiles instead of every tile of the window; entry = absolute tile index (tile = kAccN rows)
+  const int32_t* tile_list;
+  int n_list;
 };
 
 // MASKED: rows can be invalid for this call (tombstones, or a tenant filter): their tags are read
@@ -319,8 +323,10 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
   const int chunk = blockIdx.y, chunks = gridDim.y;
   // view tile v stands for gallery tile v * tile_scale (the pre-pass samples whole 128-row tiles:
   // contiguous 128 KB reads, spread evenly over the gallery)
-  const int tiles_all = (p.n_rows + kAccN - 1) / kAccN;
+  const int tiles_all = p.tile_list ? p.n_list : (p.n_rows + kAccN - 1) / kAccN;
   const int tiles_total = (tiles_all + p.tile_scale - 1) / p.tile_scale;
+  // gallery tile behind view tile v
+  auto gtile = [&](int v) { const int i = v * p.tile_scale; return p.tile_list ? __ldg(p.tile_list + i) : i; };
   const int tile_begin = int((int64_t(tiles_total) * chunk) / chunks);
   const int tile_end = int((int64_t(tiles_total) * (chunk + 1)) / chunks);
   // FUSED: the CTA's first n_probe tiles (1/64 of its chunk, at least one) are visited twice - first as
@@ -363,7 +369,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_iter && !*abort_flag; ++it) {
         const int t = tile_of(it);
-        const int row0 = t * p.tile_scale * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
+        const int row0 = gtile(t) * kAccN + int(cta_rank) * kTileR;   // this CTA's half of the tile
         for (int kb = 0; kb < kblocks; ++kb) {
           if (it == 0) {
             // the query tile's k-block kb, issued just ahead of the first gallery block that meets it
@@ -510,6 +516,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
     int buf = 0; uint32_t tphase = 0;
     for (int it = 0; it < n_iter && !*abort_flag; ++it) {
       const int t = tile_of(it);
+      const int tile_row0 = gtile(t) * kAccN;              // first gallery row of this tile
       const bool probe = MODE == kModeGroupMax || (MODE == kModeFused && it < n_probe);
       if (idle) {
         mbar_wait(bar_tfull(buf), tphase, abort_flag);
@@ -524,7 +531,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
       uint32_t vmask[kBlocksPerWarp];
 #pragma unroll
       for (int b = 0; b < kBlocksPerWarp; ++b) {
-        const int row = t * p.tile_scale * kAccN + (half * kBlocksPerWarp + b) * 32 + lane;
+        const int row = tile_row0 + (half * kBlocksPerWarp + b) * 32 + lane;
         bool ok = row < p.n_rows;
         if (MASKED && ok) {
           const int32_t tag = __ldg(p.tags + row);
@@ -557,7 +564,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant_
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
           if (m >= thr) {
-            const int row0 = t * p.tile_scale * kAccN + (half * kBlocksPerWarp + b) * 32;
+            const int row0 = tile_row0 + (half * kBlocksPerWarp + b) * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (v[j] >= thr) {
@@ -958,13 +965,14 @@ static int probe_div() {
   return v;
 }
 
+bool tc_uses_pairs(int nq);
+
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
 
 static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
   (void)dim;
   pl->qtiles = (nq + kTileQ - 1) / kTileQ;
-  static const int pair_env = []() { const char* e = getenv("FRG_TC_PAIR"); return e ? atoi(e) : 1; }();
-  pl->pair = pair_env != 0 && pl->qtiles >= 2;
+  pl->pair = tc_uses_pairs(nq);
   if (pl->pair) pl->qtiles = (pl->qtiles + 1) & ~1;      // clusters of 2 along x; a padding tile holds no query
   // Fusing the pre-pass into the filter kernel saves a launch and a query-tile reload but probes a
   // smaller sample (one tile per CTA), i.e. a looser floor and more candidates: measured on B200 it
@@ -1069,6 +1077,23 @@ static int launch_tc_scan_m(bool masked, bool pair, const CUtensorMap& qm, const
                 : launch_tc_scan<MODE, false, false>(qm, gm, pm, p, qtiles, chunks, st);
 }
 
+bool tc_uses_pairs(int nq) {
+  static const int pair_env = []() { const char* e = getenv("FRG_TC_PAIR"); return e ? atoi(e) : 1; }();
+  return pair_env != 0 && (nq + kTileQ - 1) / kTileQ >= 2;
+}
+
+// rows the plan is made for: the window's, or (tile list in use) listed tiles x rows per tile
+int64_t tc_effective_rows(const GalleryWindow* s, int nq, cudaStream_t st, const int32_t** list, int* n_list) {
+  *list = nullptr; *n_list = 0;
+  if (!s->owner || !s->want_tile_list) return s->rows;
+  const int gran = tc_uses_pairs(nq) ? 2 * kTileR : kTileR;
+  const int32_t* l = nullptr; int n = 0;
+  if (store_tile_list(s->owner, s->list_tenant, gran, st, &l, &n) != FRG_OK) return -1;
+  if (!l) return s->rows;                 // not worth it / not known: the masked scan of the window
+  *list = l; *n_list = n;
+  return int64_t(n) * gran;
+}
+
 size_t tc_workspace_bytes(int64_t rows, int dim, int nq, int k, int sm_count) {
   TcPlan pl;
   tc_plan(rows, dim, nq, k, sm_count, &pl);
@@ -1090,14 +1115,17 @@ void tc_workspace_init_targets(int64_t rows, int dim, int nq, int k, int sm_coun
 int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const __nv_bfloat16* qb, const float* eps,
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
-                    uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st) {
+                    uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st,
+                    int64_t plan_rows, const int32_t* tile_list, int n_list) {
   const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
   if (euclid != (s->plane_dim != s->dim)) { set_error("tc_match: metric does not fit the store's scan plane"); return FRG_ERR_UNSUPPORTED; }
   // columns of the query tile: dim, or dim + kEuclidQPad (its last k-block meets the plane's 16-column pad block)
   const int kdim = euclid ? s->dim + kEuclidQPad : s->dim;
   const size_t pitch = size_t(s->plane_dim) * 2;
+  // (tile_list: a tenant-filtered call whose window is mostly other tenants' rows walks only the tiles that hold
+  // rows of the tenant; everything is planned for plan_rows = listed tiles x rows per tile)
   TcPlan pl;
-  tc_plan(s->rows, s->dim, nq, k, sm_count, &pl);
+  tc_plan(plan_rows, s->dim, nq, k, sm_count, &pl);
   uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
@@ -1116,6 +1144,7 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
 
   TcScanParams p{};
   p.fault = s->fault;
+  p.tile_list = tile_list; p.n_list = n_list;
   p.eps = eps; p.none_score = euclid ? kEuclidNone : kNoScore; p.pad = euclid ? 1 : 0; p.stages = tc_stages(kdim);
   p.dim = kdim; p.nq = nq; p.tenant = tenant; p.tags = s->tags;
   p.n_rows = int(s->rows); p.group_key = keys; p.k = k;

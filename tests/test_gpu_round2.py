@@ -219,31 +219,62 @@ def test_threads_match_while_the_gallery_is_compacted(frg):
     store.close()
 
 
-def test_stretched_tenant_window_takes_the_sparse_fallback(frg):
-    """A company enrolled as one block, then ONE person re-enrolled at the end of the gallery: the company's row
-    window now spans almost everything while its rows stay concentrated in one CTA's chunk, whose private
-    candidate segments overflow.  Those queries are redone exactly by the tag-first
-    ("sparse") fallback scan, which fetches only the company's rows.  Results against the oracle's masked scan;
-    F = 64 (single-CTA kernels) and F = 300 (CTA pairs)."""
-    n, d, T = 400_000, 512, 8_000
+def _stretched(frg, n, T, tenant, alternate):
+    """Companies enrolled as blocks of T rows; ONE person of `tenant` re-enrolled at the very end of the gallery, so
+    that company's row window spans almost everything while its rows stay concentrated in one CTA's chunk.
+    alternate: inside its block the company's rows alternate with another company's (thousands of 1-row intervals:
+    the store gives up on an interval list for it - "scattered")."""
+    d = 512
     G = synth.gallery(n, d, 41)
     tags = (1 + np.arange(n) // T).astype(np.int32)
-    tenant = 7
     lo = (tenant - 1) * T
+    if alternate:
+        tags[lo + 1:lo + T:2] = 9999
     tags[n - 1] = tenant                                 # the late re-enrolment
     store = frg.GalleryStore(dim=d, capacity=n)
     store.append_rows(G, tags, prenormalised=True)
     store._tenants = {"c%d" % i: i for i in range(1, n // T + 2)}
+    return store, G, tags, lo
+
+
+@pytest.mark.parametrize("alternate", [False, True])
+def test_stretched_tenant_window(frg, alternate):
+    """alternate=False: the kernels walk only the TILES the company's row intervals touch (tile list, DESIGN.md
+    section 4.4) - no overflow, no fallback.  alternate=True: no interval list; the masked scan of the wide window
+    overflows the private candidate segments of the one chunk that holds the company and those queries are redone
+    exactly by the tag-first ("sparse") fallback scan.  Both against the oracle's masked scan; F = 64 (single-CTA
+    kernels) and F = 300 (CTA pairs)."""
+    n, T, tenant = 400_000, 12_000, 7
+    store, G, tags, lo = _stretched(frg, n, T, tenant, alternate)
     rng = np.random.default_rng(3)
     m = frg.Matcher(store)
+    mine = np.nonzero(tags == tenant)[0]
     for F in (64, 300):
-        pick = rng.integers(lo, lo + T, size=F)
+        pick = rng.choice(mine, size=F)
         pick[0] = n - 1
-        Q = G[pick] + np.float32(0.03) * rng.standard_normal((F, d)).astype(np.float32)
-        Q[F // 2:] = rng.standard_normal((F - F // 2, d)).astype(np.float32)
+        Q = G[pick] + np.float32(0.03) * rng.standard_normal((F, 512)).astype(np.float32)
+        Q[F // 2:] = rng.standard_normal((F - F // 2, 512)).astype(np.float32)
         ref = mo.match_topk_fast(Q, G, 6, 0.4, tags, tenant)
-        r = m.match(Q, 5, 0.4, company_id="c%d" % tenant, with_ids=False)
-        compare(r.rows, r.scores, r.accept, ref, 5, 0.4)
-        assert r.rows[0, 0] == n - 1
-        assert r.launches >= 5
+        for variant in ("auto", "tc_bf16"):
+            r = m.match(Q, 5, 0.4, company_id="c%d" % tenant, variant=variant, with_ids=False)
+            if variant == "auto":
+                compare(r.rows, r.scores, r.accept, ref, 5, 0.4)
+            else:                                        # bf16 scores: own tolerance
+                assert np.abs(r.scores - ref[1][:, :5]).max() <= 8e-3
+            assert r.rows[0, 0] == n - 1
+    # after more enrolment and a compaction the lists follow (store version)
+    store.remove_rows(np.arange(0, 50_000))
+    extra = synth.gallery(100, 512, 43)
+    store.append_rows(extra, np.full(100, tenant, np.int32), prenormalised=True)
+    G2 = np.concatenate([G, extra]); tags2 = np.concatenate([tags, np.full(100, tenant, np.int32)])
+    tags2[:50_000] = -1
+    Q = np.concatenate([extra[:3], G[mine[:5]]])
+    ref = mo.match_topk_fast(Q, G2, 3, 0.4, tags2, tenant)
+    r = m.match(Q, 2, 0.4, company_id="c%d" % tenant, with_ids=False)
+    compare(r.rows, r.scores, r.accept, ref, 2, 0.4)
+    store.compact()
+    keep = np.nonzero(tags2 >= 0)[0]
+    ref = mo.match_topk_fast(Q, G2[keep], 3, 0.4, tags2[keep], tenant)
+    r = m.match(Q, 2, 0.4, company_id="c%d" % tenant, with_ids=False)
+    compare(r.rows, r.scores, r.accept, ref, 2, 0.4)
     store.close()
