@@ -44,6 +44,38 @@ def test_enrol_checks_golden(frg, golden):
     store.close()
 
 
+def test_enrolment_gallery_scans_what_the_reference_scans(frg):
+    """trainingServer.py:170-200 scans ONE collection of the company (employees or visitors), every document with an
+    embeddingId whatever its status, and returns doc[id_field].  The live matching store has evicted inactive /
+    blacklisted employees (infrenceServer.py:234-258) and mixes both collections - an EnrolmentGallery does not."""
+    rng = np.random.default_rng(8)
+    d = 512
+    V = mo.normalise_rows(rng.standard_normal((6, d)).astype(np.float32))
+    gal = frg.EnrolmentGallery(dim=d, capacity=16)
+    #        doc id   company  kind        ref_id (doc[id_field])
+    docs = [("e1", "acme", "employee", "EMP-001"), ("e2", "acme", "employee", "EMP-002"),
+            ("v1", "acme", "visitor", "VIS-001"), ("e3", "globex", "employee", "EMP-900"),
+            ("e4", "acme", "employee", None)]
+    gal.add([x[0] for x in docs], V[:5], [x[1] for x in docs], [x[2] for x in docs], [x[3] for x in docs])
+    chk = frg.EnrolmentChecker(gal)
+    near = lambda i: V[i] + np.float32(0.02) * rng.standard_normal(d).astype(np.float32)      # noqa: E731
+    assert chk.check_duplicate_face(near(0), "acme", kind="employee") == (True, "EMP-001")
+    # an inactive / blacklisted employee is still in the enrolment gallery: the re-enrolment is caught
+    assert chk.check_duplicate_face(near(1), "acme", kind="employee") == (True, "EMP-002")
+    # a visitor's template does not make an EMPLOYEE enrolment a duplicate, and the other way round
+    assert chk.check_duplicate_face(near(2), "acme", kind="employee") == (False, None)
+    assert chk.check_duplicate_face(near(2), "acme", kind="visitor") == (True, "VIS-001")
+    assert chk.check_duplicate_face(near(0), "acme", kind="visitor") == (False, None)
+    # another company's people never match; a document without the id field falls back to its _id
+    assert chk.check_duplicate_face(near(3), "acme", kind="employee") == (False, None)
+    assert chk.check_duplicate_face(near(3), "globex", kind="employee") == (True, "EMP-900")
+    assert chk.check_duplicate_face(near(4), "acme", kind="employee") == (True, "e4")
+    assert chk.check_duplicate_face(V[5], "acme", kind="employee") == (False, None)
+    ok, pair = chk.check_image_similarity([V[0], near(0), V[1]])
+    assert not ok and pair == (0, 2)
+    gal.close()
+
+
 def test_first_above_is_first_not_best(frg):
     d = 512
     G = synth.gallery(5000, d, 3)
