@@ -241,6 +241,9 @@ def ours_arm(args, rank, world):
     from oracle import matcher_oracle as mo
     from oracle import synth
 
+    # the library's bound on a rank waiting for its peers is 2 s; a bench whose ranks also do unsynchronised host
+    # work (allocating 150 GB, CPU spot checks) gives them 10 s before a skew is called a failure
+    os.environ.setdefault("FRG_EXCHANGE_TIMEOUT_MS", "10000")
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -631,7 +634,8 @@ def ours_arm(args, rank, world):
                                           "(no collective call on the data path; bounded waits, status codes)",
                                    "nccl": "NCCL all_gather_into_tensor + frg_merge_topk_strided"}.get(
                                        smatcher.exchange, str(smatcher.exchange)),
-                          "fallback_reason": smatcher.p2p_error} if sharded else None),
+                          "fallback_reason": smatcher.p2p_error,
+                          "timeout_ms": int(os.environ["FRG_EXCHANGE_TIMEOUT_MS"])} if sharded else None),
             "config3": config3, "config4": config4, "config5": config5,
             "notes": ["e2e may exceed the device-timed value on a power-capped box: the per-step host synchronisation "
                       "of the e2e loop lets the SM clock recover between steps, the back-to-back device loop does not"],
