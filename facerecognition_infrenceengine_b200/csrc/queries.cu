@@ -78,7 +78,6 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
 // largest S <=> smallest distance.  eps[w] bounds |S - exact| for every row of the store:
 //   bf16 rounding of both operands  (2u + u^2) ||q|| ||g||,  u = 2^-9   ->  < 3.92e-3 ||q|| Gmax
 //   fp32 bias / accumulation          O(dim * 2^-24) (||q|| ||g|| + ||g||^2 / 2)
-// taken as 4e-3 * ||q|| * Gmax + 1e-4 * Gmax^2 (the cosine filter's 4e-3 for unit vectors, plus the bias term).
 __global__ void __launch_bounds__(128)
 prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, const uint32_t* __restrict__ gmax_bits,
                               float* __restrict__ qn, __nv_bfloat16* __restrict__ q_aug, float* __restrict__ eps,

@@ -276,7 +276,7 @@ class ShardedMatcher:
     def __init__(self, gallery: ShardedGallery,
                  local_match: Optional[Callable] = None, merge: Optional[Callable] = None,
                  exchange: str = "auto", metric: str = "cosine"):
-        """exchange: "p2p" (fused push + flag + merge kernel over NVLink peer memory), "nccl" (all-gather +
+        """exchange: "p2p" (the match kernels push over NVLink peer memory, a poll-only kernel merges; bounded waits), "nccl" (all-gather +
         merge kernel) or "auto" (p2p when the peer mapping can be set up, else nccl; `self.exchange` tells
         which one runs, `self.p2p_error` why not)."""
         self.g = gallery
@@ -339,7 +339,8 @@ class ShardedMatcher:
 
     def _match_exchange_p2p(self, Q, rows_l, scores_l, F, k, threshold, variant, tenant, out):
         """frg_match_exchange: local match whose select stage pushes each query's top-k to all ranks as it
-        becomes final, then the push-stragglers + poll + merge kernel - one enqueue, no collective call."""
+        becomes final (the exact fallback pushes what it redoes), then the poll + merge kernel - one enqueue, no
+        collective call; a void call (missing rank, other shape) is reported by check_exchange()."""
         import torch
         t, hdl, cap, _ = self._x
         rows, scores, accept = out

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 KIND = {"recognized": 0, "unknown": 1, "ignored": 2}
 VARIANTS = ["scan_f32", "tc_exact", "auto"]
-COARSE_EPS = 4e-3            # |bf16 filter score - fp32 score| bound; bf16 gallery mode tolerance
+COARSE_EPS = 4e-3            # bf16 filter score vs fp32 score on ORDINARY data (the measured bound eps[q] is ~3.6e-3
+                             # there; adversarial roundings: tests/rounding_case.py)
 
 
 @pytest.fixture(scope="module")
@@ -366,7 +367,7 @@ def test_embedding_manager_replays_reference_scenario(frg, golden):
 @pytest.mark.parametrize("n,f,k", [(20000, 40, 5), (300000, 130, 10)])
 def test_bf16_gallery_mode(frg, n, f, k):
     """FRG_VARIANT_TC_BF16: the coarse bf16 scores are returned as they are.  Stated bound:
-    |delta score| <= 4e-3 (rigorous for unit vectors: 2 x 2^-9 + accumulation); ids exact wherever the
+    |delta score| <= 4e-3 on this (random) data - the measured bound eps[q] ~ 3.6e-3; ids exact wherever the
     oracle gap exceeds 2 x 4e-3; decisions identical outside that band around the threshold."""
     d = 512
     store = frg.GalleryStore(dim=d, capacity=n)

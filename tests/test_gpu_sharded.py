@@ -159,7 +159,7 @@ if dist.get_rank() == 0:
     assert np.abs(scores.cpu().numpy() - rs[:, :k]).max() <= 1e-4
     assert (acc.cpu().numpy().astype(bool) == ra).all()
     print("SHARDED_OK world=%%d" %% dist.get_world_size())
-# the fused peer-memory exchange (push + flag + merge in one kernel, no collective call) gives the same
+# the peer-memory exchange (pushes from the match kernels, a poll-only merge kernel, no collective call) gives the same
 # answer bit for bit, call after call (epoch parity reuse), for changing batch sizes (buffer regrowth), and
 # when one rank runs late
 m_p2p = ShardedMatcher(g, exchange="p2p")
