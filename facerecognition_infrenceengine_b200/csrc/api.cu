@@ -1,5 +1,4 @@
 // C ABI of libfrg.so (include/frg.h): store life-cycle, ingest, match dispatch, merge.
-#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -11,8 +10,6 @@
 namespace frg {
 
 static thread_local char g_err[512] = "";
-static thread_local int g_capturing = 0;          // this thread is capturing a match into a CUDA graph (frg_match_host)
-static std::atomic<uint64_t> g_store_serial{1};   // frg_store::serial: graph keys must never alias a recycled address
 static thread_local int g_launches = 0;
 static thread_local const char* g_variant = "none";
 
@@ -160,7 +157,6 @@ static int grow_locked(frg_store* s, int64_t cap) {
   cudaFree(s->master); cudaFree(s->plane); cudaFree(s->tags);
   s->master = m; s->plane = p; s->tags = t;
   s->capacity = cap;
-  s->version++;                    // the arrays moved: captured graphs and cached lists of the old layout are void
   s->readers.clear();
   s->has_write = false;
   return FRG_OK;
@@ -391,7 +387,6 @@ int frg_store_create(int32_t device, int32_t dim, int64_t capacity, uint32_t fla
   frg_store* s = new (std::nothrow) frg_store();
   if (!s) { set_error("out of host memory"); return FRG_ERR_NOMEM; }
   s->device = device; s->dim = dim; s->flags = flags;
-  s->serial = g_store_serial.fetch_add(1);
   // a raw store's scan plane is the Euclidean one (norm terms in kEuclidPad more columns) where the
   // tensor-core tile shapes cover it; other raw stores keep a plain image nobody scans
   const char* why = "";
@@ -913,12 +908,11 @@ static int match_impl(frg_store* s, const float* q, int32_t nq, int32_t k, const
 
   std::lock_guard<std::mutex> lk(s->mu);   // enqueue under the lock: the snapshot a match sees is the
                                            // store as of this call (peopleCount.py:816-819 semantics)
-  if (!g_capturing) FRG_CHECK(store_begin_read(s, st));      // (a captured match is ordered at every graph launch)
+  FRG_CHECK(store_begin_read(s, st));
   struct SeqBump { ~SeqBump() { ++g_match_seq; } } bump;      // sampled profiling: every 4th match is bracketed
   // a tenant-filtered call scans only the rows that tenant can sit in (the whole gallery otherwise)
   const int variant = pick_variant(s, p, nq);
   const GalleryWindow w = window_of(s, p->tenant, variant == FRG_VARIANT_TC_EXACT || variant == FRG_VARIANT_TC_BF16);
-  if (g_capturing && w.want_tile_list) { set_error("match: tile lists are not captured into graphs"); return FRG_ERR_UNSUPPORTED; }
   frg_match_params_t pw = *p;
   pw.row_offset += w.row0;
   switch (variant) {
@@ -1006,130 +1000,6 @@ struct PinnedScratch {
 };
 static thread_local PinnedScratch g_result_bounce;
 
-// ---- captured matches for the reference's own operating point -------------------------------------------------
-// One frame of a few faces against a gallery of some ten thousand templates (infrenceServer.py:603-622: one call per
-// frame) takes ~32 us on the device and ~80 us end to end: the rest is host work - three stream-ordered allocations,
-// two copies, five launches, three tensor-map encodes.  The second frg_match_host with the same (store version, batch
-// shape, parameters) on a thread is CAPTURED into a CUDA graph (H2D from a pinned staging buffer, the whole match,
-// D2H into a pinned buffer); from then on such a call is a memcpy into the staging buffer, one cudaGraphLaunch and a
-// stream synchronise.  A mutation bumps the store version, so a stale graph is never launched.  FRG_GRAPH=0 turns
-// it off.  Per thread, at most kGraphSlots graphs (least recently used goes).
-namespace {
-constexpr int kGraphSlots = 16;
-constexpr int kGraphMaxQueries = 256;
-constexpr int64_t kGraphMaxRows = 262144;
-struct GraphKey {
-  uint64_t serial; int64_t version, row_offset; int32_t nq, k, metric, variant, tenant; uint32_t thr_bits, flags;
-  bool operator==(const GraphKey& o) const {
-    return serial == o.serial && version == o.version && row_offset == o.row_offset && nq == o.nq && k == o.k &&
-           metric == o.metric && variant == o.variant && tenant == o.tenant && thr_bits == o.thr_bits && flags == o.flags;
-  }
-};
-struct GraphEntry {
-  GraphKey key{};
-  cudaGraphExec_t exec = nullptr;
-  unsigned char *dev = nullptr, *hin = nullptr, *hout = nullptr;
-  size_t qb = 0, rb = 0, sb = 0, ab = 0, o_r = 0, o_s = 0, o_a = 0;
-  uint64_t tick = 0;
-  int launches = 0;
-  bool dead = false;               // capture failed once: this shape keeps the ordinary path
-  const char* variant = "none";
-  void release() {
-    if (exec) cudaGraphExecDestroy(exec);
-    if (dev) cudaFree(dev);
-    if (hin) cudaFreeHost(hin);
-    if (hout) cudaFreeHost(hout);
-    exec = nullptr; dev = hin = hout = nullptr;
-  }
-};
-struct GraphCache {
-  std::vector<GraphEntry> e;
-  uint64_t tick = 0;
-  ~GraphCache() { for (auto& x : e) x.release(); }
-  GraphEntry* find(const GraphKey& k) { for (auto& x : e) if (x.key == k) { x.tick = ++tick; return &x; } return nullptr; }
-  GraphEntry* add(const GraphKey& k) {
-    if (int(e.size()) >= kGraphSlots) {
-      size_t v = 0;
-      for (size_t i = 1; i < e.size(); ++i) if (e[i].tick < e[v].tick) v = i;
-      e[v].release();
-      e.erase(e.begin() + v);
-    }
-    e.emplace_back();
-    e.back().key = k; e.back().tick = ++tick;
-    return &e.back();
-  }
-};
-thread_local GraphCache g_graphs;
-
-const char* graph_variant_name(const char* v) {
-  if (!strcmp(v, "tc_exact")) return "tc_exact+graph";
-  if (!strcmp(v, "tc_bf16")) return "tc_bf16+graph";
-  if (!strcmp(v, "scan_f32")) return "scan_f32+graph";
-  return "graph";
-}
-
-int capture_match(frg_store* s, GraphEntry* ge, int32_t nq, int32_t k, const frg_match_params_t* p) {
-  cudaStream_t st = cudaStreamPerThread;
-  ge->qb = size_t(nq) * s->dim * sizeof(float);
-  ge->rb = size_t(nq) * k * sizeof(int64_t); ge->sb = size_t(nq) * k * sizeof(float); ge->ab = size_t(nq);
-  ge->o_r = (ge->qb + 255) & ~size_t(255);
-  ge->o_s = (ge->o_r + ge->rb + 255) & ~size_t(255);
-  ge->o_a = (ge->o_s + ge->sb + 255) & ~size_t(255);
-  const size_t span = ge->o_a + ge->ab - ge->o_r;
-  FRG_CUDA(cudaStreamSynchronize(st));
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ge->dev), ge->o_a + ge->ab);
-  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ge->hin), ge->qb, cudaHostAllocDefault);
-  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&ge->hout), span, cudaHostAllocDefault);
-  if (e != cudaSuccess) { ge->release(); return cuda_fail(e, "graph buffers", __FILE__, __LINE__); }
-  e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
-  if (e != cudaSuccess) { ge->release(); return cuda_fail(e, "cudaStreamBeginCapture", __FILE__, __LINE__); }
-  g_capturing = 1;
-  int rc = FRG_OK;
-  e = cudaMemcpyAsync(ge->dev, ge->hin, ge->qb, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess)
-    rc = frg_match(s, reinterpret_cast<float*>(ge->dev), nq, k, p, reinterpret_cast<int64_t*>(ge->dev + ge->o_r),
-                   reinterpret_cast<float*>(ge->dev + ge->o_s), ge->dev + ge->o_a, st);
-  ge->launches = g_launches; ge->variant = graph_variant_name(g_variant);
-  if (e == cudaSuccess && rc == FRG_OK) e = cudaMemcpyAsync(ge->hout, ge->dev + ge->o_r, span, cudaMemcpyDeviceToHost, st);
-  g_capturing = 0;
-  cudaGraph_t graph = nullptr;
-  const cudaError_t e2 = cudaStreamEndCapture(st, &graph);
-  if (e == cudaSuccess && rc == FRG_OK && e2 == cudaSuccess && graph) e = cudaGraphInstantiate(&ge->exec, graph, 0);
-  else if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : cudaErrorUnknown;
-  if (graph) cudaGraphDestroy(graph);
-  if (e != cudaSuccess || rc != FRG_OK || !ge->exec) {
-    (void)cudaGetLastError();
-    ge->release();
-    return rc != FRG_OK ? rc : cuda_fail(e, "graph capture", __FILE__, __LINE__);
-  }
-  return FRG_OK;
-}
-
-// 1 = done (results delivered or a real error in *rc_out), 0 = the graph is stale: take the ordinary path
-int replay_match(frg_store* s, GraphEntry* ge, const float* q, int64_t* out_rows, float* out_scores,
-                 uint8_t* out_accept, int* rc_out) {
-  cudaStream_t st = cudaStreamPerThread;
-  memcpy(ge->hin, q, ge->qb);
-  {
-    std::lock_guard<std::mutex> lk(s->mu);
-    if (s->version != ge->key.version) return 0;
-    *rc_out = store_begin_read(s, st);               // ordered after the last mutation, known to later mutations
-    if (*rc_out != FRG_OK) return 1;
-    const cudaError_t e = cudaGraphLaunch(ge->exec, st);
-    if (e != cudaSuccess) { *rc_out = cuda_fail(e, "cudaGraphLaunch", __FILE__, __LINE__); return 1; }
-  }
-  const cudaError_t e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) { *rc_out = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); return 1; }
-  memcpy(out_rows, ge->hout, ge->rb);
-  memcpy(out_scores, ge->hout + (ge->o_s - ge->o_r), ge->sb);
-  if (out_accept) memcpy(out_accept, ge->hout + (ge->o_a - ge->o_r), ge->ab);
-  reset_launches();
-  g_launches = ge->launches; g_variant = ge->variant;
-  *rc_out = store_fault(s);
-  return 1;
-}
-}  // namespace
-
 int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const frg_match_params_t* p,
                    int64_t* out_rows, float* out_scores, uint8_t* out_accept) {
   if (!s || nq < 0 || (nq > 0 && (!q || !out_rows || !out_scores))) { set_error("match_host: bad argument"); return FRG_ERR_INVALID; }
@@ -1137,37 +1007,6 @@ int frg_match_host(frg_store* s, const float* q, int32_t nq, int32_t k, const fr
   if (nq == 0) return FRG_OK;
   DeviceGuard g(s->device);
   cudaStream_t st = cudaStreamPerThread;
-  static const bool graphs_on = []() { const char* e = getenv("FRG_GRAPH"); return !e || atoi(e) != 0; }();
-  if (graphs_on && p && nq <= kGraphMaxQueries && !g_profile) {
-    GraphKey key{};
-    int64_t rows_now;
-    {
-      std::lock_guard<std::mutex> lk(s->mu);
-      key.serial = s->serial; key.version = s->version; rows_now = s->rows;
-    }
-    if (rows_now > 0 && rows_now <= kGraphMaxRows) {
-      key.row_offset = p->row_offset; key.nq = nq; key.k = k; key.metric = p->metric; key.variant = p->variant;
-      key.tenant = p->tenant; key.flags = p->flags;
-      memcpy(&key.thr_bits, &p->threshold, sizeof(uint32_t));
-      GraphEntry* ge = g_graphs.find(key);
-      int rc = FRG_OK;
-      if (ge && ge->exec) {
-        if (replay_match(s, ge, q, out_rows, out_scores, out_accept, &rc)) return rc;
-      } else if (ge && !ge->dead) {
-        // second call with this key: capture it, then serve this very call from the graph
-        if (capture_match(s, ge, nq, k, p) == FRG_OK) {
-          bool fresh;
-          { std::lock_guard<std::mutex> lk(s->mu); fresh = s->version == key.version; }
-          if (fresh && replay_match(s, ge, q, out_rows, out_scores, out_accept, &rc)) return rc;
-          if (!fresh) ge->release();             // the gallery changed under the capture: try again later
-        } else {
-          ge->dead = true;
-        }
-      } else if (!ge) {
-        g_graphs.add(key);                       // seen once: the ordinary path; captured if it comes back
-      }
-    }
-  }
   const size_t qb = size_t(nq) * s->dim * sizeof(float);
   const size_t rb = size_t(nq) * k * sizeof(int64_t), sb = size_t(nq) * k * sizeof(float), ab = size_t(nq);
   const size_t o_r = (qb + 255) & ~size_t(255), o_s = (o_r + rb + 255) & ~size_t(255), o_a = (o_s + sb + 255) & ~size_t(255);

@@ -108,7 +108,6 @@ struct DeviceGuard {
 
 // ---- the store ------------------------------------------------------------------------------
 struct frg_store {
-  uint64_t serial = 0;    // unique per store ever created in this process
   int device = 0;
   int dim = 0;
   uint32_t flags = 0;
