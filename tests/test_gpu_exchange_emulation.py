@@ -222,3 +222,46 @@ def test_missing_rank_times_out_with_a_status_not_a_trap(frg):
     torch.cuda.synchronize()
     assert same(torch, outs, R.reference(Qd, 5))
     R.close()
+
+
+def test_emulated_ranks_with_a_stretched_tenant_window(frg):
+    """Row-sharded AND company-filtered: on each shard the company is a block plus one late row at the shard's end,
+    so every rank's local match walks its own tile list; the merged result equals the single store's (which walks
+    its own) and the oracle's masked scan."""
+    import torch
+    from facerecognition_infrenceengine_b200 import _native as N
+    n, d, T, tenant = 300_000, 512, 10_000, 3
+    R = Ranks(frg, n, 2)
+    for st in R.stores + [R.full]:
+        st.close()
+    G = synth.gallery(n, d)
+    tags = (1 + np.arange(n) // T).astype(np.int32)
+    tags[n // 2 - 1] = tenant                  # last row of shard 0
+    tags[n - 1] = tenant                       # last row of shard 1 (the company has no block there: just this row)
+    tags[200_000:205_000] = tenant             # ... and a second block on shard 1
+    R.stores = []
+    for lo, hi in R.bounds:
+        st = frg.GalleryStore(dim=d, capacity=hi - lo)
+        st.append_rows(G[lo:hi], tags[lo:hi], prenormalised=True)
+        R.stores.append(st)
+    R.full = frg.GalleryStore(dim=d, capacity=n)
+    R.full.append_rows(G, tags, prenormalised=True)
+    rng = np.random.default_rng(1)
+    mine = np.nonzero(tags == tenant)[0]
+    for F in (32, 200):
+        pick = rng.choice(mine, size=F)
+        pick[:2] = [n // 2 - 1, n - 1]
+        Q = G[pick] + np.float32(0.03) * rng.standard_normal((F, d)).astype(np.float32)
+        Qd = torch.from_numpy(Q).cuda()
+        R.epoch += 1
+        for r in (0, 1):
+            R.call(r, Qd, 5, N.XCHG_PUSH_ONLY, R.epoch, 0.4, tenant=tenant)
+        outs = [R.call(r, Qd, 5, N.XCHG_MERGE_ONLY, R.epoch, 0.4, tenant=tenant)[0] for r in (0, 1)]
+        ref = frg.Matcher(R.full).match_device(Qd, 5, 0.4, tenant=tenant)
+        torch.cuda.synchronize()
+        assert same(torch, outs, ref), F
+        rr, rs, ra = mo.match_topk_fast(Q, G, 6, 0.4, tags, tenant)
+        rows, scores, acc = (t.cpu().numpy() for t in outs[0])
+        assert mo.ids_match_with_gap(rr, rs, rows, 1e-4).all() and np.abs(scores - rs[:, :5]).max() <= 1e-4
+        assert rows[0, 0] == n // 2 - 1 and rows[1, 0] == n - 1
+    R.close()

@@ -352,3 +352,30 @@ def test_small_frames_across_mutations(frg):
     t = threading.Thread(target=other); t.start(); t.join(60)
     assert not err, err
     store.close()
+
+
+def test_stretched_tenant_window_euclidean(frg):
+    """Tile lists serve the Euclidean scan plane too (raw store, 128-d, pad block): a company's block plus one far
+    row, against the fp64 direct-difference oracle; bit-identical to the exact scan."""
+    rng = np.random.default_rng(37)
+    n, d, T, tenant = 100_000, 128, 9_000, 4
+    G = (synth.gallery(n, d, 61) * np.float32(1.3)).astype(np.float32)
+    tags = (1 + np.arange(n) // T).astype(np.int32)
+    tags[n - 1] = tenant
+    store = frg.GalleryStore(dim=d, capacity=n, raw=True)
+    store.append_rows(G, tags)
+    store._tenants = {"c%d" % i: i for i in range(1, n // T + 2)}
+    mine = np.nonzero(tags == tenant)[0]
+    m = frg.Matcher(store, metric="euclidean")
+    for F in (40, 130):
+        pick = rng.choice(mine, size=F)
+        pick[0] = n - 1
+        Q = G[pick] + np.float32(0.02) * rng.standard_normal((F, d)).astype(np.float32)
+        ref_r, ref_d, ref_a = mo.euclidean_topk(Q, G, 3, 0.6, tags, tenant)
+        a = m.match(Q, 2, 0.6, company_id="c%d" % tenant, variant="tc_exact", with_ids=False)
+        b = m.match(Q, 2, 0.6, company_id="c%d" % tenant, variant="scan_f32", with_ids=False)
+        assert np.array_equal(a.rows, b.rows) and np.array_equal(a.scores.view(np.uint32), b.scores.view(np.uint32))
+        assert np.array_equal(a.accept, b.accept)
+        assert mo.ids_match_with_gap(ref_r, -ref_d, a.rows, TOL).all()
+        assert np.abs(a.scores - ref_d[:, :2]).max() <= TOL and a.rows[0, 0] == n - 1
+    store.close()
