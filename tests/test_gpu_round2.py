@@ -379,3 +379,72 @@ def test_stretched_tenant_window_euclidean(frg):
         assert mo.ids_match_with_gap(ref_r, -ref_d, a.rows, TOL).all()
         assert np.abs(a.scores - ref_d[:, :2]).max() <= TOL and a.rows[0, 0] == n - 1
     store.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_life_of_a_multi_tenant_gallery(frg, seed):
+    """Companies enrolled as blocks, then a random sequence of late enrolments (stretch the row windows), in-place
+    moves between companies, evictions and compactions, with company-filtered matches in between (single-CTA and pair
+    kernels, both exact variants) against the oracle's masked scan over a host mirror: row windows, span intervals,
+    the tile-list cache and its versioning can never change an answer, only the time it takes."""
+    rng = np.random.default_rng(500 + seed)
+    d, T, C = 512, 9_000, 8
+    n0 = T * C
+    G = synth.gallery(n0 + 4_000, d, 70 + seed)
+    vec = {"r%d" % i: G[i] for i in range(n0)}
+    comp = {"r%d" % i: "c%d" % (i // T) for i in range(n0)}
+    order = list(vec)
+    store = frg.GalleryStore(dim=d, capacity=n0 + 8_000)
+    store.upsert(order, G[:n0], [comp[p] for p in order], prenormalised=True)
+    m = frg.Matcher(store)
+    fresh = n0
+
+    def check():
+        company = "c%d" % rng.integers(0, C)
+        F = int(rng.choice([3, 40, 150]))
+        mine = [p for p in order if comp[p] == company]
+        pick = rng.choice(len(mine), size=F)
+        Q = np.stack([vec[mine[i]] for i in pick]) + np.float32(0.03) * rng.standard_normal((F, d)).astype(np.float32)
+        Q[F // 2:] = rng.standard_normal((F - F // 2, d)).astype(np.float32)
+        Gm = np.stack([vec[p] for p in order])
+        tg = np.array([int(comp[p][1:]) for p in order], np.int32)
+        ref = mo.match_topk_fast(Q, Gm, 4, 0.4, tg, int(company[1:]))
+        for variant in ("auto", "scan_f32"):
+            r = m.match(Q, 3, 0.4, company_id=company, variant=variant)
+            got = np.array([[order.index(x) if x is not None else -1 for x in row] for row in r.ids]) if F <= 40 else None
+            # rows are positions in the store (tombstones included): compare through ids for small F, scores always
+            filled = ref[0][:, :3] >= 0
+            assert np.abs(r.scores[filled] - ref[1][:, :3][filled]).max(initial=0) <= TOL, (variant, company, F)
+            assert (r.scores[~filled] == -1).all()
+            if got is not None:
+                assert mo.ids_match_with_gap(ref[0], ref[1], got, TOL).all(), (variant, company, F)
+            near = np.abs(ref[1][:, 0].astype(np.float64) - 0.4) <= TOL
+            assert (r.accept[~near] == ref[2][~near]).all()
+
+    check()
+    for step in range(14):
+        op = rng.choice(["late", "move", "evict", "compact", "late"])
+        if op == "late":                                   # a few people of one company enrolled at the end
+            c = "c%d" % rng.integers(0, C)
+            cnt = int(rng.integers(1, 40))
+            ids = ["n%d" % (fresh + i) for i in range(cnt)]
+            store.upsert(ids, G[fresh:fresh + cnt], [c] * cnt, prenormalised=True)
+            for i, p in enumerate(ids):
+                vec[p] = G[fresh + i]; comp[p] = c; order.append(p)
+            fresh += cnt
+        elif op == "move":                                 # existing ids change company, in place
+            ids = [order[i] for i in rng.choice(len(order), size=5, replace=False)]
+            c = "c%d" % rng.integers(0, C)
+            store.upsert(ids, np.stack([vec[p] for p in ids]), [c] * len(ids), prenormalised=True)
+            for p in ids:
+                comp[p] = c
+        elif op == "evict":
+            ids = [order[i] for i in rng.choice(len(order), size=int(rng.integers(1, 300)), replace=False)]
+            store.remove(ids)
+            for p in ids:
+                order.remove(p); del vec[p], comp[p]
+        else:
+            store.compact()
+        check()
+    assert len(store) == len(order) and store.ids() == order
+    store.close()
