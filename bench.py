@@ -880,7 +880,7 @@ def ncu_traffic(variant, n, dim, F, world):
     capture committed under profiles/ (only when it was taken on this very workload), else None."""
     if world != 1 or variant != "tc_exact" or (n, dim) != (1_000_000, 512):
         return None, None
-    name = {1024: "r02_ncu_full_tc_scan_b1024.txt", 64: "r01_ncu_full_tc_scan_b64_v1.txt"}.get(F)
+    name = {1024: "r02_ncu_full_tc_scan_b1024_grouped.txt", 64: "r01_ncu_full_tc_scan_b64_v1.txt"}.get(F)
     path = os.path.join(ROOT, "profiles", name) if name else None
     if not path or not os.path.exists(path):
         return None, None
