@@ -54,6 +54,38 @@ void profile_end(cudaStream_t st, int launches);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
+#ifdef __CUDACC__
+// order-preserving float <-> uint32 key (a < b  <=>  key(a) < key(b) for non-NaN floats): lets atomicMax fold float
+// maxima and redux.sync find a warp's best score in one instruction
+__device__ __forceinline__ uint32_t float_key(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// (float_key(-1.0f) == 0x407FFFFF: the value normalise_queries_kernel resets the group keys to)
+
+// Lane of the warp's best (score desc, row asc, lane asc) entry.  One REDUX over the ordered keys and a ballot; only
+// when several lanes hold exactly the best score (exact ties; exhausted lists, where every lane holds the sentinel)
+// does the (row, lane) butterfly run.  -0.0 and +0.0 compare equal, as in the float comparison.  No NaNs in `s`.
+template <typename RowT>
+__device__ __forceinline__ int warp_argbest(float s, RowT r, RowT none, int lane) {
+  const uint32_t key = float_key(s + 0.0f);
+  const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
+  const unsigned tied = __ballot_sync(0xffffffffu, key == mx);
+  if ((tied & (tied - 1u)) == 0u) return __ffs(tied) - 1;
+  RowT br = key == mx ? r : none;
+  int bl = key == mx ? lane : 64;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const RowT orow = __shfl_xor_sync(0xffffffffu, br, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    if (orow < br || (orow == br && ol < bl)) { br = orow; bl = ol; }
+  }
+  return bl;
+}
+#endif
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

@@ -83,17 +83,10 @@ __device__ __forceinline__ void merge_lists(const Lists& lists, int parts, int k
 
   // k_out rounds of warp arg-best over the lane heads; the winner pops its head
   for (int j = 0; j < k_out; ++j) {
-    float bs = sc[0];
-    RowT br = ix[0];
-    int bl = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const RowT orow = __shfl_xor_sync(0xffffffffu, br, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      // total order (score, row, lane) so that every lane converges on the same winner
-      if (better<RowT>(os, orow, bs, br) || (os == bs && orow == br && ol < bl)) { bs = os; br = orow; bl = ol; }
-    }
+    // total order (score, row, lane): every lane agrees on the winner (warp_argbest, frg_internal.cuh)
+    const int bl = warp_argbest<RowT>(sc[0], ix[0], RowLimits<RowT>::none(), lane);
+    const float bs = __shfl_sync(0xffffffffu, sc[0], bl);
+    const RowT br = __shfl_sync(0xffffffffu, ix[0], bl);
     if (lane == bl) {
 #pragma unroll
       for (int t = 0; t < KMAX - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }

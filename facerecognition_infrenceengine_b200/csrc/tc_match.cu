@@ -233,16 +233,8 @@ constexpr uint32_t make_idesc(int m, int n) {
 enum TcMode { kModeGroupMax = 0, kModeFilter = 1, kModeFused = 2 };
 constexpr int kGroups = 32;
 
-// order-preserving float <-> uint32 key, so that the group maxima of all pre-pass CTAs can be folded
-// with one atomicMax per (query, group)
-__device__ __forceinline__ uint32_t float_key(float x) {
-  const uint32_t b = __float_as_uint(x);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float key_float(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-// (float_key(-1.0f) == 0x407FFFFF: the value normalise_queries_kernel resets the keys to)
+// (float_key / key_float, frg_internal.cuh: the group maxima of all pre-pass CTAs are folded with one atomicMax per
+// (query, group) on order-preserving keys)
 
 struct TcScanParams {
   int dim;                 // 512 etc. (multiple of 64)
@@ -699,14 +691,9 @@ __device__ __forceinline__ void lane_insert(float (&sc)[K], int32_t (&ix)[K], fl
 template <int K>
 __device__ __forceinline__ void warp_pop_best(float (&sc)[K], int32_t (&ix)[K], int lane, float sentinel,
                                               float* best_s, int32_t* best_r) {
-  float bs = sc[0]; int32_t br = ix[0]; int bl = lane;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-    const int32_t orow = __shfl_xor_sync(0xffffffffu, br, o);
-    const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-    if (os > bs || (os == bs && (orow < br || (orow == br && ol < bl)))) { bs = os; br = orow; bl = ol; }
-  }
+  const int bl = warp_argbest<int32_t>(sc[0], ix[0], 0x7fffffff, lane);
+  const float bs = __shfl_sync(0xffffffffu, sc[0], bl);
+  const int32_t br = __shfl_sync(0xffffffffu, ix[0], bl);
   if (lane == bl) {
 #pragma unroll
     for (int t = 0; t < K - 1; ++t) { sc[t] = sc[t + 1]; ix[t] = ix[t + 1]; }
