@@ -992,13 +992,9 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   static const int fused_env = []() { const char* e = getenv("FRG_TC_FUSED"); return e ? atoi(e) : -1; }();
   pl->fused = fused_env >= 0 ? fused_env != 0 : nq <= 8;
   const int tile_rows = pl->pair ? 2 * kTileR : kTileR;
-  // pre-pass sample: every stride-th tile, stride the largest power of two <= 64 that still leaves >= 16 K
-  // (single-CTA form) / 8 K (pair form) sampled rows
-  // (r2: with the grouped rare path the filter no longer cares how many candidates the floor lets through -
-  // profiles/r02_ab_grouped.txt - so the tensor-bound pair form samples half as many rows: its pre-pass is MMA-bound,
-  // 32 -> ~20 us at batch 1024)
-  static const int64_t pre_min_env = []() { const char* e = getenv("FRG_TC_PRE_MIN_ROWS"); const long v = e ? atol(e) : 0; return int64_t(v < 1 ? 0 : v); }();
-  const int64_t pre_min_rows = pre_min_env ? pre_min_env : (pl->pair ? 8192 : 16384);
+  // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
+  // leaves >= 16 K sampled rows
+  static const int64_t pre_min_rows = []() { const char* e = getenv("FRG_TC_PRE_MIN_ROWS"); const long v = e ? atol(e) : 16384; return int64_t(v < 1 ? 16384 : v); }();
   int stride = 1;
   while (stride < 64 && rows / (stride * 2) >= pre_min_rows) stride *= 2;
   pl->stride = stride;
