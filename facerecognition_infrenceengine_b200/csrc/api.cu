@@ -848,29 +848,34 @@ static int match_tc(const GalleryWindow* s, const float* q, int nq, int k, const
   const size_t qn_bytes = (size_t(nq) * s->dim * sizeof(float) + 255) & ~size_t(255);
   const size_t qb_bytes = (size_t(nq) * (s->dim + (euclid ? kEuclidQPad : 0)) * sizeof(__nv_bfloat16) + 255) & ~size_t(255);
   const size_t eps_bytes = (size_t(nq) * sizeof(float) + 255) & ~size_t(255);     // per-query filter error bound
+  const size_t qb2_bytes = euclid ? qb_bytes : 0;                                 // the pre-pass (lower-bound) image
+  const size_t coef_bytes = euclid ? ((size_t(nq) * 4 * sizeof(float) + 255) & ~size_t(255)) : 0;
   const int32_t* tile_list = nullptr;
   int n_list = 0;
   const int64_t plan_rows = tc_effective_rows(s, nq, st, &tile_list, &n_list);
   if (plan_rows < 0) return FRG_ERR_CUDA;
-  const size_t tc_bytes = tc_workspace_bytes(plan_rows, s->dim, nq, k, sm_count);
+  const int plan_dim = euclid ? -s->dim : s->dim;          // (negative: Euclidean plane, tc_plan)
+  const size_t tc_bytes = tc_workspace_bytes(plan_rows, plan_dim, nq, k, sm_count);
   unsigned char* ws = nullptr;
-  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + eps_bytes + tc_bytes, st));
+  FRG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), qn_bytes + qb_bytes + eps_bytes + qb2_bytes + coef_bytes + tc_bytes, st));
   float* qn = reinterpret_cast<float*>(ws);
   __nv_bfloat16* qb = reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes);
   float* eps = reinterpret_cast<float*>(ws + qn_bytes + qb_bytes);
-  unsigned char* tc_ws = ws + qn_bytes + qb_bytes + eps_bytes;
+  __nv_bfloat16* qb2 = euclid ? reinterpret_cast<__nv_bfloat16*>(ws + qn_bytes + qb_bytes + eps_bytes) : nullptr;
+  float* coef = euclid ? reinterpret_cast<float*>(ws + qn_bytes + qb_bytes + eps_bytes + qb2_bytes) : nullptr;
+  unsigned char* tc_ws = ws + qn_bytes + qb_bytes + eps_bytes + qb2_bytes + coef_bytes;
   int* flagged = nullptr; int* n_flagged = nullptr;
   uint32_t* keys = nullptr; int* ct0 = nullptr; int* nf0 = nullptr;
-  tc_workspace_init_targets(plan_rows, s->dim, nq, k, sm_count, tc_ws, &keys, &ct0, &nf0);
+  tc_workspace_init_targets(plan_rows, plan_dim, nq, k, sm_count, tc_ws, &keys, &ct0, &nf0);
   profile_begin(st, kStagePrep);
-  int rc = euclid ? launch_prepare_queries_euclid(q, nq, s->dim, s->gmax_bits, qn, qb, eps, keys, ct0, nf0, st)
+  int rc = euclid ? launch_prepare_queries_euclid(q, nq, s->dim, s->gmax_bits, qn, qb, qb2, coef, eps, keys, ct0, nf0, st)
                   : launch_normalise_queries(q, nq, s->dim, !(p->flags & FRG_QUERY_PRENORMALISED), qn, qb, keys, ct0,
                                              nf0, st, eps, s->gmax_bits);
   profile_end(st, 1);
   if (rc == FRG_OK)
     rc = launch_tc_match(s, p->metric, qn, qb, eps, nq, k, p->tenant, rescore, p->threshold, p->row_offset, tc_ws,
                          sm_count, tail.active ? tail.x : XPush(), out_rows, out_scores, out_accept, &flagged,
-                         &n_flagged, st, plan_rows, tile_list, n_list);
+                         &n_flagged, st, plan_rows, tile_list, n_list, qb2, coef);
   if (rc == FRG_OK) {
     // queries whose candidate lists overflowed are redone exactly, inside the same enqueue
     ScanArgs a;

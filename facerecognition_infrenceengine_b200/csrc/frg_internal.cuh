@@ -233,9 +233,11 @@ int launch_normalise_queries(const float* q, int nq, int dim, bool normalise, fl
                              cudaStream_t st, float* eps = nullptr, const uint32_t* bounds = nullptr);
 // queries.cu: Euclidean tensor-core prep: qn = q as given, bf16 image [nq][dim + kEuclidQPad] = [q, 1, 1, 1, 0...],
 // eps[f] = filter error bound of query f from ||q|| and the store's max row norm
+// q_aug: the filter's image [q, 1, 1, 1, +A, +B, +C, 0...], q_aug_lo: the pre-pass image (-A, -B, -C); coef[f][4] = the
+// bf16 coefficient values A, B, C of query f (select recomputes a candidate's bound from them); eps[f] = 0
 int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_t* gmax_bits, float* qn,
-                                  __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
-                                  int* n_flagged, cudaStream_t st);
+                                  __nv_bfloat16* q_aug, __nv_bfloat16* q_aug_lo, float* coef, float* eps,
+                                  uint32_t* group_keys, int* cand_total, int* n_flagged, cudaStream_t st);
 
 struct XPush;      // exchange.cu, below
 // scan_f32.cu: exact scan; writes nq x k best (score desc, row asc) into rows32/scores
@@ -330,7 +332,8 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
                     uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st,
-                    int64_t plan_rows, const int32_t* tile_list, int n_list);
+                    int64_t plan_rows, const int32_t* tile_list, int n_list,
+                    const __nv_bfloat16* qb_prepass = nullptr, const float* coef = nullptr);
 
 // first_match.cu
 int launch_first_match(const float* master, const int32_t* tags, int64_t rows, int dim, const float* qn, int nq,

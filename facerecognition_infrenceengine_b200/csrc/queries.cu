@@ -72,6 +72,13 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
   }
 }
 
+__device__ __forceinline__ uint32_t bf16_up_bits(float x) {      // smallest bf16 >= x, x >= 0
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  uint32_t u = __bfloat16_as_ushort(b);
+  if (__bfloat162float(b) < x) ++u;
+  return u;
+}
+
 // Euclidean tensor-core prep (BASELINE config 3; ours, not in the reference).  The query is used as
 // given; its bf16 image gets kEuclidQPad more columns [1, 1, 1, 0 ...] that pick up the three bias terms of
 // the Euclidean scan plane, so that the tensor-core score is S = q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2:
@@ -80,7 +87,8 @@ normalise_queries_kernel(const float* __restrict__ q, int nq, int dim, int norma
 //   fp32 bias / accumulation          O(dim * 2^-24) (||q|| ||g|| + ||g||^2 / 2)
 __global__ void __launch_bounds__(128)
 prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, const uint32_t* __restrict__ gmax_bits,
-                              float* __restrict__ qn, __nv_bfloat16* __restrict__ q_aug, float* __restrict__ eps,
+                              float* __restrict__ qn, __nv_bfloat16* __restrict__ q_aug,
+                              __nv_bfloat16* __restrict__ q_aug_lo, float* __restrict__ coef, float* __restrict__ eps,
                               uint32_t* __restrict__ group_keys, uint32_t none_key, int* __restrict__ cand_total,
                               int* __restrict__ n_flagged) {
   pdl_wait();
@@ -105,6 +113,7 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
     p.x = *reinterpret_cast<uint32_t*>(&lo);
     p.y = *reinterpret_cast<uint32_t*>(&hi);
     reinterpret_cast<uint2*>(q_aug + size_t(w) * aug)[v] = p;
+    reinterpret_cast<uint2*>(q_aug_lo + size_t(w) * aug)[v] = p;
     const float2 l = __bfloat1622float2(lo), h = __bfloat1622float2(hi);
     const float a = x.x - l.x, b = x.y - l.y, c = x.z - h.x, d = x.w - h.y;
     rq = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, rq))));
@@ -114,24 +123,42 @@ prepare_queries_euclid_kernel(const float* __restrict__ q, int nq, int dim, cons
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
     rq += __shfl_xor_sync(0xffffffffu, rq, o);
   }
+  // |S - s| <= ||q^|| ||g^ - g|| + ||q^ - q|| ||g|| + fp32 accumulation  =  A R_g + B N_g + C SS_g   per ROW, with
+  //   A = 1.01 (1 + 2^-8) ||q||,  B = 1.01 ||q - bf16(q)|| + 1e-4 ||q||,  C = 1e-4
+  // (R_g, N_g, SS_g: the row's bound columns, store_kernels.cu; the bias columns carry -0.5*||g||^2 exactly).  The
+  // coefficients, rounded UP to bf16, sit behind the three ones of the image: +A, +B, +C in the filter's image (the
+  // tensor core returns an UPPER bound of the exact score), -A, -B, -C in the pre-pass image (a LOWER bound: its
+  // k-th best is a floor of the true k-th best).  No eps arithmetic is left for the epilogue: eps[w] = 0.
+  (void)gmax_bits;
+  const float nq_ = __fsqrt_ru(ss);
+  const uint32_t a = bf16_up_bits(1.01f * 1.00390625f * nq_);
+  const uint32_t b = bf16_up_bits(1.01f * __fsqrt_ru(rq) + 1e-4f * nq_);
+  const uint32_t c = bf16_up_bits(1e-4f);
   if (lane < kEuclidQPad / 4) {
-    // bf16(1.0) = 0x3F80
-    const uint2 ones = lane == 0 ? make_uint2(0x3F803F80u, 0x00003F80u) : make_uint2(0u, 0u);
-    reinterpret_cast<uint2*>(q_aug + size_t(w) * aug + dim)[lane] = ones;
+    // bf16(1.0) = 0x3F80; sign bit 0x8000
+    uint2 hi_img = make_uint2(0u, 0u), lo_img = make_uint2(0u, 0u);
+    if (lane == 0) {
+      hi_img = make_uint2(0x3F803F80u, 0x00003F80u | (a << 16));
+      lo_img = make_uint2(0x3F803F80u, 0x00003F80u | ((a | 0x8000u) << 16));
+    } else if (lane == 1) {
+      hi_img = make_uint2(b | (c << 16), 0u);
+      lo_img = make_uint2((b | 0x8000u) | ((c | 0x8000u) << 16), 0u);
+    }
+    reinterpret_cast<uint2*>(q_aug + size_t(w) * aug + dim)[lane] = hi_img;
+    reinterpret_cast<uint2*>(q_aug_lo + size_t(w) * aug + dim)[lane] = lo_img;
   }
   if (lane == 0) {
-    // |S - s| <= ||q^|| ||g^ - g|| + ||q^ - q|| ||g||  (the bias columns carry -0.5*||g||^2 exactly), residuals
-    // measured: the row side at ingest (gmax_bits[1]), the query side above; fp32 accumulation term scaled by the
-    // magnitudes it sums (||q|| ||g|| and the bias)
-    const float g2 = __uint_as_float(gmax_bits[0]), rg = __uint_as_float(gmax_bits[1]);
-    const float nq_ = __fsqrt_rn(ss), ng = __fsqrt_rn(g2);
-    eps[w] = 1.01f * (1.00390625f * nq_ * __fsqrt_rn(rg) + __fsqrt_rn(rq) * ng) + 1e-4f * (nq_ * ng + g2);
+    eps[w] = 0.f;
+    coef[size_t(w) * 4 + 0] = __uint_as_float(a << 16);        // the bf16 values the tensor core multiplies with
+    coef[size_t(w) * 4 + 1] = __uint_as_float(b << 16);
+    coef[size_t(w) * 4 + 2] = __uint_as_float(c << 16);
+    coef[size_t(w) * 4 + 3] = 0.f;
   }
 }
 
 int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_t* gmax_bits, float* qn,
-                                  __nv_bfloat16* q_aug, float* eps, uint32_t* group_keys, int* cand_total,
-                                  int* n_flagged, cudaStream_t st) {
+                                  __nv_bfloat16* q_aug, __nv_bfloat16* q_aug_lo, float* coef, float* eps,
+                                  uint32_t* group_keys, int* cand_total, int* n_flagged, cudaStream_t st) {
   if (nq <= 0) return FRG_OK;
   FRG_CUDA(func_attr_once(prepare_queries_euclid_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   // group maxima start from "nothing seen" = the ordered key of -3e38 (Euclidean scores are unbounded below)
@@ -140,7 +167,7 @@ int launch_prepare_queries_euclid(const float* q, int nq, int dim, const uint32_
   memcpy(&none_bits, &none, sizeof(none_bits));
   const uint32_t none_key = ~none_bits;        // float_key() of a negative value: all bits complemented
   FRG_CUDA(launch_kernel(prepare_queries_euclid_kernel, dim3((nq + 3) / 4), dim3(128), 0, st, true, q, nq, dim, gmax_bits,
-                         qn, q_aug, eps, group_keys, none_key, cand_total, n_flagged));
+                         qn, q_aug, q_aug_lo, coef, eps, group_keys, none_key, cand_total, n_flagged));
   note_launch(nullptr);
   FRG_CUDA(cudaGetLastError());
   return FRG_OK;

@@ -28,9 +28,10 @@ __device__ __forceinline__ float store_bf16x4(__nv_bfloat16* dst, float4 v) {
 // ||q^ - q|| ||g|| (q^, g^ the bf16 images).  bounds[1] keeps the largest ||g^ - g||^2 of any row ever stored
 // (non-negative floats order like their bit patterns); the query side is measured per query (queries.cu).
 // A NaN row (zero vector) is left out: it can never match either way.
-__device__ __forceinline__ void fold_residual(uint32_t* bounds, float rr, int lane) {
+__device__ __forceinline__ float fold_residual(uint32_t* bounds, float rr, int lane) {
   rr = warp_sum(rr);
   if (bounds && lane == 0 && rr < INFINITY) atomicMax(bounds + 1, __float_as_uint(rr));
+  return rr;                // the row's ||g - bf16(g)||^2, on every lane
 }
 
 // Euclidean scan plane (raw stores): columns dim .. dim+15 of the row = [hi, mid, lo, 0 ...], the exact
@@ -38,7 +39,18 @@ __device__ __forceinline__ void fold_residual(uint32_t* bounds, float rr, int la
 // product with a query image [q, 1, 1, 1, 0 ...] accumulates q.g - 0.5*||g||^2.  The largest ||g||^2
 // ever stored is folded into gmax_bits[0] (non-negative floats order like their bit patterns); it scales
 // the filter's error bound.  Non-finite norms are left out: such rows can never match either way.
-__device__ __forceinline__ void store_bias_columns(__nv_bfloat16* row_aug, float ss, uint32_t* gmax_bits, int lane) {
+// Columns 3..5 carry THIS ROW's share of the filter's error bound, each rounded UP to bf16: R = ||g - bf16(g)||,
+// N = ||g||, SS = ||g||^2.  The query image holds the matching coefficients (queries.cu), so the tensor core
+// itself adds (filter) or subtracts (pre-pass) the bound: scores come out as upper / lower bounds of the exact
+// score, per row - one row of huge norm no longer loosens the bound of every other row.
+__device__ __forceinline__ uint32_t bf16_up(float x) {          // smallest bf16 >= x, for x >= 0 (bits)
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  uint32_t u = __bfloat16_as_ushort(b);
+  if (__bfloat162float(b) < x) ++u;                              // next bf16 up (x >= 0: bit patterns are ordered)
+  return u;
+}
+__device__ __forceinline__ void store_bias_columns(__nv_bfloat16* row_aug, float ss, float rr, uint32_t* gmax_bits,
+                                                   int lane) {
   if (lane < kEuclidPad / 4) {
     uint2 packed = make_uint2(0u, 0u);
     if (lane == 0) {
@@ -49,8 +61,10 @@ __device__ __forceinline__ void store_bias_columns(__nv_bfloat16* row_aug, float
       const float r2 = r1 - __bfloat162float(mid);
       const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
       packed.x = uint32_t(__bfloat16_as_ushort(hi)) | (uint32_t(__bfloat16_as_ushort(mid)) << 16);
-      packed.y = uint32_t(__bfloat16_as_ushort(lo));
+      packed.y = uint32_t(__bfloat16_as_ushort(lo)) | (bf16_up(__fsqrt_ru(rr)) << 16);
       if (gmax_bits && ss < INFINITY) atomicMax(gmax_bits, __float_as_uint(ss));
+    } else if (lane == 1) {
+      packed.x = bf16_up(__fsqrt_ru(ss)) | (bf16_up(ss) << 16);
     }
     reinterpret_cast<uint2*>(row_aug)[lane] = packed;
   }
@@ -94,8 +108,8 @@ ingest_kernel(const float* __restrict__ vecs, const int64_t* __restrict__ rows,
       if (m) m[v] = x;
       if (plane) rr += store_bf16x4(plane + dst * plane_dim + v * 4, x);
     }
-    if (plane) fold_residual(gmax_bits, rr, lane);
-    if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), gmax_bits, lane);
+    if (plane) rr = fold_residual(gmax_bits, rr, lane);
+    if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), rr, gmax_bits, lane);
     if (lane == 0) tag_out[dst] = tags ? tags[i] : 0;
   }
 }
@@ -209,8 +223,8 @@ synth_kernel(int64_t n, int64_t append_at, int64_t global_row0, uint32_t k0, uin
         ss_stored = fmaf(hi.z, hi.z, ss_stored); ss_stored = fmaf(hi.w, hi.w, ss_stored);
       }
     }
-    if (plane) fold_residual(gmax_bits, rr, lane);
-    if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), gmax_bits, lane);
+    if (plane) rr = fold_residual(gmax_bits, rr, lane);
+    if (plane && plane_dim > dim) store_bias_columns(plane + dst * plane_dim + dim, warp_sum(ss_stored), rr, gmax_bits, lane);
     if (lane == 0) tag_out[dst] = tag;
   }
 }

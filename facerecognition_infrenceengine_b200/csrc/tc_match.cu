@@ -717,7 +717,8 @@ template <int K, bool EUCLID>
 __global__ void __launch_bounds__(kSelectWarps * 32)
 select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ cand_total,
                       int dense_cap, int nq, int k, int dim, const float* __restrict__ qn,
-                      const float* __restrict__ eps,
+                      const float* __restrict__ eps, const __nv_bfloat16* __restrict__ plane, int plane_dim,
+                      const float* __restrict__ coef,
                       const float* __restrict__ master, int rescore, float threshold, int64_t row_offset,
                       int64_t* __restrict__ out_rows, float* __restrict__ out_scores,
                       uint8_t* __restrict__ out_accept, int* __restrict__ flagged, int* __restrict__ n_flagged,
@@ -745,6 +746,19 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
   const int2* mine = dense + size_t(q) * dense_cap;
   if (threadIdx.x == 0) s_m = 0;
 
+  // EUCLID: an entry's coarse score is an UPPER bound U of the row's exact score (the filter's query image adds the
+  // row's own error bound, queries.cu); tau must be a floor of the true k-th best, so entries are ranked by their
+  // LOWER bounds L = U - 2 err, err recomputed from the row's bound columns (the same bf16 numbers the tensor core
+  // multiplied) - and every entry with U >= tau survives.  Cosine: ranked by the score itself, margin 2 eps below.
+  const float ca = EUCLID ? coef[size_t(q) * 4] : 0.f, cb = EUCLID ? coef[size_t(q) * 4 + 1] : 0.f,
+              cc = EUCLID ? coef[size_t(q) * 4 + 2] : 0.f;
+  auto rank_key = [&](const int2& e) {
+    const float u_ = __int_as_float(e.y);
+    if (!EUCLID) return u_;
+    const __nv_bfloat16* pr = plane + size_t(e.x) * plane_dim + dim + 3;
+    const float err = fmaf(ca, __bfloat162float(pr[0]), fmaf(cb, __bfloat162float(pr[1]), cc * __bfloat162float(pr[2])));
+    return u_ - 2.0001f * err;
+  };
   // (a) this warp's k best coarse scores: lane-local top-K over its slices, then k rounds of warp arg-max
   float sc[K];
   int32_t ix[K];
@@ -759,7 +773,7 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (c0 + u * kSelectWarps * 32 < n) lane_insert<K>(sc, ix, __int_as_float(e[u].y), e[u].x);
+      if (c0 + u * kSelectWarps * 32 < n) lane_insert<K>(sc, ix, rank_key(e[u]), e[u].x);
   }
   for (int j = 0; j < k; ++j) {
     float bs; int32_t br;
@@ -801,7 +815,7 @@ select_rescore_kernel(const int2* __restrict__ dense, const int* __restrict__ ca
 
   // (b) compact the rows that can still be in the true top-k (their order is irrelevant: the final
   //     order below is total)
-  const float keep_thr = tau - 2.0f * (eps ? __ldg(eps + q) : kCoarseEps);
+  const float keep_thr = EUCLID ? tau : tau - 2.0f * (eps ? __ldg(eps + q) : kCoarseEps);
   for (int c0 = w * 32; c0 < n; c0 += 4 * kSelectWarps * 32) {     // 4 independent loads per lane per round
     int2 e[4];
 #pragma unroll
@@ -980,8 +994,10 @@ bool tc_uses_pairs(int nq);
 
 static int reg_k(int k) { return k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16)); }
 
+// dim < 0: Euclidean plane (|dim| columns).  Its probe and filter phases need DIFFERENT query images (lower / upper
+// bounds of the exact score), so the pre-pass is never folded into the filter kernel there.
 static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* pl) {
-  (void)dim;
+  const bool euclid_plane = dim < 0;
   pl->qtiles = (nq + kTileQ - 1) / kTileQ;
   pl->pair = tc_uses_pairs(nq);
   if (pl->pair) pl->qtiles = (pl->qtiles + 1) & ~1;      // clusters of 2 along x; a padding tile holds no query
@@ -990,7 +1006,7 @@ static void tc_plan(int64_t rows, int dim, int nq, int k, int sm_count, TcPlan* 
   // wins for a handful of queries (F = 1: 198 vs 208 us) and loses from F = 64 on (F = 1024: 814 vs
   // 735 us).  FRG_TC_FUSED=0/1 forces either path.
   static const int fused_env = []() { const char* e = getenv("FRG_TC_FUSED"); return e ? atoi(e) : -1; }();
-  pl->fused = fused_env >= 0 ? fused_env != 0 : nq <= 8;
+  pl->fused = !euclid_plane && (fused_env >= 0 ? fused_env != 0 : nq <= 8);
   const int tile_rows = pl->pair ? 2 * kTileR : kTileR;
   // pre-pass sample: every stride-th 128-row tile, stride the largest power of two <= 64 that still
   // leaves >= 16 K sampled rows
@@ -1138,8 +1154,10 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
                     int nq, int k, int32_t tenant, bool rescore, float threshold, int64_t row_offset,
                     unsigned char* ws, int sm_count, const XPush& push, int64_t* out_rows, float* out_scores,
                     uint8_t* out_accept, int** flagged_out, int** n_flagged_out, cudaStream_t st,
-                    int64_t plan_rows, const int32_t* tile_list, int n_list) {
+                    int64_t plan_rows, const int32_t* tile_list, int n_list, const __nv_bfloat16* qb_prepass,
+                    const float* coef) {
   const bool euclid = metric == FRG_METRIC_EUCLIDEAN;
+  if (euclid && (!qb_prepass || !coef)) { set_error("tc_match: the Euclidean filter needs both query images"); return FRG_ERR_INVALID; }
   if (euclid != (s->plane_dim != s->dim)) { set_error("tc_match: metric does not fit the store's scan plane"); return FRG_ERR_UNSUPPORTED; }
   // columns of the query tile: dim, or dim + kEuclidQPad (its last k-block meets the plane's 16-column pad block)
   const int kdim = euclid ? s->dim + kEuclidQPad : s->dim;
@@ -1147,7 +1165,7 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
   // (tile_list: a tenant-filtered call whose window is mostly other tenants' rows walks only the tiles that hold
   // rows of the tenant; everything is planned for plan_rows = listed tiles x rows per tile)
   TcPlan pl;
-  tc_plan(plan_rows, s->dim, nq, k, sm_count, &pl);
+  tc_plan(plan_rows, euclid ? -s->dim : s->dim, nq, k, sm_count, &pl);
   uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int2* cand = reinterpret_cast<int2*>(ws + pl.off_cand);
@@ -1158,8 +1176,10 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
   *n_flagged_out = n_flagged;
   const bool masked = tenant >= 0 || s->maybe_dead;
 
-  CUtensorMap qm, gm_full, pm;
+  CUtensorMap qm, qm_pre, gm_full, pm;
   FRG_CHECK(make_map(&qm, qb, kdim, nq, size_t(kdim) * 2, kTileQ));
+  if (euclid) FRG_CHECK(make_map(&qm_pre, qb_prepass, kdim, nq, size_t(kdim) * 2, kTileQ));   // lower-bound image
+  else qm_pre = qm;
   FRG_CHECK(make_map(&gm_full, s->plane, s->dim, s->rows, pitch, kTileR));   // box = one CTA's half
   if (euclid) FRG_CHECK(make_map(&pm, s->plane + s->dim, kEuclidPad, s->rows, pitch, kTileR, kEuclidPad));
   else pm = gm_full;                                                          // never dereferenced (p.pad == 0)
@@ -1191,7 +1211,7 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
     // 1. pre-pass over the sampled tiles
     p.tile_scale = pl.stride;
     profile_begin(st, kStagePrepass);
-    FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm, gm_full, pm, p, pl.qtiles, pl.chunks_pre, st));
+    FRG_CHECK(launch_tc_scan_m<kModeGroupMax>(masked, pl.pair, qm_pre, gm_full, pm, p, pl.qtiles, pl.chunks_pre, st));
     profile_end(st, 1);
     // 2. filter over the whole plane
     p.tile_scale = 1;
@@ -1207,7 +1227,8 @@ int launch_tc_match(const GalleryWindow* s, int metric, const float* qn, const _
 #define FRG_SELECT_M(KK, EU)                                                                                    \
   FRG_CUDA(func_attr_once(select_rescore_kernel<KK, EU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
   FRG_CUDA(launch_kernel(select_rescore_kernel<KK, EU>, dim3(grid), dim3(kSelectWarps * 32), 0, st, true, dense, \
-      cnt, pl.stage_entries, nq, k, s->dim, qn, eps, s->master, rs, threshold, row_offset, out_rows, out_scores,   \
+      cnt, pl.stage_entries, nq, k, s->dim, qn, eps, s->plane, s->plane_dim, coef, s->master, rs, threshold,     \
+      row_offset, out_rows, out_scores,                                                                             \
       out_accept, flagged, n_flagged, push))
 #define FRG_SELECT(KK)                                                                                          \
   if (euclid) { FRG_SELECT_M(KK, true); } else { FRG_SELECT_M(KK, false); }

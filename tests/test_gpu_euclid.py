@@ -162,22 +162,37 @@ def test_overwrite_in_place_and_compaction_keep_the_norm_terms(frg):
     store.close()
 
 
-def test_one_outlier_row_of_huge_norm_overflows_every_query(frg):
-    """The filter's bound uses the LARGEST row norm of the store: one row 30x longer than the rest makes
-    every row a candidate of every query, every private segment overflows (the poisoned totals must not
-    wrap), and all queries are redone by the exact scan on the device - slow, still right."""
+def test_one_outlier_row_of_huge_norm_does_not_loosen_the_other_rows_bound(frg):
+    """The filter's bound is per ROW (r2): every row carries its own rounding residual, norm and squared norm in the
+    plane's pad columns, the query image the matching coefficients, so the tensor core itself returns upper (filter)
+    and lower (pre-pass) bounds of the exact score.  One row 30x longer than the rest used to loosen a store-wide
+    bound until every row was a candidate of every query and all of them fell back to the exact scan; now it
+    only widens its own interval: results right, bit-identical to the exact scan, and the fallback stays idle."""
+    from facerecognition_infrenceengine_b200 import _native as N
     rng = np.random.default_rng(14)
     n, d = 40_000, 128
     G = (rng.standard_normal((n, d)) * 0.1).astype(np.float32)
     G[31_000] = (rng.standard_normal(d) * 3.0).astype(np.float32)
+    G[100] = (rng.standard_normal(d) * 20.0).astype(np.float32)
     store = frg.GalleryStore(dim=d, capacity=n, raw=True)
     store.append_rows(G)
-    Q = np.concatenate([G[[31_000, 4, 39_999]] + np.float32(0.01),
+    Q = np.concatenate([G[[31_000, 4, 39_999, 100]] + np.float32(0.01),
                         (rng.standard_normal((150, d)) * 0.1).astype(np.float32)])
     for k in (1, 5):
         r = check(frg, store, Q, G, k, 0.6)
         same_as_scan(frg, store, Q, k, 0.6)
-    assert list(r.rows[:3, 0]) == [31_000, 4, 39_999]
+    assert list(r.rows[:4, 0]) == [31_000, 4, 39_999, 100]
+    # the exact fallback had nothing to redo: its launch stays at the idle few microseconds
+    m = frg.Matcher(store, metric="euclidean")
+    m.match(Q, 5, 0.6, variant="tc_exact")
+    N.profile_enable(True)
+    N.profile_collect()
+    for _ in range(5):
+        m.match(Q, 5, 0.6, variant="tc_exact")
+    N.profile_collect()
+    st = N.profile_stages()
+    N.profile_enable(False)
+    assert st["fallback"] / 5 < 0.05, st            # ms per match (a redo of 154 queries takes ~0.5 ms here)
     store.close()
 
 
