@@ -60,8 +60,9 @@ extern "C" {
 #define FRG_STORE_BF16_PLANE  1u /* keep the bf16 scan plane next to the fp32 master (needed by TC variants) */
 #define FRG_STORE_RAW         2u /* never normalise on ingest (Euclidean galleries, cluster means).  Together with
                                    FRG_STORE_BF16_PLANE the plane is the EUCLIDEAN scan plane: each row carries
-                                   -0.5*||g||^2 in 16 more bf16 columns, so that the tensor-core product with
-                                   [q, 1, 1, 1, 0..] is q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2 */
+                                   -0.5*||g||^2 (and its own error-bound terms) in 16 more bf16 columns, so that the
+                                   tensor-core product with [q, 1, 1, 1, +-A, +-B, +-C, 0..] is an upper / lower bound
+                                   of q.g - 0.5*||g||^2 = (||q||^2 - d^2) / 2 */
 #define FRG_STORE_BF16_ONLY   4u /* keep ONLY the bf16 scan plane (1 KB / 512-d row instead of 3 KB): "bf16 gallery
                                    mode".  Matches run as FRG_VARIANT_TC_BF16 (scores within the measured bound, ~3.6e-3 of fp32 for ordinary data);
                                    the exact variants, first_match and the Euclidean metric are not available. */
