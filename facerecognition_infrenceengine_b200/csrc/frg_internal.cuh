@@ -151,8 +151,9 @@ struct frg_store {
   float* master = nullptr;            // [capacity][dim] fp32, unit rows
   __nv_bfloat16* plane = nullptr;     // [capacity][plane_dim] bf16 image (scan plane) or null
   // plane_dim == dim for unit-row stores.  A FRG_STORE_RAW store's plane is the EUCLIDEAN scan plane:
-  // plane_dim = dim + kEuclidPad (16), columns dim..dim+2 hold -0.5*||g||^2 split exactly into three bf16
-  // terms (the rest 0), so that Qaug . Gaug = q.g - 0.5*||g||^2 with Qaug = [q, 1, 1, 1, 0...] (tc_match.cu)
+  // plane_dim = dim + kEuclidPad (16): columns dim..dim+2 hold -0.5*||g||^2 split exactly into three bf16 terms,
+  // columns dim+3..dim+5 the row's error-bound terms ||g - bf16(g)||, ||g||, ||g||^2 rounded up (the rest 0), so that
+  // Qaug . Gaug = q.g - 0.5*||g||^2 +- bound with Qaug = [q, 1, 1, 1, +-A, +-B, +-C, 0...] (queries.cu, tc_match.cu)
   int plane_dim = 0;
   uint32_t* gmax_bits = nullptr;      // device uint32[2], float bits: [0] max ||g||^2 ever ingested (raw stores with a
                                       // Euclidean plane), [1] max ||g - bf16(g)||^2 (any store with a plane)
