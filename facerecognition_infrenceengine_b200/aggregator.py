@@ -23,6 +23,9 @@ class BatchAggregator:
 
     A batch is flushed when `max_batch` faces are waiting or the oldest request is `max_delay_ms` old.
     Requests with different company_id are batched separately (the tenant filter is per call).
+    Rows are positions in the gallery: if the store may be compacted while requests are in flight, let `match_fn`
+    translate rows to ids itself (``Matcher.match(..., with_ids=True)`` does so inside the store's read section) or
+    carry ``MatchResult.layout_version`` along (``store.ids_of(rows, layout_version=...)``).
     `workers` batches are in flight at once, each on its own host thread (= its own CUDA stream inside
     frg_match_host): with two, the copies and launch latency of one batch hide behind the kernels of the
     other (bench `e2e.concurrent`: +10 % at 1024 queries per batch, +30 % at 64)."""
